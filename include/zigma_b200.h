@@ -1,0 +1,219 @@
+/*
+ * zigma_b200 -- C-ABI of the B200 (sm_100a) kernels for the ZigMa denoiser hot path.
+ *
+ * This header is the drop-in boundary.  Every entry point replaces one native interface of the
+ * reference (CompVis/zigma, paths relative to /root/reference):
+ *
+ *   zg_selective_scan_fwd   <- selective_scan_cuda.fwd   dis_mamba/csrc/selective_scan/selective_scan.cpp:226-336
+ *   zg_selective_scan_bwd   <- selective_scan_cuda.bwd   dis_mamba/csrc/selective_scan/selective_scan.cpp:338-492
+ *   zg_causal_conv1d_fwd    <- causal_conv1d_cuda.causal_conv1d_fwd   dis_causal_conv1d/csrc/causal_conv1d.cpp:130-189
+ *   zg_causal_conv1d_bwd    <- causal_conv1d_cuda.causal_conv1d_bwd   dis_causal_conv1d/csrc/causal_conv1d.cpp:191-268
+ *   zg_add_norm_fwd         <- Triton _layer_norm_fwd_1pass_kernel    dis_mamba/mamba_ssm/ops/triton/layernorm.py:64-177
+ *   zg_add_norm_bwd         <- Triton _layer_norm_bwd_kernel          dis_mamba/mamba_ssm/ops/triton/layernorm.py:195-377
+ *   zg_block_tail_fwd       <- the unfused elementwise tail of Block.forward + next block's fused add+norm
+ *                              model_zigma.py:416-445 (gate * mixer + x, residual add, RMSNorm, modulate)
+ *                              and backward_permutation  mamba_simple.py:59-61,388-394
+ *   zg_gemm_bf16_tn         <- the cuBLAS calls behind in_proj / x_proj / dt_proj / out_proj
+ *                              mamba_simple.py:290-294, selective_scan_interface.py:322-323,365
+ *
+ * Conventions
+ *   - plain pointers and sizes only; all pointers are DEVICE pointers unless stated otherwise;
+ *   - the caller allocates every output (the reference allocates inside the op with the caller's
+ *     allocator, selective_scan.cpp:304-313 -- here Python/torch allocates, the kernels fill);
+ *   - strides are in ELEMENTS;
+ *   - all launches are asynchronous on `stream` (a cudaStream_t passed as void*); no allocation,
+ *     no synchronisation inside -> CUDA-graph capturable;
+ *   - return value 0 = success; non-zero = error, message via zg_last_error() (thread local).
+ *     The Python wrapper turns that into RuntimeError like TORCH_CHECK does in the reference.
+ */
+#ifndef ZIGMA_B200_H
+#define ZIGMA_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum { ZG_F32 = 0, ZG_F16 = 1, ZG_BF16 = 2 };
+
+/* flags for zg_scan_params.flags */
+enum {
+    ZG_SCAN_DELTA_SOFTPLUS = 1,  /* delta' = softplus(delta + bias), identity above 20 */
+    ZG_SCAN_VARIABLE_B = 2,      /* B is (batch, groups, dstate, seqlen) in act dtype; else (dim, dstate) fp32 */
+    ZG_SCAN_VARIABLE_C = 4
+};
+
+int zg_abi_version(void);
+const char *zg_last_error(void);
+/* number of kernels launched through this library since load (bench `gpu_launches` evidence) */
+uint64_t zg_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Selective scan (S6).  Logical shapes: u, delta, z, out (batch, dim, seqlen); any of the two
+ * layouts is accepted through the strides, but ONE of {seq stride, dim stride} must be 1 for all
+ * four tensors alike:
+ *     seq-contiguous ("channel first", the reference layout, selective_scan.cpp:252-253)  *_sl == 1
+ *     dim-contiguous ("token major", what the fused model path uses)                      *_sd == 1
+ * B/C variable: (batch, groups, dstate, seqlen) with the SAME contiguity class (seq stride 1 for
+ * seq-contiguous activations, dstate stride 1 for dim-contiguous activations).
+ * A (dim, dstate) fp32 contiguous, real only (complex64 A of the reference is not supported: ZigMa
+ * never uses it).  D, delta_bias (dim) fp32 or NULL.  z NULL -> out = y, else out = y * silu(z).
+ * z_rowmap (int32[seqlen], NULL = identity): step l reads z at sequence position z_rowmap[l]
+ *   (fuses forward_permutation of the z half, mamba_simple.py:55-56,365-370; dim-contiguous only).
+ * last_state (batch, dim, dstate) fp32 or NULL.
+ * ckpt (batch, dim, n_ckpt, dstate) fp32 or NULL: state after every ckpt_every steps
+ *   (n_ckpt = ceil(seqlen / ckpt_every); ckpt_every must be a multiple of 16) -- the recompute
+ *   seeds of the backward pass; plays the role of the reference's `x` (selective_scan.cpp:313).
+ * dstate <= 64.
+ */
+typedef struct {
+    const void *u, *delta, *z, *B, *C;
+    const float *A, *D, *delta_bias;
+    const int32_t *z_rowmap;
+    void *out;
+    float *last_state, *ckpt;
+    int64_t u_sb, u_sd, u_sl;
+    int64_t delta_sb, delta_sd, delta_sl;
+    int64_t z_sb, z_sd, z_sl;
+    int64_t out_sb, out_sd, out_sl;
+    int64_t B_sb, B_sg, B_sn, B_sl;
+    int64_t C_sb, C_sg, C_sn, C_sl;
+    int32_t batch, dim, seqlen, dstate, ngroups;
+    int32_t dtype, flags, ckpt_every;
+} zg_scan_params;
+
+int zg_selective_scan_fwd(const zg_scan_params *p, void *stream);
+
+/* Backward of the above.  Extra inputs: dout (like out), ckpt from the forward.  Outputs: du,
+ * ddelta (like u), dz (like z, NULL if no z), dA (dim, dstate), dD, ddelta_bias (dim) fp32
+ * ACCUMULATED with atomics -> caller zero-fills (reference: selective_scan.cpp:460-466),
+ * dB, dC (batch, groups, dstate, seqlen) fp32 accumulated likewise.  seq-contiguous layout only.
+ */
+typedef struct {
+    zg_scan_params fwd;
+    const void *dout;
+    int64_t dout_sb, dout_sd, dout_sl;
+    void *du, *ddelta, *dz;
+    int64_t du_sb, du_sd, du_sl;
+    int64_t ddelta_sb, ddelta_sd, ddelta_sl;
+    int64_t dz_sb, dz_sd, dz_sl;
+    float *dA, *dD, *ddelta_bias, *dB, *dC;
+} zg_scan_bwd_params;
+
+int zg_selective_scan_bwd(const zg_scan_bwd_params *p, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Depthwise causal conv1d (+bias, +SiLU).  x, out logical (batch, dim, seqlen), either layout (the
+ * reference's channel-first and channel-last kernels, causal_conv1d_fwd.cu:39-158,193-330).
+ * weight (dim, width) and bias (dim) in weight dtype `wdtype`; 2 <= width <= 4 (causal_conv1d.cpp:157).
+ * x_rowmap (int32[seqlen] or NULL; dim-contiguous only): output position l convolves the input
+ *   positions x_rowmap[l-w], i.e. the conv runs over the PERMUTED sequence without materialising
+ *   it (fuses forward_permutation of the x half, mamba_simple.py:365-370).
+ */
+typedef struct {
+    const void *x, *weight, *bias;
+    const int32_t *x_rowmap;
+    void *out;
+    int64_t x_sb, x_sd, x_sl;
+    int64_t out_sb, out_sd, out_sl;
+    int32_t batch, dim, seqlen, width;
+    int32_t dtype, wdtype, silu;
+} zg_conv_params;
+
+int zg_causal_conv1d_fwd(const zg_conv_params *p, void *stream);
+
+/* Backward: dx (like x, written), dweight (dim, width) / dbias (dim) fp32 accumulated with atomics
+ * (caller zero-fills; reference causal_conv1d.cpp:247-249, causal_conv1d_bwd.cu:225-239). */
+typedef struct {
+    zg_conv_params fwd;
+    const void *dout;
+    int64_t dout_sb, dout_sd, dout_sl;
+    void *dx;
+    int64_t dx_sb, dx_sd, dx_sl;
+    float *dweight, *dbias;
+} zg_conv_bwd_params;
+
+int zg_causal_conv1d_bwd(const zg_conv_bwd_params *p, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Fused residual-add + RMSNorm / LayerNorm over rows of length ncols (rows contiguous in the last
+ * dim, row strides in elements).   r = x (+ residual) in fp32;  residual_out = r  (dtype
+ * res_dtype, NULL to skip);  y = norm(r) * weight (+ bias)  in dtype `dtype`;  rstd (and mean for
+ * LayerNorm) saved when non-NULL.  weight/bias have dtype wdtype (NULL weight = 1).
+ */
+typedef struct {
+    const void *x, *residual, *weight, *bias;
+    void *y, *residual_out;
+    float *mean, *rstd;
+    int64_t x_rs, res_rs, y_rs, resout_rs;
+    int32_t nrows, ncols;
+    int32_t dtype, res_dtype, wdtype, is_rms;
+    float eps;
+} zg_norm_params;
+
+int zg_add_norm_fwd(const zg_norm_params *p, void *stream);
+
+typedef struct {
+    const void *dy, *dresidual;   /* dresidual: grad wrt residual_out (res dtype) or NULL */
+    const void *x;                /* the saved residual_out = r (res dtype)               */
+    const void *weight;
+    const float *mean, *rstd;
+    void *dx, *dresidual_in;      /* dx in dtype; dresidual_in (res dtype) or NULL        */
+    float *dweight, *dbias;       /* (ncols) fp32 accumulated with atomics, caller zero-fills */
+    int64_t dy_rs, dres_rs, x_rs, dx_rs, dresin_rs;
+    int32_t nrows, ncols;
+    int32_t dtype, res_dtype, wdtype, is_rms;
+} zg_norm_bwd_params;
+
+int zg_add_norm_bwd(const zg_norm_bwd_params *p, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Block tail (inference fast path), token-major (batch, seqlen, dim) contiguous tensors:
+ *     hidden   = x + gate[b,:] * mix[b, rowmap[l], :]          (rowmap = perm_rev or NULL)
+ *     r        = residual + hidden              (fp32, written to residual_out)
+ *     normed   = r * rsqrt(mean(r^2) + eps) * norm_w            (dtype; the next block's x)
+ *     modded   = normed * (1 + scale[b,:]) + shift[b,:]         (dtype; the next in_proj input)
+ * gate/shift/scale are (batch, dim) with row stride mod_rs (views into adaLN's (batch, 3*dim)).
+ * With final != 0 the last two lines become the model tail (model_zigma.py:971-984,335):
+ *     normed = LayerNorm_noaffine(normed, eps=1e-6) and modded is not written.
+ * Intermediate roundings replicate the reference's unfused bf16 path: hidden and normed are
+ * rounded to `dtype` where the reference materialises them.
+ */
+typedef struct {
+    const void *x, *mix, *gate, *shift, *scale, *norm_w;
+    const float *residual;
+    const int32_t *rowmap;
+    float *residual_out;
+    void *normed, *modded;
+    int64_t mod_rs;
+    int32_t batch, seqlen, dim;
+    int32_t dtype, final_layer;
+    float eps;
+} zg_block_tail_params;
+
+int zg_block_tail_fwd(const zg_block_tail_params *p, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * bf16 GEMM on tcgen05 tensor cores:  C[M,N] = A[M,K] * B[N,K]^T (+ bias[N]), fp32 accumulate in
+ * TMEM, bf16 output.  A, B row-major with leading dims lda/ldb (elements, multiples of 8);
+ * C row-major ldc.  out_rowmap (int32[rows_per_batch] or NULL): output row m of batch
+ * m / rows_per_batch is stored at row out_rowmap[m % rows_per_batch] of that batch (scatter of
+ * the out_proj result back to raster order, mamba_simple.py:388-394).
+ * Requires K % 64 == 0.  The CUtensorMaps are built on the host per call and passed to the
+ * kernel by value (__grid_constant__), so nothing has to outlive the call.
+ */
+typedef struct {
+    const void *A, *B, *bias;
+    void *C;
+    const int32_t *out_rowmap;
+    int64_t lda, ldb, ldc;
+    int32_t M, N, K, rows_per_batch;
+} zg_gemm_params;
+
+int zg_gemm_bf16_tn(const zg_gemm_params *p, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ZIGMA_B200_H */

@@ -1,0 +1,94 @@
+"""CPU: host-side logic of the product package that needs no kernel -- module construction and
+state-dict parity with the reference, scan tables per layer, the sampler driver, the sharding used
+by bench.py (world_size-2 gloo)."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import synth, zigma_oracle as zo
+from util import ROOT, model_case
+
+CASES = ["tiny_zigzag8", "tiny_sweep2", "tiny_hilbert2", "tiny_patch2_cls", "tiny_video_sst", "full_zigzag8_b1"]
+
+
+def build(cfg, device="cpu", dtype=torch.float32):
+    from zigma_b200 import ZigMa
+    return ZigMa(device=device, dtype=dtype, **cfg).eval()
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_state_dict_layout_matches_reference(name):
+    g, cfg, shapes = model_case(name)
+    m = build(cfg)
+    mine = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+    assert mine == shapes
+    m.load_state_dict(synth.synth_state_dict(shapes), strict=True)
+
+
+def test_layer_tables_follow_reference_rules():
+    g, cfg, _ = model_case("tiny_zigzag8")
+    m = build(cfg)
+    fwd, rev, _ = zo.build_scan_tables(cfg["scan_type"], cfg["depth"], (cfg["img_dim"] // cfg["patch_size"]) ** 2)
+    for i, blk in enumerate(m.blocks):
+        assert np.array_equal(blk.mixer.zigzag_paths[i].numpy(), fwd[i])
+        assert np.array_equal(blk.mixer.zigzag_paths_reverse[i].numpy(), rev[i])
+    g, cfg, _ = model_case("tiny_video_sst")
+    m = build(cfg)
+    fwd, rev, st = zo.build_scan_tables(cfg["scan_type"], cfg["depth"], (cfg["img_dim"] // cfg["patch_size"]) ** 2, cfg["video_frames"])
+    for i, blk in enumerate(m.blocks):
+        assert blk.mixer.st_order[i] == st[i]
+        assert np.array_equal(blk.mixer.zigzag_paths[i].numpy(), fwd[i])
+        assert np.array_equal(blk.mixer.zigzag_paths_reverse[i].numpy(), rev[i])
+
+
+def test_reference_constructor_init_properties():
+    """Init rules of the reference constructor (model_zigma.py:840-872, mamba_simple.py:128-162)."""
+    from zigma_b200 import ZigMa
+    torch.manual_seed(0)
+    m = ZigMa(in_channels=4, embed_dim=32, depth=2, img_dim=8, scan_type="zigzagN8", use_pe=1, device="cpu")
+    for blk in m.blocks:
+        assert torch.count_nonzero(blk.adaLN_modulation[1].weight) == 0 and torch.count_nonzero(blk.adaLN_modulation[1].bias) == 0
+        A = torch.exp(blk.mixer.A_log)
+        assert torch.allclose(A, torch.arange(1, 17, dtype=torch.float32).repeat(64, 1), rtol=1e-5)
+        dt = torch.nn.functional.softplus(blk.mixer.dt_proj.bias)
+        assert dt.min() >= 1e-4 * 0.99 and dt.max() <= 0.1 * 1.01
+    assert m.pos_embed.abs().sum() > 0 and not m.pos_embed.requires_grad
+
+
+def test_sampler_euler_matches_oracle_and_reference_grid():
+    from zigma_b200 import create_transport, Sampler
+    tr = create_transport("Linear", "velocity", None, None, None)
+    fn = Sampler(tr).sample_ode(sampling_method="euler", num_steps=50)
+    W = torch.randn(6, 6) * 0.3
+    model = lambda x, t, **kw: torch.tanh(x @ W) * (1 + t.view(-1, 1))
+    x0 = torch.randn(4, 6)
+    out = fn(x0, model)
+    assert len(out) == 50                     # one state per grid point, like odeint
+    ref = zo.sample_ode_fixed(model, x0, num_steps=50)
+    assert torch.allclose(out[-1], ref, rtol=1e-5, atol=1e-6)
+    calls = []
+    fn(x0, lambda x, t, **kw: (calls.append(float(t[0])), x)[1])
+    assert len(calls) == 49 and abs(calls[1] - 1 / 49) < 1e-6   # 49 evaluations on linspace(0, 1, 50)
+
+
+def test_training_loss_shapes():
+    from zigma_b200 import create_transport
+    tr = create_transport()
+    out = tr.training_losses(lambda x, t: x * 0, torch.randn(5, 4, 8, 8))
+    assert out["loss"].shape == (5,)
+
+
+def test_shard_sampling_world2_gloo():
+    """bench.py's multi-GPU contract on CPU: 2 gloo ranks shard the batch, no collective inside the
+    steps, one all_gather of the latents at the end, identical to the unsharded run."""
+    script = os.path.join(ROOT, "tests", "_dist_worker.py")
+    env = dict(os.environ, PYTHONPATH=ROOT)
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29531", script],
+                       env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "DIST_OK" in r.stdout

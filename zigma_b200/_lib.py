@@ -1,0 +1,128 @@
+"""ctypes binding of the C-ABI in include/zigma_b200.h (libzigma_b200.so, sm_100a).
+
+There is NO fallback: if the shared library is missing or a call fails, a RuntimeError is raised
+(the reference raises RuntimeError from TORCH_CHECK the same way, selective_scan.cpp:226-336).
+"""
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libzigma_b200.so")
+
+ZG_F32, ZG_F16, ZG_BF16 = 0, 1, 2
+SCAN_DELTA_SOFTPLUS, SCAN_VARIABLE_B, SCAN_VARIABLE_C = 1, 2, 4
+_DT = {torch.float32: ZG_F32, torch.float16: ZG_F16, torch.bfloat16: ZG_BF16}
+
+vp, i64, i32, f32 = C.c_void_p, C.c_int64, C.c_int32, C.c_float
+
+
+class ScanParams(C.Structure):
+    _fields_ = ([(n, vp) for n in ("u", "delta", "z", "B", "C", "A", "D", "delta_bias", "z_rowmap", "out", "last_state", "ckpt")]
+                + [(n, i64) for n in ("u_sb", "u_sd", "u_sl", "delta_sb", "delta_sd", "delta_sl", "z_sb", "z_sd", "z_sl",
+                                      "out_sb", "out_sd", "out_sl", "B_sb", "B_sg", "B_sn", "B_sl", "C_sb", "C_sg", "C_sn", "C_sl")]
+                + [(n, i32) for n in ("batch", "dim", "seqlen", "dstate", "ngroups", "dtype", "flags", "ckpt_every")])
+
+
+class ScanBwdParams(C.Structure):
+    _fields_ = ([("fwd", ScanParams), ("dout", vp)]
+                + [(n, i64) for n in ("dout_sb", "dout_sd", "dout_sl")]
+                + [(n, vp) for n in ("du", "ddelta", "dz")]
+                + [(n, i64) for n in ("du_sb", "du_sd", "du_sl", "ddelta_sb", "ddelta_sd", "ddelta_sl", "dz_sb", "dz_sd", "dz_sl")]
+                + [(n, vp) for n in ("dA", "dD", "ddelta_bias", "dB", "dC")])
+
+
+class ConvParams(C.Structure):
+    _fields_ = ([(n, vp) for n in ("x", "weight", "bias", "x_rowmap", "out")]
+                + [(n, i64) for n in ("x_sb", "x_sd", "x_sl", "out_sb", "out_sd", "out_sl")]
+                + [(n, i32) for n in ("batch", "dim", "seqlen", "width", "dtype", "wdtype", "silu")])
+
+
+class ConvBwdParams(C.Structure):
+    _fields_ = ([("fwd", ConvParams), ("dout", vp)]
+                + [(n, i64) for n in ("dout_sb", "dout_sd", "dout_sl")]
+                + [("dx", vp)]
+                + [(n, i64) for n in ("dx_sb", "dx_sd", "dx_sl")]
+                + [(n, vp) for n in ("dweight", "dbias")])
+
+
+class NormParams(C.Structure):
+    _fields_ = ([(n, vp) for n in ("x", "residual", "weight", "bias", "y", "residual_out", "mean", "rstd")]
+                + [(n, i64) for n in ("x_rs", "res_rs", "y_rs", "resout_rs")]
+                + [(n, i32) for n in ("nrows", "ncols", "dtype", "res_dtype", "wdtype", "is_rms")]
+                + [("eps", f32)])
+
+
+class NormBwdParams(C.Structure):
+    _fields_ = ([(n, vp) for n in ("dy", "dresidual", "x", "weight", "mean", "rstd", "dx", "dresidual_in", "dweight", "dbias")]
+                + [(n, i64) for n in ("dy_rs", "dres_rs", "x_rs", "dx_rs", "dresin_rs")]
+                + [(n, i32) for n in ("nrows", "ncols", "dtype", "res_dtype", "wdtype", "is_rms")])
+
+
+class BlockTailParams(C.Structure):
+    _fields_ = ([(n, vp) for n in ("x", "mix", "gate", "shift", "scale", "norm_w", "residual", "rowmap", "residual_out", "normed", "modded")]
+                + [("mod_rs", i64)]
+                + [(n, i32) for n in ("batch", "seqlen", "dim", "dtype", "final_layer")]
+                + [("eps", f32)])
+
+
+class GemmParams(C.Structure):
+    _fields_ = ([(n, vp) for n in ("A", "B", "bias", "C", "out_rowmap")]
+                + [(n, i64) for n in ("lda", "ldb", "ldc")]
+                + [(n, i32) for n in ("M", "N", "K", "rows_per_batch")])
+
+
+EXPORTS = ["zg_abi_version", "zg_last_error", "zg_launch_count", "zg_selective_scan_fwd", "zg_selective_scan_bwd",
+           "zg_causal_conv1d_fwd", "zg_causal_conv1d_bwd", "zg_add_norm_fwd", "zg_add_norm_bwd",
+           "zg_block_tail_fwd", "zg_gemm_bf16_tn"]
+
+_lib = None
+
+
+def lib():
+    """Loads libzigma_b200.so (built by ``__graft_entry__.build()`` / ``zigma_b200/csrc/build.sh``)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"zigma_b200: native library {LIB_PATH} not found -- build it with "
+                f"`python -c 'import __graft_entry__ as g; g.build()'` (nvcc, sm_100a). There is no CPU/PyTorch fallback.")
+        l = C.CDLL(LIB_PATH)
+        l.zg_last_error.restype = C.c_char_p
+        l.zg_launch_count.restype = C.c_uint64
+        for name in EXPORTS[3:]:
+            getattr(l, name).restype = C.c_int
+            getattr(l, name).argtypes = [C.c_void_p, C.c_void_p]
+        _lib = l
+    return _lib
+
+
+def launch_count():
+    return int(lib().zg_launch_count())
+
+
+def call(name, params):
+    """Invokes an entry point on torch's current CUDA stream; raises RuntimeError on failure."""
+    l = lib()
+    stream = torch.cuda.current_stream().cuda_stream
+    rc = getattr(l, name)(C.byref(params), C.c_void_p(stream))
+    if rc != 0:
+        raise RuntimeError(f"{name}: {l.zg_last_error().decode()}")
+
+
+def dt(t):
+    try:
+        return _DT[t.dtype if isinstance(t, torch.Tensor) else t]
+    except KeyError:
+        raise RuntimeError(f"zigma_b200: unsupported dtype {t.dtype if isinstance(t, torch.Tensor) else t}")
+
+
+def ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def require_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("zigma_b200: expected CUDA tensors (the kernels are sm_100a only; there is no CPU path)")

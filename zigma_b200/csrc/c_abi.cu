@@ -1,0 +1,78 @@
+// C-ABI entry points (include/zigma_b200.h): argument validation, dispatch, error string.
+#include "zg_common.cuh"
+#include "scan_fwd.cuh"
+#include <atomic>
+#include <string.h>
+
+static thread_local char g_err[512] = "";
+static std::atomic<uint64_t> g_launches{0};
+
+int zg_set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return 1;
+}
+void zg_count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
+int zg_check_launch(const char *what) {
+    cudaError_t err = cudaPeekAtLastError();
+    if (err != cudaSuccess) {
+        cudaGetLastError();
+        return zg_set_error("%s: kernel launch failed: %s", what, cudaGetErrorString(err));
+    }
+    return 0;
+}
+
+extern "C" {
+
+int zg_abi_version(void) { return 1; }
+const char *zg_last_error(void) { return g_err; }
+uint64_t zg_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int zg_selective_scan_fwd(const zg_scan_params *pp, void *stream) {
+    ZG_REQUIRE(pp != nullptr, "selective_scan_fwd: null params");
+    const zg_scan_params &p = *pp;
+    ZG_REQUIRE(p.dtype == ZG_F32 || p.dtype == ZG_F16 || p.dtype == ZG_BF16, "selective_scan_fwd: bad dtype %d", p.dtype);
+    ZG_REQUIRE(p.batch >= 0 && p.dim > 0 && p.seqlen >= 0, "selective_scan_fwd: bad shape (%d, %d, %d)", p.batch, p.dim, p.seqlen);
+    ZG_REQUIRE(p.dstate >= 1 && p.dstate <= 64, "selective_scan_fwd: dstate must be in [1, 64], got %d", p.dstate);
+    ZG_REQUIRE(p.ngroups >= 1 && p.dim % p.ngroups == 0, "selective_scan_fwd: dim %d not divisible by groups %d", p.dim, p.ngroups);
+    ZG_REQUIRE(p.u && p.delta && p.A && p.B && p.C && p.out, "selective_scan_fwd: null tensor pointer");
+    const bool seq = p.u_sl == 1 && p.delta_sl == 1 && p.out_sl == 1 && (!p.z || p.z_sl == 1);
+    const bool dimc = p.u_sd == 1 && p.delta_sd == 1 && p.out_sd == 1 && (!p.z || p.z_sd == 1);
+    ZG_REQUIRE(seq || dimc, "selective_scan_fwd: u, delta, z, out must all have seq stride 1 or all have dim stride 1");
+    // (seqlen == 1 or dim == 1 tensors satisfy both; prefer the reference layout)
+    const bool use_seq = seq;
+    const bool varB = p.flags & ZG_SCAN_VARIABLE_B, varC = p.flags & ZG_SCAN_VARIABLE_C;
+    if (use_seq) {
+        ZG_REQUIRE(!varB || p.B_sl == 1 || p.seqlen == 1, "selective_scan_fwd: B must have seq stride 1 for seq-contiguous activations");
+        ZG_REQUIRE(!varC || p.C_sl == 1 || p.seqlen == 1, "selective_scan_fwd: C must have seq stride 1 for seq-contiguous activations");
+        ZG_REQUIRE(p.z_rowmap == nullptr, "selective_scan_fwd: z_rowmap needs the dim-contiguous layout");
+    } else {
+        ZG_REQUIRE(!varB || p.B_sn == 1 || p.dstate == 1, "selective_scan_fwd: B must have dstate stride 1 for dim-contiguous activations");
+        ZG_REQUIRE(!varC || p.C_sn == 1 || p.dstate == 1, "selective_scan_fwd: C must have dstate stride 1 for dim-contiguous activations");
+    }
+    ZG_REQUIRE(!p.ckpt || (p.ckpt_every > 0 && p.ckpt_every % zg::SCAN_TL == 0), "selective_scan_fwd: ckpt_every must be a positive multiple of %d", zg::SCAN_TL);
+    if (p.batch == 0 || p.seqlen == 0) return 0;
+    const bool constbc = !(varB && varC);
+    cudaStream_t s = (cudaStream_t)stream;
+    switch (p.dtype) {
+        case ZG_F32: return zg::scan_fwd_f32(p, use_seq, constbc, s);
+        case ZG_F16: return zg::scan_fwd_f16(p, use_seq, constbc, s);
+        default: return zg::scan_fwd_bf16(p, use_seq, constbc, s);
+    }
+}
+
+}  // extern "C"
+
+// ---- entry points implemented in later files fall back to a loud error until they exist -------------
+#ifndef ZG_HAVE_SCAN_BWD
+extern "C" int zg_selective_scan_bwd(const zg_scan_bwd_params *, void *) {
+    return zg_set_error("selective_scan_bwd: not built into this library");
+}
+#endif
+#ifndef ZG_HAVE_GEMM
+extern "C" int zg_gemm_bf16_tn(const zg_gemm_params *, void *) {
+    return zg_set_error("gemm_bf16_tn: not built into this library");
+}
+#endif

@@ -1,0 +1,272 @@
+// Depthwise causal conv1d (+bias, +SiLU) forward / backward for sm_100a.
+//
+// Replaces causal_conv1d_fwd_kernel / causal_conv1d_channellast_fwd_kernel and their backward
+// (dis_causal_conv1d/csrc/causal_conv1d_fwd.cu:39-158,193-330, causal_conv1d_bwd.cu:46-505).
+// HBM-bound elementwise work: one 16-byte vector per thread per step, fully coalesced, fp32 math.
+//   dim-contiguous ("channel last", token major): a thread owns VEC adjacent channels and slides
+//     down LCH consecutive tokens with the W-1 previous inputs in registers; optional x_rowmap
+//     gathers the input ROWS through the zigzag permutation (whole 2E*2-byte rows are contiguous,
+//     so the gather is free: it only changes which row address is loaded).
+//   seq-contiguous ("channel first", reference layout): a thread owns VEC consecutive positions of
+//     one (batch, channel) row and reads the preceding vector for the halo.
+#include "zg_common.cuh"
+
+namespace zg {
+
+constexpr int CONV_LCH = 32;   // tokens per thread, dim-contiguous kernels
+
+template <typename T, int VEC> struct VecT;  // VEC elements of T
+template <typename T> struct VecT<T, 1> { T e[1]; };
+template <> struct alignas(16) VecT<float, 4> { float e[4]; };
+template <> struct alignas(16) VecT<__half, 8> { __half e[8]; };
+template <> struct alignas(16) VecT<__nv_bfloat16, 8> { __nv_bfloat16 e[8]; };
+
+template <typename T, int VEC>
+__device__ __forceinline__ void load_vec(float (&dst)[VEC], const T *src) {
+    VecT<T, VEC> v = *reinterpret_cast<const VecT<T, VEC> *>(src);
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) dst[i] = zg_to_float<T>(v.e[i]);
+}
+template <typename T, int VEC>
+__device__ __forceinline__ void store_vec(T *dst, const float (&src)[VEC]) {
+    VecT<T, VEC> v;
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) v.e[i] = zg_from_float<T>(src[i]);
+    *reinterpret_cast<VecT<T, VEC> *>(dst) = v;
+}
+
+template <typename W> __device__ __forceinline__ float load_w(const void *p, int64_t i) {
+    return zg_to_float<W>(reinterpret_cast<const W *>(p)[i]);
+}
+__device__ __forceinline__ float load_w_dt(const void *p, int64_t i, int wdtype) {
+    if (wdtype == ZG_F32) return load_w<float>(p, i);
+    if (wdtype == ZG_F16) return load_w<__half>(p, i);
+    return load_w<__nv_bfloat16>(p, i);
+}
+
+// ------------------------------------------------------------------------------------------------
+// forward, dim-contiguous
+template <typename T, int VEC>
+__global__ void __launch_bounds__(128) conv_fwd_dimc_kernel(const zg_conv_params p) {
+    const int E = p.dim, L = p.seqlen, W = p.width;
+    const int nvec = (E + VEC - 1) / VEC;
+    const int nchunk = (L + CONV_LCH - 1) / CONV_LCH;
+    const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= (int64_t)p.batch * nchunk * nvec) return;
+    const int v = (int)(gid % nvec);
+    const int ch = (int)((gid / nvec) % nchunk);
+    const int b = (int)(gid / ((int64_t)nvec * nchunk));
+    const int e0 = v * VEC;
+    const int l0 = ch * CONV_LCH;
+    const T *x = reinterpret_cast<const T *>(p.x) + (int64_t)b * p.x_sb + e0;
+    T *out = reinterpret_cast<T *>(p.out) + (int64_t)b * p.out_sb + e0;
+
+    float w[4][VEC], bias[VEC];
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+        const bool ok = e0 + i < E;
+        bias[i] = (p.bias && ok) ? load_w_dt(p.bias, e0 + i, p.wdtype) : 0.f;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)   // w[k] multiplies x[l - k]  (weight index W-1-k)
+            w[k][i] = (ok && k < W) ? load_w_dt(p.weight, (int64_t)(e0 + i) * W + (W - 1 - k), p.wdtype) : 0.f;
+    }
+    auto load_row = [&](int l, float (&dst)[VEC]) {
+        if (l < 0 || l >= L) {
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) dst[i] = 0.f;
+            return;
+        }
+        const int64_t row = p.x_rowmap ? p.x_rowmap[l] : l;
+        load_vec<T, VEC>(dst, x + row * p.x_sl);
+    };
+    float x1[VEC], x2[VEC], x3[VEC], x0[VEC];   // x[l-1], x[l-2], x[l-3], x[l]
+    load_row(l0 - 1, x1);
+    load_row(l0 - 2, x2);
+    load_row(l0 - 3, x3);
+    const int lend = min(l0 + CONV_LCH, L);
+#pragma unroll 4
+    for (int l = l0; l < lend; ++l) {
+        load_row(l, x0);
+        float o[VEC];
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) {
+            float acc = bias[i];
+            acc = fmaf(w[3][i], x3[i], acc);
+            acc = fmaf(w[2][i], x2[i], acc);
+            acc = fmaf(w[1][i], x1[i], acc);
+            acc = fmaf(w[0][i], x0[i], acc);
+            o[i] = p.silu ? zg_silu(acc) : acc;
+            x3[i] = x2[i]; x2[i] = x1[i]; x1[i] = x0[i];
+        }
+        store_vec<T, VEC>(out + (int64_t)l * p.out_sl, o);
+    }
+}
+
+// forward, seq-contiguous
+template <typename T, int VEC>
+__global__ void __launch_bounds__(128) conv_fwd_seqc_kernel(const zg_conv_params p) {
+    const int E = p.dim, L = p.seqlen, W = p.width;
+    const int nvec = (L + VEC - 1) / VEC;
+    const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= (int64_t)p.batch * E * nvec) return;
+    const int v = (int)(gid % nvec);
+    const int e = (int)((gid / nvec) % E);
+    const int b = (int)(gid / ((int64_t)nvec * E));
+    const int l0 = v * VEC;
+    const T *x = reinterpret_cast<const T *>(p.x) + (int64_t)b * p.x_sb + (int64_t)e * p.x_sd;
+    T *out = reinterpret_cast<T *>(p.out) + (int64_t)b * p.out_sb + (int64_t)e * p.out_sd;
+    float w[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) w[k] = k < W ? load_w_dt(p.weight, (int64_t)e * W + (W - 1 - k), p.wdtype) : 0.f;
+    const float bias = p.bias ? load_w_dt(p.bias, e, p.wdtype) : 0.f;
+    float win[VEC + 3];   // win[3 + i] = x[l0 + i]
+    if (VEC > 1) {
+        float cur[VEC], prev[VEC];
+        load_vec<T, VEC>(cur, x + l0);
+        if (l0 > 0) load_vec<T, VEC>(prev, x + l0 - VEC);
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) win[3 + i] = cur[i];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) win[i] = (l0 > 0) ? prev[VEC - 3 + i] : 0.f;
+    } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) win[i] = (l0 - 3 + i >= 0) ? zg_to_float<T>(x[l0 - 3 + i]) : 0.f;
+    }
+    float o[VEC];
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+        float acc = bias;
+        acc = fmaf(w[3], win[i], acc);
+        acc = fmaf(w[2], win[i + 1], acc);
+        acc = fmaf(w[1], win[i + 2], acc);
+        acc = fmaf(w[0], win[i + 3], acc);
+        o[i] = p.silu ? zg_silu(acc) : acc;
+    }
+    store_vec<T, VEC>(out + l0, o);
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward, seq-contiguous (the autograd path of causal_conv1d_fn; causal_conv1d_bwd.cu:46-240).
+// One warp per (batch, channel) row: lanes stride over l, dx written, dweight/dbias reduced in the
+// warp and accumulated with one fp32 atomicAdd per (row, tap).
+//   g[l]   = dout[l] * (silu ? silu'(pre[l]) : 1),  pre[l] = bias + sum_k w[k] x[l-k]
+//   dx[l]  = sum_k w[k] g[l+k]          dw[k] = sum_l g[l] x[l-k]        db = sum_l g[l]
+template <typename T>
+__global__ void __launch_bounds__(128) conv_bwd_seqc_kernel(const zg_conv_bwd_params q) {
+    const zg_conv_params &p = q.fwd;
+    const int E = p.dim, L = p.seqlen, W = p.width;
+    const int warp = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    const int lane = threadIdx.x & 31;
+    if (warp >= p.batch * E) return;
+    const int b = warp / E, e = warp % E;
+    const T *x = reinterpret_cast<const T *>(p.x) + (int64_t)b * p.x_sb + (int64_t)e * p.x_sd;
+    const T *dout = reinterpret_cast<const T *>(q.dout) + (int64_t)b * q.dout_sb + (int64_t)e * q.dout_sd;
+    T *dx = reinterpret_cast<T *>(q.dx) + (int64_t)b * q.dx_sb + (int64_t)e * q.dx_sd;
+    float w[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) w[k] = k < W ? load_w_dt(p.weight, (int64_t)e * W + (W - 1 - k), p.wdtype) : 0.f;
+    const float bias = p.bias ? load_w_dt(p.bias, e, p.wdtype) : 0.f;
+    auto X = [&](int l) { return (l >= 0 && l < L) ? zg_to_float<T>(x[l]) : 0.f; };
+    auto G = [&](int l) {   // gradient wrt the pre-activation at position l
+        if (l < 0 || l >= L) return 0.f;
+        float g = zg_to_float<T>(dout[l]);
+        if (p.silu) {
+            const float pre = bias + w[0] * X(l) + w[1] * X(l - 1) + w[2] * X(l - 2) + w[3] * X(l - 3);
+            const float s = 1.f / (1.f + __expf(-pre));
+            g *= s * (1.f + pre * (1.f - s));
+        }
+        return g;
+    };
+    float dw[4] = {0.f, 0.f, 0.f, 0.f}, db = 0.f;
+    for (int l = lane; l < L; l += 32) {
+        const float g0 = G(l), g1 = G(l + 1), g2 = G(l + 2), g3 = G(l + 3);
+        dx[l] = zg_from_float<T>(w[0] * g0 + w[1] * g1 + w[2] * g2 + w[3] * g3);
+        db += g0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) dw[k] += g0 * X(l - k);
+    }
+    db = zg_warp_sum(db);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) dw[k] = zg_warp_sum(dw[k]);
+    if (lane == 0) {
+        if (q.dbias) atomicAdd(q.dbias + e, db);
+        for (int k = 0; k < W; ++k) atomicAdd(q.dweight + (int64_t)e * W + (W - 1 - k), dw[k]);
+    }
+}
+
+template <typename T> static int conv_fwd_t(const zg_conv_params &p, bool seq, cudaStream_t s) {
+    constexpr int VEC = 16 / sizeof(T);
+    const uintptr_t align_bits = reinterpret_cast<uintptr_t>(p.x) | reinterpret_cast<uintptr_t>(p.out);
+    if (seq) {
+        const bool vec_ok = (p.seqlen % VEC == 0) && (align_bits % 16 == 0) && (p.x_sb % VEC == 0) && (p.x_sd % VEC == 0) &&
+                            (p.out_sb % VEC == 0) && (p.out_sd % VEC == 0) && (p.seqlen >= VEC);
+        if (vec_ok) {
+            const int64_t n = (int64_t)p.batch * p.dim * (p.seqlen / VEC);
+            conv_fwd_seqc_kernel<T, VEC><<<(unsigned)((n + 127) / 128), 128, 0, s>>>(p);
+        } else {
+            const int64_t n = (int64_t)p.batch * p.dim * p.seqlen;
+            conv_fwd_seqc_kernel<T, 1><<<(unsigned)((n + 127) / 128), 128, 0, s>>>(p);
+        }
+    } else {
+        const bool vec_ok = (p.dim % VEC == 0) && (align_bits % 16 == 0) && (p.x_sb % VEC == 0) && (p.x_sl % VEC == 0) &&
+                            (p.out_sb % VEC == 0) && (p.out_sl % VEC == 0);
+        const int nchunk = (p.seqlen + CONV_LCH - 1) / CONV_LCH;
+        if (vec_ok) {
+            const int64_t n = (int64_t)p.batch * nchunk * (p.dim / VEC);
+            conv_fwd_dimc_kernel<T, VEC><<<(unsigned)((n + 127) / 128), 128, 0, s>>>(p);
+        } else {
+            const int64_t n = (int64_t)p.batch * nchunk * p.dim;
+            conv_fwd_dimc_kernel<T, 1><<<(unsigned)((n + 127) / 128), 128, 0, s>>>(p);
+        }
+    }
+    zg_count_launch();
+    return zg_check_launch("causal_conv1d_fwd");
+}
+
+}  // namespace zg
+
+static int conv_validate(const zg_conv_params &p, const char *who) {
+    ZG_REQUIRE(p.dtype == ZG_F32 || p.dtype == ZG_F16 || p.dtype == ZG_BF16, "%s: bad dtype %d", who, p.dtype);
+    ZG_REQUIRE(p.wdtype == ZG_F32 || p.wdtype == ZG_F16 || p.wdtype == ZG_BF16, "%s: bad weight dtype %d", who, p.wdtype);
+    ZG_REQUIRE(p.width >= 2 && p.width <= 4, "%s only supports width between 2 and 4, got %d", who, p.width);
+    ZG_REQUIRE(p.batch >= 0 && p.dim > 0 && p.seqlen >= 0, "%s: bad shape (%d, %d, %d)", who, p.batch, p.dim, p.seqlen);
+    ZG_REQUIRE(p.x && p.weight && p.out, "%s: null tensor pointer", who);
+    ZG_REQUIRE((p.x_sl == 1 && p.out_sl == 1) || (p.x_sd == 1 && p.out_sd == 1),
+               "%s: x and out must both be seq-contiguous or both dim-contiguous", who);
+    return 0;
+}
+
+extern "C" int zg_causal_conv1d_fwd(const zg_conv_params *pp, void *stream) {
+    ZG_REQUIRE(pp != nullptr, "causal_conv1d_fwd: null params");
+    const zg_conv_params &p = *pp;
+    if (int rc = conv_validate(p, "causal_conv1d_fwd")) return rc;
+    const bool seq = (p.x_sl == 1 && p.out_sl == 1);
+    ZG_REQUIRE(!(seq && p.x_rowmap), "causal_conv1d_fwd: x_rowmap needs the dim-contiguous layout");
+    if (p.batch == 0 || p.seqlen == 0) return 0;
+    cudaStream_t s = (cudaStream_t)stream;
+    switch (p.dtype) {
+        case ZG_F32: return zg::conv_fwd_t<float>(p, seq, s);
+        case ZG_F16: return zg::conv_fwd_t<__half>(p, seq, s);
+        default: return zg::conv_fwd_t<__nv_bfloat16>(p, seq, s);
+    }
+}
+
+extern "C" int zg_causal_conv1d_bwd(const zg_conv_bwd_params *qq, void *stream) {
+    ZG_REQUIRE(qq != nullptr, "causal_conv1d_bwd: null params");
+    const zg_conv_bwd_params &q = *qq;
+    if (int rc = conv_validate(q.fwd, "causal_conv1d_bwd")) return rc;
+    ZG_REQUIRE(q.fwd.x_sl == 1 && q.dout_sl == 1 && q.dx_sl == 1, "causal_conv1d_bwd: seq-contiguous tensors required");
+    ZG_REQUIRE(q.dout && q.dx && q.dweight, "causal_conv1d_bwd: null tensor pointer");
+    ZG_REQUIRE(q.fwd.x_rowmap == nullptr, "causal_conv1d_bwd: x_rowmap not supported");
+    if (q.fwd.batch == 0 || q.fwd.seqlen == 0) return 0;
+    cudaStream_t s = (cudaStream_t)stream;
+    const int64_t nthreads = (int64_t)q.fwd.batch * q.fwd.dim * 32;
+    const unsigned grid = (unsigned)((nthreads + 127) / 128);
+    switch (q.fwd.dtype) {
+        case ZG_F32: zg::conv_bwd_seqc_kernel<float><<<grid, 128, 0, s>>>(q); break;
+        case ZG_F16: zg::conv_bwd_seqc_kernel<__half><<<grid, 128, 0, s>>>(q); break;
+        default: zg::conv_bwd_seqc_kernel<__nv_bfloat16><<<grid, 128, 0, s>>>(q); break;
+    }
+    zg_count_launch();
+    return zg_check_launch("causal_conv1d_bwd");
+}

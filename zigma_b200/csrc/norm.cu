@@ -1,0 +1,375 @@
+// Fused residual-add + RMSNorm/LayerNorm (forward, backward) and the fused ZigMa block tail, sm_100a.
+//
+// Replaces the Triton kernels _layer_norm_fwd_1pass_kernel / _layer_norm_bwd_kernel
+// (dis_mamba/mamba_ssm/ops/triton/layernorm.py:64-120,195-290) and, for the inference fast path,
+// the chain of unfused elementwise ops around them in Block.forward (model_zigma.py:416-445).
+// HBM-bound: one warp per token row, 16-byte vector loads, the fp32 row lives in registers between
+// the statistics pass and the normalisation pass (single global read of every operand).
+#include "zg_common.cuh"
+
+namespace zg {
+
+// generic element access by runtime dtype (used for (B, D)-sized modulation vectors and weights)
+__device__ __forceinline__ float ld_dt(const void *p, int64_t i, int dt) {
+    if (dt == ZG_F32) return reinterpret_cast<const float *>(p)[i];
+    if (dt == ZG_F16) return __half2float(reinterpret_cast<const __half *>(p)[i]);
+    return __bfloat162float(reinterpret_cast<const __nv_bfloat16 *>(p)[i]);
+}
+__device__ __forceinline__ void st_dt(void *p, int64_t i, int dt, float v) {
+    if (dt == ZG_F32) reinterpret_cast<float *>(p)[i] = v;
+    else if (dt == ZG_F16) reinterpret_cast<__half *>(p)[i] = __float2half_rn(v);
+    else reinterpret_cast<__nv_bfloat16 *>(p)[i] = __float2bfloat16_rn(v);
+}
+template <typename T> __device__ __forceinline__ float round_to(float v) { return zg_to_float<T>(zg_from_float<T>(v)); }
+
+// 4 consecutive elements starting at i (i % 4 == 0, pointers 16B/8B aligned by contract)
+template <typename T> __device__ __forceinline__ void ld4(const T *p, int64_t i, float (&o)[4]);
+template <> __device__ __forceinline__ void ld4<float>(const float *p, int64_t i, float (&o)[4]) {
+    float4 v = *reinterpret_cast<const float4 *>(p + i);
+    o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
+}
+template <> __device__ __forceinline__ void ld4<__nv_bfloat16>(const __nv_bfloat16 *p, int64_t i, float (&o)[4]) {
+    uint2 v = *reinterpret_cast<const uint2 *>(p + i);
+    o[0] = __uint_as_float(v.x << 16); o[1] = __uint_as_float(v.x & 0xffff0000u);
+    o[2] = __uint_as_float(v.y << 16); o[3] = __uint_as_float(v.y & 0xffff0000u);
+}
+template <> __device__ __forceinline__ void ld4<__half>(const __half *p, int64_t i, float (&o)[4]) {
+    uint2 v = *reinterpret_cast<const uint2 *>(p + i);
+    float2 a = __half22float2(*reinterpret_cast<__half2 *>(&v.x)), b = __half22float2(*reinterpret_cast<__half2 *>(&v.y));
+    o[0] = a.x; o[1] = a.y; o[2] = b.x; o[3] = b.y;
+}
+template <typename T> __device__ __forceinline__ void st4(T *p, int64_t i, const float (&o)[4]);
+template <> __device__ __forceinline__ void st4<float>(float *p, int64_t i, const float (&o)[4]) {
+    *reinterpret_cast<float4 *>(p + i) = make_float4(o[0], o[1], o[2], o[3]);
+}
+template <> __device__ __forceinline__ void st4<__nv_bfloat16>(__nv_bfloat16 *p, int64_t i, const float (&o)[4]) {
+    __nv_bfloat162 a = __floats2bfloat162_rn(o[0], o[1]), b = __floats2bfloat162_rn(o[2], o[3]);
+    uint2 v; v.x = *reinterpret_cast<unsigned *>(&a); v.y = *reinterpret_cast<unsigned *>(&b);
+    *reinterpret_cast<uint2 *>(p + i) = v;
+}
+template <> __device__ __forceinline__ void st4<__half>(__half *p, int64_t i, const float (&o)[4]) {
+    __half2 a = __floats2half2_rn(o[0], o[1]), b = __floats2half2_rn(o[2], o[3]);
+    uint2 v; v.x = *reinterpret_cast<unsigned *>(&a); v.y = *reinterpret_cast<unsigned *>(&b);
+    *reinterpret_cast<uint2 *>(p + i) = v;
+}
+
+constexpr int NORM_MAXQ = 16;   // quads (4 elements) per lane held in registers -> ncols <= 2048
+
+// ------------------------------------------------------------------------------------------------
+// add + norm forward.  T = x/y dtype, R = residual dtype.  Requires ncols % 4 == 0, ncols <= 2048.
+template <typename T, typename R>
+__global__ void __launch_bounds__(128) add_norm_fwd_kernel(const zg_norm_params p) {
+    const int row = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= p.nrows) return;
+    const int N = p.ncols, nq = N >> 2;
+    const T *x = reinterpret_cast<const T *>(p.x) + (int64_t)row * p.x_rs;
+    const R *res = p.residual ? reinterpret_cast<const R *>(p.residual) + (int64_t)row * p.res_rs : nullptr;
+    R *rout = p.residual_out ? reinterpret_cast<R *>(p.residual_out) + (int64_t)row * p.resout_rs : nullptr;
+    T *y = reinterpret_cast<T *>(p.y) + (int64_t)row * p.y_rs;
+    float r[NORM_MAXQ][4];
+    float sum = 0.f, sumsq = 0.f;
+#pragma unroll
+    for (int k = 0; k < NORM_MAXQ; ++k) {
+        const int q = lane + 32 * k;
+        if (q < nq) {
+            ld4<T>(x, 4 * q, r[k]);
+            if (res) {
+                float t[4];
+                ld4<R>(res, 4 * q, t);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) r[k][i] += t[i];
+            }
+            if (rout) {
+                st4<R>(rout, 4 * q, r[k]);
+                // the reference stores residual_out in R and normalises the fp32 value (layernorm.py:96-101)
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { sum += r[k][i]; sumsq += r[k][i] * r[k][i]; }
+        }
+    }
+    float mean = 0.f, var;
+    if (p.is_rms) {
+        var = zg_warp_sum(sumsq) / N;
+    } else {
+        mean = zg_warp_sum(sum) / N;
+        float s2 = 0.f;
+#pragma unroll
+        for (int k = 0; k < NORM_MAXQ; ++k)
+            if (lane + 32 * k < nq)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) { const float d = r[k][i] - mean; s2 += d * d; }
+        var = zg_warp_sum(s2) / N;
+    }
+    const float rstd = 1.f / sqrtf(var + p.eps);
+    if (lane == 0) {
+        if (p.rstd) p.rstd[row] = rstd;
+        if (p.mean && !p.is_rms) p.mean[row] = mean;
+    }
+#pragma unroll
+    for (int k = 0; k < NORM_MAXQ; ++k) {
+        const int q = lane + 32 * k;
+        if (q < nq) {
+            float o[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                float v = (r[k][i] - mean) * rstd;
+                if (p.weight) v *= ld_dt(p.weight, 4 * q + i, p.wdtype);
+                if (p.bias) v += ld_dt(p.bias, 4 * q + i, p.wdtype);
+                o[i] = v;
+            }
+            st4<T>(y, 4 * q, o);
+        }
+    }
+}
+
+// add + norm backward (layernorm.py:195-290).  x = saved residual_out (dtype R), one warp per row;
+// dw/db accumulated per CTA in shared memory then atomically into the fp32 outputs.
+//   xhat = (x - mean) * rstd;  wdy = dy * w;  c1 = mean(xhat * wdy);  c2 = mean(wdy) (0 for RMS)
+//   dx = (wdy - (xhat * c1 + c2)) * rstd (+ dresidual)
+template <typename T, typename R>
+__global__ void __launch_bounds__(128) add_norm_bwd_kernel(const zg_norm_bwd_params p) {
+    // persistent warps: each warp walks rows with a grid stride and keeps its dweight/dbias partial
+    // sums in registers (lane owns columns lane, lane+32, ...), one atomicAdd per column at the end.
+    constexpr int MAXC = 4 * NORM_MAXQ;   // columns per lane
+    const int warp = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    const int nwarps = (int)(((int64_t)gridDim.x * blockDim.x) >> 5);
+    const int lane = threadIdx.x & 31;
+    const int N = p.ncols;
+    float dw[MAXC], db[MAXC];
+#pragma unroll
+    for (int k = 0; k < MAXC; ++k) { dw[k] = 0.f; db[k] = 0.f; }
+    for (int row = warp; row < p.nrows; row += nwarps) {
+        const T *dy = reinterpret_cast<const T *>(p.dy) + (int64_t)row * p.dy_rs;
+        const R *x = reinterpret_cast<const R *>(p.x) + (int64_t)row * p.x_rs;
+        const R *dres = p.dresidual ? reinterpret_cast<const R *>(p.dresidual) + (int64_t)row * p.dres_rs : nullptr;
+        T *dx = reinterpret_cast<T *>(p.dx) + (int64_t)row * p.dx_rs;
+        R *dresin = p.dresidual_in ? reinterpret_cast<R *>(p.dresidual_in) + (int64_t)row * p.dresin_rs : nullptr;
+        const float rstd = p.rstd[row];
+        const float mean = (p.is_rms || !p.mean) ? 0.f : p.mean[row];
+        float c1 = 0.f, c2 = 0.f;
+#pragma unroll
+        for (int k = 0; k < MAXC; ++k) {
+            const int i = lane + 32 * k;
+            if (i < N) {
+                const float xhat = (zg_to_float<R>(x[i]) - mean) * rstd;
+                const float g = zg_to_float<T>(dy[i]);
+                const float wdy = g * (p.weight ? ld_dt(p.weight, i, p.wdtype) : 1.f);
+                c1 += xhat * wdy;
+                c2 += wdy;
+                dw[k] += g * xhat;
+                db[k] += g;
+            }
+        }
+        c1 = zg_warp_sum(c1) / N;
+        c2 = p.is_rms ? 0.f : zg_warp_sum(c2) / N;
+        for (int i = lane; i < N; i += 32) {
+            const float xhat = (zg_to_float<R>(x[i]) - mean) * rstd;
+            const float wdy = zg_to_float<T>(dy[i]) * (p.weight ? ld_dt(p.weight, i, p.wdtype) : 1.f);
+            float d = (wdy - (xhat * c1 + c2)) * rstd;
+            if (dres) d += zg_to_float<R>(dres[i]);
+            if (dresin) dresin[i] = zg_from_float<R>(d);
+            dx[i] = zg_from_float<T>(d);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < MAXC; ++k) {
+        const int i = lane + 32 * k;
+        if (i < N) {
+            if (p.dweight) atomicAdd(p.dweight + i, dw[k]);
+            if (p.dbias) atomicAdd(p.dbias + i, db[k]);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Block tail (see include/zigma_b200.h).  One warp per token; all row operands are read exactly once.
+template <typename T>
+__global__ void __launch_bounds__(128) block_tail_kernel(const zg_block_tail_params p) {
+    const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    const int64_t nrows = (int64_t)p.batch * p.seqlen;
+    if (row >= nrows) return;
+    const int D = p.dim, nq = D >> 2;
+    const int b = (int)(row / p.seqlen), l = (int)(row % p.seqlen);
+    const T *x = reinterpret_cast<const T *>(p.x) + row * D;
+    const T *mix = nullptr;
+    if (p.mix) {
+        const int64_t src = (int64_t)b * p.seqlen + (p.rowmap ? p.rowmap[l] : l);
+        mix = reinterpret_cast<const T *>(p.mix) + src * D;
+    }
+    const T *gate = p.gate ? reinterpret_cast<const T *>(p.gate) + (int64_t)b * p.mod_rs : nullptr;
+    const T *shift = p.shift ? reinterpret_cast<const T *>(p.shift) + (int64_t)b * p.mod_rs : nullptr;
+    const T *scale = p.scale ? reinterpret_cast<const T *>(p.scale) + (int64_t)b * p.mod_rs : nullptr;
+    const T *nw = reinterpret_cast<const T *>(p.norm_w);
+    const float *res = p.residual ? p.residual + row * D : nullptr;
+    float *rout = p.residual_out ? p.residual_out + row * D : nullptr;
+    T *normed = reinterpret_cast<T *>(p.normed) + row * D;
+    T *modded = p.modded ? reinterpret_cast<T *>(p.modded) + row * D : nullptr;
+
+    float r[NORM_MAXQ][4];
+    float sumsq = 0.f;
+#pragma unroll
+    for (int k = 0; k < NORM_MAXQ; ++k) {
+        const int q = lane + 32 * k;
+        if (q < nq) {
+            ld4<T>(x, 4 * q, r[k]);
+            if (mix) {
+                float m[4], g[4];
+                ld4<T>(mix, 4 * q, m);
+                ld4<T>(gate, 4 * q, g);
+#pragma unroll
+                for (int i = 0; i < 4; ++i)   // x + gate * mixer(...)  each op rounded to T as in eager torch
+                    r[k][i] = round_to<T>(r[k][i] + round_to<T>(g[i] * m[i]));
+            }
+            if (res) {
+                float t[4];
+                ld4<float>(res, 4 * q, t);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) r[k][i] += t[i];
+            }
+            if (rout) st4<float>(rout, 4 * q, r[k]);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) sumsq += r[k][i] * r[k][i];
+        }
+    }
+    const float rstd = 1.f / sqrtf(zg_warp_sum(sumsq) / D + p.eps);
+    float sum2 = 0.f;
+#pragma unroll
+    for (int k = 0; k < NORM_MAXQ; ++k) {
+        const int q = lane + 32 * k;
+        if (q < nq) {
+            float w[4];
+            ld4<T>(nw, 4 * q, w);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                r[k][i] = round_to<T>(r[k][i] * rstd * w[i]);   // RMSNorm output as stored by the reference
+                sum2 += r[k][i];
+            }
+        }
+    }
+    if (p.final_layer) {
+        // norm_final = LayerNorm(no affine, eps 1e-6) on the materialised norm_f output (model_zigma.py:320,335)
+        const float mean = zg_warp_sum(sum2) / D;
+        float s2 = 0.f;
+#pragma unroll
+        for (int k = 0; k < NORM_MAXQ; ++k)
+            if (lane + 32 * k < nq)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) { const float d = r[k][i] - mean; s2 += d * d; }
+        const float rstd2 = 1.f / sqrtf(zg_warp_sum(s2) / D + 1e-6f);
+#pragma unroll
+        for (int k = 0; k < NORM_MAXQ; ++k) {
+            const int q = lane + 32 * k;
+            if (q < nq) {
+                float o[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) o[i] = (r[k][i] - mean) * rstd2;
+                st4<T>(normed, 4 * q, o);
+            }
+        }
+        return;
+    }
+#pragma unroll
+    for (int k = 0; k < NORM_MAXQ; ++k) {
+        const int q = lane + 32 * k;
+        if (q < nq) {
+            st4<T>(normed, 4 * q, r[k]);
+            if (modded) {
+                float sc[4], sh[4], o[4];
+                ld4<T>(scale, 4 * q, sc);
+                ld4<T>(shift, 4 * q, sh);
+#pragma unroll
+                for (int i = 0; i < 4; ++i)   // x * (1 + scale) + shift, eager-torch rounding points
+                    o[i] = round_to<T>(r[k][i] * round_to<T>(1.f + sc[i])) + sh[i];
+                st4<T>(modded, 4 * q, o);
+            }
+        }
+    }
+}
+
+template <typename T, typename R> static int norm_fwd_tr(const zg_norm_params &p, cudaStream_t s) {
+    const int64_t nthreads = (int64_t)p.nrows * 32;
+    add_norm_fwd_kernel<T, R><<<(unsigned)((nthreads + 127) / 128), 128, 0, s>>>(p);
+    zg_count_launch();
+    return zg_check_launch("add_norm_fwd");
+}
+template <typename T> static int norm_fwd_t(const zg_norm_params &p, cudaStream_t s) {
+    if (p.res_dtype == ZG_F32) return norm_fwd_tr<T, float>(p, s);
+    if (p.res_dtype == p.dtype) return norm_fwd_tr<T, T>(p, s);
+    return zg_set_error("add_norm_fwd: residual dtype must be fp32 or the activation dtype");
+}
+template <typename T, typename R> static int norm_bwd_tr(const zg_norm_bwd_params &p, cudaStream_t s) {
+    const int64_t want = ((int64_t)p.nrows * 32 + 127) / 128;
+    const unsigned grid = (unsigned)(want < 148 * 4 ? want : 148 * 4);
+    add_norm_bwd_kernel<T, R><<<grid, 128, 0, s>>>(p);
+    zg_count_launch();
+    return zg_check_launch("add_norm_bwd");
+}
+template <typename T> static int norm_bwd_t(const zg_norm_bwd_params &p, cudaStream_t s) {
+    if (p.res_dtype == ZG_F32) return norm_bwd_tr<T, float>(p, s);
+    if (p.res_dtype == p.dtype) return norm_bwd_tr<T, T>(p, s);
+    return zg_set_error("add_norm_bwd: residual dtype must be fp32 or the activation dtype");
+}
+
+}  // namespace zg
+
+static bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+extern "C" int zg_add_norm_fwd(const zg_norm_params *pp, void *stream) {
+    ZG_REQUIRE(pp != nullptr, "add_norm_fwd: null params");
+    const zg_norm_params &p = *pp;
+    ZG_REQUIRE(p.x && p.y, "add_norm_fwd: null tensor pointer");
+    ZG_REQUIRE(p.ncols > 0 && p.ncols % 4 == 0 && p.ncols <= 4 * 32 * zg::NORM_MAXQ,
+               "add_norm_fwd: ncols must be a multiple of 4 and <= %d, got %d", 4 * 32 * zg::NORM_MAXQ, p.ncols);
+    ZG_REQUIRE(p.x_rs % 4 == 0 && p.y_rs % 4 == 0 && p.res_rs % 4 == 0 && p.resout_rs % 4 == 0, "add_norm_fwd: row strides must be multiples of 4");
+    ZG_REQUIRE(aligned16(p.x) && aligned16(p.y) && aligned16(p.residual) && aligned16(p.residual_out), "add_norm_fwd: pointers must be 16-byte aligned");
+    if (p.nrows == 0) return 0;
+    cudaStream_t s = (cudaStream_t)stream;
+    switch (p.dtype) {
+        case ZG_F32: return zg::norm_fwd_t<float>(p, s);
+        case ZG_F16: return zg::norm_fwd_t<__half>(p, s);
+        case ZG_BF16: return zg::norm_fwd_t<__nv_bfloat16>(p, s);
+    }
+    return zg_set_error("add_norm_fwd: bad dtype %d", p.dtype);
+}
+
+extern "C" int zg_add_norm_bwd(const zg_norm_bwd_params *pp, void *stream) {
+    ZG_REQUIRE(pp != nullptr, "add_norm_bwd: null params");
+    const zg_norm_bwd_params &p = *pp;
+    ZG_REQUIRE(p.dy && p.x && p.dx && p.rstd, "add_norm_bwd: null tensor pointer");
+    ZG_REQUIRE(p.ncols > 0 && p.ncols <= 4 * 32 * zg::NORM_MAXQ, "add_norm_bwd: ncols must be <= %d, got %d", 4 * 32 * zg::NORM_MAXQ, p.ncols);
+    if (p.nrows == 0) return 0;
+    cudaStream_t s = (cudaStream_t)stream;
+    switch (p.dtype) {
+        case ZG_F32: return zg::norm_bwd_t<float>(p, s);
+        case ZG_F16: return zg::norm_bwd_t<__half>(p, s);
+        case ZG_BF16: return zg::norm_bwd_t<__nv_bfloat16>(p, s);
+    }
+    return zg_set_error("add_norm_bwd: bad dtype %d", p.dtype);
+}
+
+extern "C" int zg_block_tail_fwd(const zg_block_tail_params *pp, void *stream) {
+    ZG_REQUIRE(pp != nullptr, "block_tail_fwd: null params");
+    const zg_block_tail_params &p = *pp;
+    ZG_REQUIRE(p.x && p.norm_w && p.normed, "block_tail_fwd: null tensor pointer");
+    ZG_REQUIRE(!p.mix || p.gate, "block_tail_fwd: mix needs gate");
+    ZG_REQUIRE(!p.modded || (p.shift && p.scale), "block_tail_fwd: modded needs shift and scale");
+    ZG_REQUIRE(p.dim > 0 && p.dim % 4 == 0 && p.dim <= 4 * 32 * zg::NORM_MAXQ, "block_tail_fwd: dim must be a multiple of 4 and <= %d, got %d",
+               4 * 32 * zg::NORM_MAXQ, p.dim);
+    ZG_REQUIRE(p.mod_rs % 4 == 0, "block_tail_fwd: modulation row stride must be a multiple of 4");
+    ZG_REQUIRE(aligned16(p.x) && aligned16(p.mix) && aligned16(p.residual) && aligned16(p.residual_out) && aligned16(p.normed) && aligned16(p.modded),
+               "block_tail_fwd: row tensors must be 16-byte aligned");
+    const int64_t nrows = (int64_t)p.batch * p.seqlen;
+    if (nrows == 0) return 0;
+    cudaStream_t s = (cudaStream_t)stream;
+    const unsigned grid = (unsigned)((nrows * 32 + 127) / 128);
+    switch (p.dtype) {
+        case ZG_F32: zg::block_tail_kernel<float><<<grid, 128, 0, s>>>(p); break;
+        case ZG_F16: zg::block_tail_kernel<__half><<<grid, 128, 0, s>>>(p); break;
+        case ZG_BF16: zg::block_tail_kernel<__nv_bfloat16><<<grid, 128, 0, s>>>(p); break;
+        default: return zg_set_error("block_tail_fwd: bad dtype %d", p.dtype);
+    }
+    zg_count_launch();
+    return zg_check_launch("block_tail_fwd");
+}

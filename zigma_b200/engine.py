@@ -1,0 +1,235 @@
+"""Inference fast path of ZigMa.forward on B200: token-major, fused, CUDA-graph capturable.
+
+What the reference executes per block and what replaces it here:
+
+  reference (channel-first, ~25 launches / block)            here (token-major, 7 launches / block)
+  ---------------------------------------------------------  -----------------------------------------
+  in_proj GEMM + "b l d -> d (b l)" rearranges               GEMM  modded(B*L, D) @ W_in^T -> xz(B*L, 2E)
+  xz[:, :, perm].contiguous() + torch.cat  (1.3 GB / layer)  -- gone: kernels read rows through `perm`
+  causal_conv1d_fwd                                          zg_causal_conv1d_fwd(x_rowmap = perm)
+  x_proj GEMM, dt_proj GEMM, B/C rearrange + contiguous      2 GEMMs; B/C read in place from x_dbl rows
+  selective_scan_fwd (out AND out_z written)                 zg_selective_scan_fwd(z_rowmap = perm)
+  out_proj GEMM, out[:, perm_rev].contiguous() + cat         GEMM; scatter folded into the block tail
+  gate*mix + x, fused add+RMSNorm (Triton), modulate         zg_block_tail_fwd (one pass)
+
+Numerics follow the reference's bf16 path rounding for rounding (every tensor the reference
+materialises in bf16 is rounded to bf16 at the same point), so results agree with the reference
+to fp32-accumulation-order noise.  The dense projections are library GEMMs (cuBLAS through
+torch.matmul) unless ``ZIGMA_TCGEN05=1`` routes the bf16 ones through ``zg_gemm_bf16_tn``.
+"""
+import os
+
+import torch
+import torch.nn.functional as F
+
+from . import _lib
+from .causal_conv1d_interface import _conv_fwd
+from .selective_scan_interface import _scan_fwd
+
+
+def _i32(t):
+    return t.to(torch.int32).contiguous()
+
+
+def block_tail(x, mix, gate, shift, scale, norm_w, residual, rowmap, eps, final=False, mod_div=1, want_modded=True):
+    """zg_block_tail_fwd wrapper.  x: (Bt, L, D) contiguous; gate/shift/scale: (Bt // mod_div, D)
+    views with a common row stride.  Returns residual_out (fp32), normed, modded."""
+    Bt, L, D = x.shape
+    if mod_div != 1:
+        # modulation vectors are per ORIGINAL batch element; expand to the folded batch (tiny)
+        gate = None if gate is None else gate.repeat_interleave(mod_div, dim=0)
+        shift = None if shift is None else shift.repeat_interleave(mod_div, dim=0)
+        scale = None if scale is None else scale.repeat_interleave(mod_div, dim=0)
+    mods = [m for m in (gate, shift, scale) if m is not None]
+    rs = mods[0].stride(0) if mods else 0
+    for m in mods:
+        if m.stride(0) != rs or m.stride(1) != 1:
+            raise RuntimeError("block_tail: modulation views must share one row stride")
+    if norm_w.dtype != x.dtype:
+        norm_w = norm_w.to(x.dtype)
+    if residual is not None and residual.dtype != torch.float32:
+        raise RuntimeError("block_tail: the residual stream must be fp32 (residual_in_fp32=True)")
+    res_out = torch.empty((Bt, L, D), dtype=torch.float32, device=x.device) if not final else None
+    normed = torch.empty_like(x)
+    modded = torch.empty_like(x) if (want_modded and not final) else None
+    p = _lib.BlockTailParams()
+    p.x, p.mix, p.gate, p.shift, p.scale = _lib.ptr(x), _lib.ptr(mix), _lib.ptr(gate), _lib.ptr(shift), _lib.ptr(scale)
+    p.norm_w, p.residual, p.rowmap = _lib.ptr(norm_w), _lib.ptr(residual), _lib.ptr(rowmap)
+    p.residual_out, p.normed, p.modded = _lib.ptr(res_out), _lib.ptr(normed), _lib.ptr(modded)
+    p.mod_rs = rs
+    p.batch, p.seqlen, p.dim = Bt, L, D
+    p.dtype, p.final_layer, p.eps = _lib.dt(x), int(final), float(eps)
+    _lib.call("zg_block_tail_fwd", p)
+    return res_out, normed, modded
+
+
+class ZigMaEngine:
+    def __init__(self, model):
+        self.m = model
+        self._versions = None
+        self._graphs = {}
+        self.use_graph = os.environ.get("ZIGMA_CUDA_GRAPH", "1") != "0"
+        self.refresh()
+
+    # ---- derived, cached tensors ------------------------------------------------------------------
+    def _param_versions(self):
+        return tuple((p.data_ptr(), p._version) for p in self.m.parameters())
+
+    def refresh(self):
+        m = self.m
+        dev = next(m.parameters()).device
+        self.layers = []
+        for blk in m.blocks:
+            mx = blk.mixer
+            E, W = mx.d_inner, mx.d_conv
+
+            def pack(sfx=""):
+                conv, xp, dp = getattr(mx, "conv1d" + sfx), getattr(mx, "x_proj" + sfx), getattr(mx, "dt_proj" + sfx)
+                A_log = mx.A_b_log if sfx else mx.A_log
+                Dp = mx.D_b if sfx else mx.D
+                return dict(conv_w=conv.weight.detach().reshape(E, W).contiguous(),
+                            conv_b=None if conv.bias is None else conv.bias.detach().contiguous(),
+                            x_proj=xp.weight.detach(), dt_proj=dp.weight.detach(),
+                            A=(-torch.exp(A_log.detach().float())).contiguous(), D=Dp.detach().float().contiguous(),
+                            dt_bias=dp.bias.detach().float().contiguous())
+            L = dict(fwd=pack(), in_proj=mx.in_proj.weight.detach(), in_bias=None if mx.in_proj.bias is None else mx.in_proj.bias.detach(),
+                     out_proj=mx.out_proj.weight.detach(), out_bias=None if mx.out_proj.bias is None else mx.out_proj.bias.detach(),
+                     norm_w=blk.norm.weight.detach(), R=mx.dt_rank, N=mx.d_state, E=E, st=mx.scan_type)
+            if mx.scan_type == "v2":
+                L["bwd"] = pack("_b")
+            if mx.zigzag_paths is not None:
+                L["perm"] = _i32(mx.zigzag_paths[mx.layer_idx].to(dev))
+                L["perm_rev"] = _i32(mx.zigzag_paths_reverse[mx.layer_idx].to(dev))
+                L["perm64"] = mx.zigzag_paths[mx.layer_idx].to(dev)
+                L["perm_rev64"] = mx.zigzag_paths_reverse[mx.layer_idx].to(dev)
+            if mx.st_order is not None:
+                L["s_or_t"] = mx.st_order[mx.layer_idx]
+            self.layers.append(L)
+        # every block's adaLN Linear in ONE GEMM: (B, D) @ (D, depth * 3D)
+        self.ada_w = torch.cat([b.adaLN_modulation[1].weight.detach() for b in m.blocks], dim=0).contiguous()
+        self.ada_b = torch.cat([b.adaLN_modulation[1].bias.detach() for b in m.blocks], dim=0).contiguous()
+        self._rev_cache = {}
+        self._versions = self._param_versions()
+        self._graphs = {}
+
+    def _flip_map(self, L, dev):
+        if L not in self._rev_cache:
+            self._rev_cache[L] = torch.arange(L - 1, -1, -1, dtype=torch.int32, device=dev)
+        return self._rev_cache[L]
+
+    # ---- one directional pass of the mixer core, token major ------------------------------------------
+    def _core(self, xz, Bt, L, lay, w, rowmap):
+        """xz: (Bt*L, 2E) token-major.  Returns y (Bt, L, E) = scan(...) * silu(z), in scan order."""
+        E, R, N = lay["E"], lay["R"], lay["N"]
+        xz3 = xz.view(Bt, L, 2 * E)
+        x_log = xz3[:, :, :E].transpose(1, 2)          # logical (Bt, E, L), dim-contiguous
+        z_log = xz3[:, :, E:].transpose(1, 2)
+        xc = _conv_fwd(x_log, w["conv_w"], w["conv_b"], True, x_rowmap=rowmap)           # logical (Bt, E, L), token-major memory
+        xc_flat = xc.transpose(1, 2).reshape(Bt * L, E)
+        x_dbl = xc_flat @ w["x_proj"].t()                                                  # (Bt*L, R + 2N)
+        delta = x_dbl[:, :R] @ w["dt_proj"].t()                                            # (Bt*L, E)
+        d_log = delta.view(Bt, L, E).transpose(1, 2)
+        xd3 = x_dbl.view(Bt, L, R + 2 * N)
+        B_log = xd3[:, :, R:R + N].permute(0, 2, 1).unsqueeze(1)                           # (Bt, 1, N, L) view
+        C_log = xd3[:, :, R + N:].permute(0, 2, 1).unsqueeze(1)
+        y, _, _, _ = _scan_fwd(xc, d_log, w["A"], B_log, C_log, w["D"], z_log, w["dt_bias"], True,
+                               z_rowmap=rowmap, want_last_state=False, want_ckpt=False)
+        return y.transpose(1, 2)                                                            # (Bt, L, E) contiguous
+
+    def _mixer(self, modded, lay):
+        """modded: (B, L, D) -> (mix (Bt', L', D) token-major in SCAN order, tail rowmap, fold info)."""
+        B, L, D = modded.shape
+        E = lay["E"]
+        xz = modded.reshape(B * L, D) @ lay["in_proj"].t()
+        if lay["in_bias"] is not None:
+            xz = xz + lay["in_bias"]
+        st = lay["st"]
+        if st == "v1":
+            y = self._core(xz, B, L, lay, lay["fwd"], None)
+            rowmap = None
+        elif st == "v2":
+            yf = self._core(xz, B, L, lay, lay["fwd"], None)
+            yb = self._core(xz, B, L, lay, lay["bwd"], self._flip_map(L, xz.device))
+            y = yf + yb.flip(1)
+            rowmap = None
+        elif "s_or_t" not in lay:
+            y = self._core(xz, B, L, lay, lay["fwd"], lay["perm"])
+            rowmap = lay["perm_rev"]
+        else:
+            T = self.m.video_frames
+            K = L // T
+            if lay["s_or_t"] == "s":      # (b t) sequences of K tokens: a pure re-view of token-major memory
+                y = self._core(xz, B * T, K, lay, lay["fwd"], lay["perm"])
+                mix = F.linear(y.reshape(B * T * K, E), lay["out_proj"], lay["out_bias"]).view(B * T, K, D)
+                return mix, lay["perm_rev"], T
+            # (b k) sequences of T tokens: strided in token-major memory -> explicit transposes
+            xz_t = xz.view(B, T, K, 2 * E).permute(0, 2, 1, 3).reshape(B * K * T, 2 * E)
+            y = self._core(xz_t, B * K, T, lay, lay["fwd"], lay["perm"])
+            mix = F.linear(y.reshape(B * K * T, E), lay["out_proj"], lay["out_bias"]).view(B * K, T, D)
+            mix = mix[:, lay["perm_rev64"], :].reshape(B, K, T, D).permute(0, 2, 1, 3).reshape(B, L, D)
+            return mix, None, 1
+        mix = F.linear(y.reshape(B * L, E), lay["out_proj"], lay["out_bias"]).view(B, L, D)
+        return mix, rowmap, 1
+
+    # ---- whole forward -----------------------------------------------------------------------------
+    def _forward_impl(self, x, t, y):
+        m = self.m
+        hs, c, _ = m.embed(x, t, y)
+        hs = hs.contiguous()
+        B, L, D = hs.shape
+        depth = len(self.layers)
+        mods = F.linear(F.silu(c), self.ada_w, self.ada_b).view(B, depth, 3, D)     # shift, scale, gate per block
+        eps = m.blocks[0].norm.eps
+        lay0 = self.layers[0]
+        residual, normed, modded = block_tail(hs, None, None, mods[:, 0, 0], mods[:, 0, 1], lay0["norm_w"], None, None, eps)
+        for i, lay in enumerate(self.layers):
+            mix, rowmap, fold = self._mixer(modded, lay)
+            last = i == depth - 1
+            nw = m.norm_f.weight if last else self.layers[i + 1]["norm_w"]
+            neps = m.norm_f.eps if last else m.blocks[i + 1].norm.eps
+            gate = mods[:, i, 2]
+            shift = None if last else mods[:, i + 1, 0]
+            scale = None if last else mods[:, i + 1, 1]
+            if fold != 1:     # spatial video layer: rows are (b t, k); same memory as (b, t k)
+                Bf = B * fold
+                residual, normed, modded = block_tail(normed.view(Bf, L // fold, D), mix, gate, shift, scale, nw,
+                                                      residual.view(Bf, L // fold, D), rowmap, neps, final=last, mod_div=fold)
+                normed = normed.view(B, L, D)
+                if not last:
+                    residual, modded = residual.view(B, L, D), modded.view(B, L, D)
+            else:
+                residual, normed, modded = block_tail(normed, mix, gate, shift, scale, nw, residual, rowmap, neps, final=last)
+        out = F.linear(normed, m.final_layer.linear.weight, m.final_layer.linear.bias)
+        if m.video_frames > 0:
+            return m.unpatchify_video(out, m.video_frames)
+        return m.unpatchify(out)
+
+    @torch.no_grad()
+    def forward(self, x, t, y=None):
+        if self._versions != self._param_versions():
+            self.refresh()
+        if not self.use_graph:
+            return self._forward_impl(x, t, y)
+        key = (tuple(x.shape), x.dtype, tuple(t.shape), t.dtype, None if y is None else (tuple(y.shape), y.dtype))
+        g = self._graphs.get(key)
+        if g is None:
+            # warm-up on a side stream (sets kernel attributes, fills cuBLAS workspaces), then capture
+            sx, st_, sy = x.clone(), t.clone(), None if y is None else y.clone()
+            s = torch.cuda.Stream()
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                for _ in range(2):
+                    self._forward_impl(sx, st_, sy)
+            torch.cuda.current_stream().wait_stream(s)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                sout = self._forward_impl(sx, st_, sy)
+            g = (graph, sx, st_, sy, sout)
+            self._graphs[key] = g
+        graph, sx, st_, sy, sout = g
+        sx.copy_(x)
+        st_.copy_(t)
+        if y is not None:
+            sy.copy_(y)
+        graph.replay()
+        return sout.clone()
