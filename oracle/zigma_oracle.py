@@ -20,6 +20,8 @@ import numpy as np
 import torch
 import torch.nn.functional as F
 
+USE_C_SCAN = False   # route mamba_inner's scan through the plain-C port (fp32 only)
+
 # ------------------------------------------------------------------------------------------------
 # a1. scan-path tables (integer, bit exact)
 # ------------------------------------------------------------------------------------------------
@@ -263,7 +265,15 @@ def mamba_inner(xz, conv_w, conv_b, x_proj_w, dt_proj_w, out_proj_w, out_proj_b,
     delta = (dt_proj_w @ x_dbl[:, :R].t()).reshape(E, Bt, L).transpose(0, 1)    # (Bt, E, L)
     Bm = x_dbl[:, R:R + N].reshape(Bt, L, N).transpose(1, 2)                    # (Bt, N, L)
     Cm = x_dbl[:, R + N:].reshape(Bt, L, N).transpose(1, 2)
-    y = selective_scan(xc, delta, A, Bm, Cm, D, z=z, delta_bias=delta_bias, delta_softplus=True)
+    if USE_C_SCAN and xz.dtype == torch.float32:
+        # same recurrence through oracle/scan_oracle.c (OpenMP over (batch, channel)): used where the
+        # python time loop is too slow (bench cpu_baseline, full-size model checks)
+        from . import c_oracle
+        yc, _ = c_oracle.scan_fwd(xc.contiguous().numpy(), delta.contiguous().numpy(), A.numpy(), Bm.contiguous().numpy()[:, None],
+                                  Cm.contiguous().numpy()[:, None], D.numpy(), z.contiguous().numpy(), delta_bias.numpy(), True)
+        y = torch.from_numpy(yc)
+    else:
+        y = selective_scan(xc, delta, A, Bm, Cm, D, z=z, delta_bias=delta_bias, delta_softplus=True)
     if no_out_proj:
         return y
     return F.linear(y.transpose(1, 2), out_proj_w, out_proj_b)

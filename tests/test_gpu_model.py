@@ -1,0 +1,106 @@
+"""GPU (B200): ZigMa.forward / mamba_inner_fn end to end against the golden vectors produced by the
+unmodified reference, through both execution paths (engine fast path and autograd path)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import synth, zigma_oracle as zo
+from oracle.gen_golden import model_io
+from util import check_close, gold, model_case, t
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _build(cfg, shapes, dtype=torch.float32):
+    from zigma_b200 import ZigMa
+    m = ZigMa(device=DEV, dtype=dtype, **cfg).eval()
+    sd = synth.synth_state_dict(shapes, seed=0, dtype=dtype)
+    m.load_state_dict(sd, strict=True)
+    return m, sd
+
+
+def test_mamba_inner_fn_golden():
+    from zigma_b200 import mamba_inner_fn
+    g = gold("mamba_inner")
+    a = {k: t(g[k], DEV) for k in g.files}
+    out = mamba_inner_fn(a["xz"], a["conv_w"], a["conv_b"], a["x_proj_w"], a["dt_proj_w"], a["out_proj_w"], a["out_proj_b"],
+                         a["A"], None, None, a["D"], a["delta_bias"], delta_softplus=True)
+    check_close(out, g["out"], "mamba_inner_fn")
+
+
+@pytest.mark.parametrize("name", ["tiny_zigzag8", "tiny_sweep2", "tiny_hilbert2", "tiny_patch2_cls", "tiny_video_sst"])
+@pytest.mark.parametrize("path", ["engine", "engine_nograph", "autograd"])
+def test_zigma_forward_golden_fp32(name, path, monkeypatch):
+    g, cfg, shapes = model_case(name)
+    m, _ = _build(cfg, shapes)
+    x, tt, y = model_io(cfg, g["out"].shape[0])
+    x, tt = x.to(DEV), tt.to(DEV)
+    y = None if y is None else y.to(DEV)
+    if path == "autograd":
+        out = m.forward_autograd(x, tt, y)
+    else:
+        if path == "engine_nograph":
+            monkeypatch.setenv("ZIGMA_CUDA_GRAPH", "0")
+        with torch.no_grad():
+            out = m(x, tt, y)
+            if path == "engine":     # second call replays the captured graph
+                out2 = m(x, tt, y)
+                assert torch.equal(out, out2)
+    check_close(out, g["out"], f"ZigMa.forward {name} [{path}]", atol=2e-5)
+
+
+def test_zigma_forward_full_model_fp32():
+    """BASELINE config-2 architecture (D=640, depth=18, 32x32, zigzag8) at bs=1, fp32, vs the reference."""
+    g, cfg, shapes = model_case("full_zigzag8_b1")
+    m, _ = _build(cfg, shapes)
+    x, tt, y = model_io(cfg, 1)
+    with torch.no_grad():
+        out = m(x.to(DEV), tt.to(DEV))
+    check_close(out, g["out"], "ZigMa.forward full zigzag8_b1 fp32", atol=2e-5)
+
+
+def test_zigma_forward_bf16():
+    """bf16 state dict (every parameter bf16): tiny model vs the reference's bf16 CPU
+    output, and the bf16 result must also sit close to the fp32 result of the same weights."""
+    g, cfg, shapes = model_case("tiny_zigzag8_bf16")
+    m, sd = _build(cfg, shapes, torch.bfloat16)
+    x, tt, y = model_io(cfg, g["out"].shape[0])
+    with torch.no_grad():
+        out = m(x.to(DEV).bfloat16(), tt.to(DEV).bfloat16())
+    assert out.dtype == torch.bfloat16
+    check_close(out, g["out"], "ZigMa.forward tiny bf16 vs reference bf16", rtol=5e-2, atol=5e-2, scale_atol=False, max_strict_viol=1.0)
+    g32 = gold("model_tiny_zigzag8")
+    check_close(out, g32["out"], "ZigMa.forward tiny bf16 vs reference fp32", rtol=5e-2, atol=5e-2, scale_atol=False, max_strict_viol=1.0)
+
+
+def test_zigma_forward_batch_consistency_bf16_full():
+    """Full-size bf16 model at bs=4: each sample equals the bs=1 run of that sample (samples are
+    independent -> the multi-GPU batch sharding cannot change results), output finite."""
+    g, cfg, shapes = model_case("full_zigzag8_b1")
+    m, _ = _build(cfg, shapes, torch.bfloat16)
+    x = synth.synth_latents((4, 4, 32, 32), seed=5).to(DEV).bfloat16()
+    tt = torch.tensor([0.1, 0.4, 0.6, 0.9], device=DEV).bfloat16()
+    with torch.no_grad():
+        out = m(x, tt)
+        one = m(x[2:3], tt[2:3])
+    assert torch.isfinite(out.float()).all()
+    check_close(out[2:3], one, "bs=4 vs bs=1 sample", rtol=2e-2, atol=2e-2, scale_atol=False, max_strict_viol=1.0)
+    # and against the fp32 reference golden for sample seed 3 at bs = 1
+    x1, t1, _ = model_io(cfg, 1)
+    with torch.no_grad():
+        o1 = m(x1.to(DEV).bfloat16(), t1.to(DEV).bfloat16())
+    check_close(o1, g["out"], "full model bf16 vs reference fp32", rtol=6e-2, atol=6e-2, scale_atol=False, max_strict_viol=1.0)
+
+
+def test_euler_sampling_loop_matches_oracle():
+    from zigma_b200 import create_transport, Sampler
+    g, cfg, shapes = model_case("tiny_zigzag8")
+    m, sd = _build(cfg, shapes)
+    x0 = synth.synth_latents((2, 4, 8, 8), seed=8)
+    fn = Sampler(create_transport()).sample_ode(sampling_method="euler", num_steps=6)
+    with torch.no_grad():
+        got = fn(x0.to(DEV), m.forward)[-1]
+    ocfg = dict(cfg, norm_epsilon=1e-5)
+    want = zo.sample_ode_fixed(lambda x, t: zo.zigma_forward(sd, ocfg, x, t), x0, num_steps=6)
+    check_close(got, want, "5-step Euler sampling", atol=5e-5)

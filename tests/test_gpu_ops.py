@@ -1,0 +1,327 @@
+"""GPU (B200): parity of every op of the C-ABI against the oracle / the reference's golden vectors.
+All calls go through the host mirror of the reference interface -> ctypes -> libzigma_b200.so."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import c_oracle, synth, zigma_oracle as zo
+from util import check_close, gold, t
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+SCAN = ["t128_g1", "t131_g2", "e64_n16", "plain", "noz", "l1", "l16_many", "n4"]
+
+
+def _scan_args(g, dev=DEV, dtype=None):
+    Bt, E, L, N, G, hasD, hasz, hasb, sp = [int(v) for v in g["flags"]]
+    c = lambda k: t(g[k], dev, dtype)
+    B, C = c("B"), c("C")
+    return dict(u=c("u"), delta=c("delta"), A=t(g["A"], dev), B=B if G > 1 else B[:, 0], C=C if G > 1 else C[:, 0],
+                D=t(g["D"], dev) if hasD else None, z=c("z") if hasz else None,
+                delta_bias=t(g["delta_bias"], dev) if hasb else None, delta_softplus=bool(sp)), (Bt, E, L, N, G)
+
+
+@pytest.mark.parametrize("name", SCAN)
+def test_selective_scan_fwd_golden_fp32(name):
+    """selective_scan_fn in the reference (channel-first) layout vs the reference's own output."""
+    from zigma_b200 import selective_scan_fn
+    g = gold("scan_" + name)
+    a, _ = _scan_args(g)
+    out, last = selective_scan_fn(a["u"], a["delta"], a["A"], a["B"], a["C"], a["D"], z=a["z"], delta_bias=a["delta_bias"],
+                                  delta_softplus=a["delta_softplus"], return_last_state=True)
+    check_close(out, g["out"], f"scan {name} out")
+    check_close(last, g["last_state"], f"scan {name} last_state")
+
+
+@pytest.mark.parametrize("name", SCAN)
+def test_selective_scan_fwd_token_major_golden_fp32(name):
+    """Same vectors through the dim-contiguous (token-major) loader: u, delta, z as transposed views
+    of (B, L, E) tensors, B/C as (B, G, N, L) views of (B, G, L, N) memory."""
+    from zigma_b200 import selective_scan_fn
+    g = gold("scan_" + name)
+    a, (Bt, E, L, N, G) = _scan_args(g)
+    tm = lambda x: None if x is None else x.transpose(1, 2).contiguous().transpose(1, 2)
+    Bv = a["B"] if a["B"].dim() == 4 else a["B"].unsqueeze(1)
+    Cv = a["C"] if a["C"].dim() == 4 else a["C"].unsqueeze(1)
+    Bv = Bv.transpose(2, 3).contiguous().transpose(2, 3)
+    Cv = Cv.transpose(2, 3).contiguous().transpose(2, 3)
+    out, last = selective_scan_fn(tm(a["u"]), tm(a["delta"]), a["A"], Bv, Cv, a["D"], z=tm(a["z"]), delta_bias=a["delta_bias"],
+                                  delta_softplus=a["delta_softplus"], return_last_state=True)
+    assert out.shape == (Bt, E, L)
+    check_close(out, g["out"], f"scan(token-major) {name} out")
+    check_close(last, g["last_state"], f"scan(token-major) {name} last_state")
+
+
+def test_selective_scan_config1_fp32():
+    """BASELINE config 1: B=2 L=1024 D=640 N=16 fp32, against the reference digest and the C oracle."""
+    from zigma_b200 import selective_scan_fn
+    g = gold("scan_config1_digest")
+    inp = synth.synth_scan_inputs(2, 640, 1024, 16, 1, seed=2)
+    d = {k: v.to(DEV) for k, v in inp.items()}
+    out, last = selective_scan_fn(d["u"], d["delta"], d["A"], d["B"], d["C"], d["D"], z=d["z"], delta_bias=d["delta_bias"],
+                                  delta_softplus=True, return_last_state=True)
+    o = out.cpu()
+    check_close(o.reshape(-1)[t(g["idx"])], g["out_sub"], "config1 vs reference digest", max_strict_viol=1e-3)
+    check_close(last.cpu().reshape(-1)[::13], g["last_sub"], "config1 last_state vs reference digest", max_strict_viol=1e-3)
+    ref, ref_last = c_oracle.scan_fwd(inp["u"], inp["delta"], inp["A"], inp["B"], inp["C"], inp["D"], inp["z"], inp["delta_bias"], True)
+    check_close(o, ref, "config1 vs C oracle (all 1.3M elements)")
+    assert abs(o.double().sum().item() - float(g["out_sum"])) <= 1e-4 * float(g["out_abs_sum"])
+
+
+@pytest.mark.parametrize("dtype,rtol,atol", [(torch.bfloat16, 1.6e-2, 1e-5), (torch.float16, 2e-3, 1e-5)])
+@pytest.mark.parametrize("layout", ["seq", "tok"])
+def test_selective_scan_lowp(dtype, rtol, atol, layout):
+    """16-bit I/O: inputs rounded to the I/O dtype first, oracle run in fp32 on the rounded inputs,
+    result must be the correctly rounded oracle value to within 2 ulp (bf16 ulp = 2^-8, fp16 2^-11)
+    (SURVEY.md section 8c protocol item 3)."""
+    from zigma_b200 import selective_scan_fn
+    Bt, E, L, N = 3, 160, 277, 16
+    inp = synth.synth_scan_inputs(Bt, E, L, N, 1, seed=7)
+    lo = {k: (v.to(dtype) if k in ("u", "delta", "z", "B", "C") else v) for k, v in inp.items()}
+    f32 = {k: v.float().numpy() for k, v in lo.items()}
+    ref, ref_last = c_oracle.scan_fwd(f32["u"], f32["delta"], f32["A"], f32["B"], f32["C"], f32["D"], f32["z"], f32["delta_bias"], True)
+    d = {k: v.to(DEV) for k, v in lo.items()}
+    if layout == "tok":
+        tm = lambda x: x.transpose(1, 2).contiguous().transpose(1, 2)
+        d["u"], d["delta"], d["z"] = tm(d["u"]), tm(d["delta"]), tm(d["z"])
+        d["B"] = d["B"].transpose(2, 3).contiguous().transpose(2, 3)
+        d["C"] = d["C"].transpose(2, 3).contiguous().transpose(2, 3)
+    out, last = selective_scan_fn(d["u"], d["delta"], d["A"], d["B"], d["C"], d["D"], z=d["z"], delta_bias=d["delta_bias"],
+                                  delta_softplus=True, return_last_state=True)
+    assert out.dtype == dtype
+    check_close(out, ref, f"scan {dtype} {layout}", rtol=rtol, atol=atol, max_strict_viol=1.0)
+    check_close(last, ref_last, f"scan {dtype} {layout} last_state (fp32)", max_strict_viol=1e-3)
+
+
+def test_selective_scan_strided_and_constant_bc():
+    """Non-contiguous batch/dim strides (delta as a view of an (E, B*L) GEMM output, u sliced out of a
+    wider tensor -- selective_scan_interface.py:323, test_causal_conv1d.py:39-46) and constant B/C."""
+    from zigma_b200 import selective_scan_fn
+    Bt, E, L, N = 2, 24, 96, 8
+    inp = synth.synth_scan_inputs(Bt, E, L, N, 1, seed=9)
+    wide = torch.randn(Bt, E + 16, L)
+    wide[:, 8:8 + E] = inp["u"]
+    u = wide.to(DEV)[:, 8:8 + E]
+    delta_el = inp["delta"].permute(1, 0, 2).reshape(E, Bt * L).contiguous().to(DEV)
+    delta = delta_el.reshape(E, Bt, L).transpose(0, 1)
+    d = {k: v.to(DEV) for k, v in inp.items()}
+    out = selective_scan_fn(u, delta, d["A"], d["B"], d["C"], d["D"], z=d["z"], delta_bias=d["delta_bias"], delta_softplus=True)
+    ref, _ = c_oracle.scan_fwd(inp["u"], inp["delta"], inp["A"], inp["B"], inp["C"], inp["D"], inp["z"], inp["delta_bias"], True)
+    check_close(out, ref, "scan strided views")
+    Bc, Cc = torch.randn(E, N), torch.randn(E, N)
+    for Bx, Cx, tag in ((Bc, inp["C"][:, 0], "constB"), (inp["B"][:, 0], Cc, "constC"), (Bc, Cc, "constBC")):
+        want = zo.selective_scan(inp["u"], inp["delta"], inp["A"], Bx, Cx, inp["D"], inp["z"], inp["delta_bias"], True)
+        got = selective_scan_fn(d["u"], d["delta"], d["A"], Bx.to(DEV), Cx.to(DEV), d["D"], z=d["z"], delta_bias=d["delta_bias"], delta_softplus=True)
+        check_close(got, want, "scan " + tag)
+
+
+def test_selective_scan_z_rowmap_fuses_permutation():
+    """z_rowmap == gathering z through the zigzag table first (forward_permutation, mamba_simple.py:55-56)."""
+    from zigma_b200.selective_scan_interface import _scan_fwd
+    import zigma_b200
+    Bt, E, L, N = 2, 96, 64, 16
+    inp = synth.synth_scan_inputs(Bt, E, L, N, 1, seed=11)
+    perm = torch.from_numpy(zigma_b200.zigzag_path(8)[3])
+    d = {k: v.to(DEV) for k, v in inp.items()}
+    tm = lambda x: x.transpose(1, 2).contiguous().transpose(1, 2)
+    Bv = d["B"].transpose(2, 3).contiguous().transpose(2, 3)
+    Cv = d["C"].transpose(2, 3).contiguous().transpose(2, 3)
+    out, _, _, _ = _scan_fwd(tm(d["u"]), tm(d["delta"]), d["A"], Bv, Cv, d["D"], tm(d["z"]), d["delta_bias"], True,
+                             z_rowmap=perm.to(DEV).to(torch.int32), want_last_state=False)
+    ref, _ = c_oracle.scan_fwd(inp["u"], inp["delta"], inp["A"], inp["B"], inp["C"], inp["D"], inp["z"][:, :, perm], inp["delta_bias"], True)
+    check_close(out, ref, "scan z_rowmap")
+
+
+def test_selective_scan_properties_full_size():
+    """BASELINE config-2 layer shape (bs=64, E=1280, L=1024, N=16, bf16, token-major): too big for
+    the CPU oracle in seconds, so size-independent properties instead:
+      * causality: the first half of the output does not depend on the second half of the inputs;
+      * batch independence + determinism: a batch slice recomputed alone is bit-identical;
+      * a random subset of (b, e) rows equals the C oracle run on just those rows."""
+    from zigma_b200 import selective_scan_fn
+    Bt, E, L, N = 64, 1280, 1024, 16
+    gen = torch.Generator(device=DEV).manual_seed(0)
+    rnd = lambda *s: torch.randn(*s, device=DEV, generator=gen)
+    u, z = rnd(Bt, L, E).bfloat16(), rnd(Bt, L, E).bfloat16()
+    delta = (0.5 * torch.rand(Bt, L, E, device=DEV, generator=gen)).bfloat16()
+    xbc = rnd(Bt, L, 2 * N).bfloat16()
+    A = -0.5 * torch.rand(E, N, device=DEV, generator=gen)
+    D, bias = rnd(E), 0.5 * torch.rand(E, device=DEV, generator=gen)
+    lg = lambda x: x.transpose(1, 2)
+    Bv = xbc[:, :, :N].permute(0, 2, 1).unsqueeze(1)
+    Cv = xbc[:, :, N:].permute(0, 2, 1).unsqueeze(1)
+    run = lambda u_, d_, z_, B_, C_: selective_scan_fn(lg(u_), lg(d_), A, B_, C_, D, z=lg(z_), delta_bias=bias, delta_softplus=True)
+    out = run(u, delta, z, Bv, Cv)
+    assert out.shape == (Bt, E, L) and torch.isfinite(out.float()).all()
+    # causality
+    u2, d2, z2, x2 = u.clone(), delta.clone(), z.clone(), xbc.clone()
+    u2[:, L // 2:] = 0; d2[:, L // 2:] = 0; z2[:, L // 2:] = 1; x2[:, L // 2:] = 0
+    out2 = run(u2, d2, z2, x2[:, :, :N].permute(0, 2, 1).unsqueeze(1), x2[:, :, N:].permute(0, 2, 1).unsqueeze(1))
+    assert torch.equal(out[:, :, : L // 2], out2[:, :, : L // 2])
+    # batch slice, bit identical
+    sl = slice(17, 19)
+    out3 = run(u[sl].contiguous(), delta[sl].contiguous(), z[sl].contiguous(),
+               xbc[sl].contiguous()[:, :, :N].permute(0, 2, 1).unsqueeze(1), xbc[sl].contiguous()[:, :, N:].permute(0, 2, 1).unsqueeze(1))
+    assert torch.equal(out[sl], out3)
+    # sampled rows vs the C oracle
+    bs, es = [0, 31, 63], [0, 5, 640, 1279]
+    f = lambda x: x[bs][:, :, es].float().cpu().permute(0, 2, 1).contiguous().numpy()
+    ref, _ = c_oracle.scan_fwd(f(u), f(delta), A[es].cpu().numpy(), xbc[bs][:, :, :N].float().cpu().permute(0, 2, 1).unsqueeze(1).contiguous().numpy(),
+                               xbc[bs][:, :, N:].float().cpu().permute(0, 2, 1).unsqueeze(1).contiguous().numpy(),
+                               D[es].cpu().numpy(), f(z), bias[es].cpu().numpy(), True)
+    check_close(out[bs][:, es].float(), ref, "full-size sampled rows vs C oracle (bf16 out)", rtol=1.6e-2, atol=1e-5, max_strict_viol=1.0)
+
+
+def test_selective_scan_rejects_bad_input():
+    from zigma_b200 import selective_scan_fn
+    u = torch.randn(1, 4, 8, device=DEV)
+    A = -torch.rand(4, 2, device=DEV)
+    Bm = torch.randn(1, 2, 8, device=DEV)
+    with pytest.raises(RuntimeError):
+        selective_scan_fn(u, u[:, :, :4], A, Bm, Bm)                       # delta shape
+    with pytest.raises(RuntimeError):
+        selective_scan_fn(u, u, A.half(), Bm, Bm)                          # A dtype
+    with pytest.raises(RuntimeError):
+        selective_scan_fn(u, u, -torch.rand(4, 65, device=DEV), torch.randn(1, 65, 8, device=DEV), torch.randn(1, 65, 8, device=DEV))
+
+
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("channel_last", [False, True])
+def test_causal_conv1d_golden_fp32(channel_last):
+    from zigma_b200 import causal_conv1d_fn
+    g = gold("conv")
+    x = t(g["x"], DEV)
+    if channel_last:
+        x = x.transpose(1, 2).contiguous().transpose(1, 2)
+    for W in (2, 3, 4):
+        for silu in (0, 1):
+            for hb in (0, 1):
+                tag = f"W{W}_s{silu}_b{hb}"
+                out = causal_conv1d_fn(x, t(g[f"w{W}"], DEV), t(g[f"b{W}"], DEV) if hb else None, "silu" if silu else None)
+                check_close(out, g["out_" + tag], f"conv {tag} cl={channel_last}")
+
+
+@pytest.mark.parametrize("itype", [torch.float32, torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("seqlen", [8, 151, 1024, 1134])
+@pytest.mark.parametrize("channel_last", [False, True])
+def test_causal_conv1d_reference_test_shapes(seqlen, itype, channel_last):
+    """Shapes and tolerances of dis_causal_conv1d/tests/test_causal_conv1d.py:14-75 (dim not divisible
+    by 64, x sliced out of a wider tensor -> non-trivial batch stride)."""
+    from zigma_b200 import causal_conv1d_fn
+    rtol, atol = (3e-4, 1e-3) if itype == torch.float32 else (3e-3, 5e-3)
+    if itype == torch.bfloat16:
+        rtol, atol = 1e-2, 5e-2
+    torch.manual_seed(0)
+    dim, W = 512 + 32, 4
+    if not channel_last:
+        x = torch.randn(2, 64 + dim + 64, seqlen, device=DEV, dtype=itype)[:, 64:64 + dim, :]
+    else:
+        x = torch.randn(2, seqlen, 64 + dim + 64, device=DEV, dtype=itype)[:, :, 64:64 + dim].transpose(1, 2)
+    w = torch.randn(dim, W, device=DEV, dtype=torch.float32)
+    b = torch.randn(dim, device=DEV, dtype=torch.float32)
+    out = causal_conv1d_fn(x, w, b, activation="silu")
+    ref = zo.causal_conv1d(x.cpu(), w.cpu(), b.cpu(), "silu")
+    assert out.dtype == itype and out.shape == x.shape
+    assert torch.allclose(out.cpu().float(), ref.float(), rtol=rtol, atol=atol), (out.cpu().float() - ref.float()).abs().max()
+
+
+def test_causal_conv1d_rowmap_fuses_permutation():
+    from zigma_b200.causal_conv1d_interface import _conv_fwd
+    import zigma_b200
+    Bt, E, L = 2, 128, 64
+    perm = torch.from_numpy(zigma_b200.zigzag_path(8)[5])
+    xz = torch.randn(Bt, L, 2 * E, device=DEV).bfloat16()
+    w, b = torch.randn(E, 4, device=DEV).bfloat16(), torch.randn(E, device=DEV).bfloat16()
+    x_log = xz[:, :, :E].transpose(1, 2)
+    out = _conv_fwd(x_log, w, b, True, x_rowmap=perm.to(DEV).to(torch.int32))
+    ref = zo.causal_conv1d(xz[:, :, :E].transpose(1, 2)[:, :, perm.to(DEV)].cpu(), w.cpu(), b.cpu(), "silu")
+    check_close(out, ref, "conv x_rowmap (bf16)", rtol=8e-3, atol=1e-5, max_strict_viol=1.0)
+
+
+def test_causal_conv1d_backward_golden():
+    from zigma_b200 import causal_conv1d_fn
+    g = gold("conv")
+    for tag in ("W4_s1_b1", "W3_s0_b0", "W2_s1_b0"):
+        W, silu, hb = int(tag[1]), int(tag[4]), int(tag[7])
+        x = t(g["x"], DEV).requires_grad_()
+        w = t(g[f"w{W}"], DEV).requires_grad_()
+        b = t(g[f"b{W}"], DEV).requires_grad_() if hb else None
+        out = causal_conv1d_fn(x, w, b, "silu" if silu else None)
+        out.backward(t(g["g"], DEV))
+        check_close(x.grad, g["dx_" + tag], "conv dx " + tag)
+        check_close(w.grad, g["dw_" + tag], "conv dweight " + tag, rtol=1e-3, atol=1e-4)
+        if hb:
+            check_close(b.grad, g["db_" + tag], "conv dbias " + tag, rtol=1e-3, atol=1e-4)
+
+
+# ------------------------------------------------------------------------------------------------
+def test_add_norm_golden():
+    from zigma_b200 import rms_norm_fn, layer_norm_fn
+    g = gold("norm")
+    x, res, w, b = (t(g[k], DEV) for k in ("x", "res", "w", "b"))
+    for rms in (1, 0):
+        for hr in (1, 0):
+            fn = rms_norm_fn if rms else layer_norm_fn
+            y, r = fn(x, w, None if rms else b, residual=res if hr else None, prenorm=True, residual_in_fp32=True, eps=1e-5)
+            check_close(y, g[f"y_rms{rms}_res{hr}"], f"norm rms={rms} res={hr} y")
+            check_close(r, g[f"r_rms{rms}_res{hr}"], f"norm rms={rms} res={hr} residual")
+    y, r = rms_norm_fn(x.bfloat16(), w.bfloat16(), None, residual=res, prenorm=True, residual_in_fp32=True, eps=1e-5)
+    assert y.dtype == torch.bfloat16 and r.dtype == torch.float32
+    check_close(y, g["y_bf16"], "norm bf16 y", rtol=8e-3, max_strict_viol=1.0)
+    check_close(r, g["r_bf16"], "norm bf16 residual")
+
+
+def test_add_norm_backward_vs_autograd_oracle():
+    from zigma_b200 import rms_norm_fn, layer_norm_fn
+    torch.manual_seed(1)
+    M, N = 37, 640
+    for rms in (True, False):
+        x = torch.randn(M, N, device=DEV, requires_grad=True)
+        res = torch.randn(M, N, device=DEV, requires_grad=True)
+        w = (1 + 0.1 * torch.randn(N, device=DEV)).requires_grad_()
+        b = None if rms else (0.1 * torch.randn(N, device=DEV)).requires_grad_()
+        gy, gr = torch.randn(M, N, device=DEV), torch.randn(M, N, device=DEV)
+        fn = rms_norm_fn if rms else layer_norm_fn
+        y, r = fn(x, w, b, residual=res, prenorm=True, residual_in_fp32=True, eps=1e-5)
+        (y * gy).sum().backward(retain_graph=True)
+        (r * gr).sum().backward()
+        xr, rr, wr = x.detach().cpu().requires_grad_(), res.detach().cpu().requires_grad_(), w.detach().cpu().requires_grad_()
+        br = None if b is None else b.detach().cpu().requires_grad_()
+        y2, r2 = zo.add_norm(xr, wr, br, rr, True, True, 1e-5, rms)
+        ((y2 * gy.cpu()).sum() + (r2 * gr.cpu()).sum()).backward()
+        check_close(x.grad, xr.grad, f"norm bwd dx rms={rms}", atol=1e-4)
+        check_close(res.grad, rr.grad, f"norm bwd dresidual rms={rms}", atol=1e-4)
+        check_close(w.grad, wr.grad, f"norm bwd dweight rms={rms}", atol=1e-4)
+        if b is not None:
+            check_close(b.grad, br.grad, "norm bwd dbias", atol=1e-4)
+
+
+def test_block_tail_matches_unfused_chain():
+    """zg_block_tail_fwd == x + gate*mix[perm_rev] -> add+RMSNorm -> modulate done with separate
+    torch ops on the CPU in the same dtype (the reference's unfused Block.forward chain)."""
+    from zigma_b200.engine import block_tail
+    import zigma_b200
+    for dtype in (torch.float32, torch.bfloat16):
+        torch.manual_seed(2)
+        Bt, L, D = 3, 64, 640
+        x, mix = torch.randn(Bt, L, D).to(dtype), torch.randn(Bt, L, D).to(dtype)
+        mods = (0.3 * torch.randn(Bt, 3 * D)).to(dtype)
+        res = torch.randn(Bt, L, D)
+        nw = (1 + 0.1 * torch.randn(D)).to(dtype)
+        rev = torch.from_numpy(zigma_b200.reverse_permut_np(zigma_b200.zigzag_path(8)[1]))
+        gate, shift, scale = mods[:, :D], mods[:, D:2 * D], mods[:, 2 * D:]
+        hidden = x + gate.unsqueeze(1) * mix[:, rev]
+        normed_ref, res_ref = zo.add_norm(hidden, nw, None, res, True, True, 1e-5, True)
+        modded_ref = normed_ref * (1 + scale.unsqueeze(1)) + shift.unsqueeze(1)
+        md = mods.to(DEV)
+        r, n, m = block_tail(x.to(DEV), mix.to(DEV), md[:, :D], md[:, D:2 * D], md[:, 2 * D:], nw.to(DEV), res.to(DEV),
+                             rev.to(DEV).to(torch.int32), 1e-5)
+        tol = dict(rtol=1e-3) if dtype == torch.float32 else dict(rtol=8e-3, max_strict_viol=1.0)
+        check_close(r, res_ref, f"block_tail residual {dtype}")
+        check_close(n, normed_ref, f"block_tail normed {dtype}", **tol)
+        check_close(m, modded_ref, f"block_tail modded {dtype}", **tol)
+        # final-layer flavour: norm_f -> LayerNorm(no affine, 1e-6)
+        _, nf, _ = block_tail(x.to(DEV), mix.to(DEV), md[:, :D], None, None, nw.to(DEV), res.to(DEV), rev.to(DEV).to(torch.int32), 1e-5, final=True)
+        fin_ref = torch.nn.functional.layer_norm(normed_ref, (D,), None, None, 1e-6)
+        check_close(nf, fin_ref, f"block_tail final {dtype}", **(dict(rtol=1e-3, atol=1e-4) if dtype == torch.float32 else dict(rtol=2e-2, atol=2e-2, max_strict_viol=1.0)))
