@@ -81,7 +81,7 @@ def cpu_reference_eval(nthreads=None, bs=2):
     from oracle import zigma_oracle as zo
     from zigma_b200 import synth, ZigMa
     if nthreads:
-        torch.set_num_threads(nthreads)
+        torch.set_num_threads(min(nthreads, 32))   # small-batch GEMMs stop scaling (and regress) beyond ~32 threads
     zo.USE_C_SCAN = True
     shapes = {k: tuple(v.shape) for k, v in ZigMa(device="cpu", **CFG).state_dict().items()}
     sd = synth.synth_state_dict(shapes, seed=0)
@@ -93,6 +93,64 @@ def cpu_reference_eval(nthreads=None, bs=2):
         t0 = time.perf_counter()
         zo.zigma_forward(sd, cfg, x, t)
         return time.perf_counter() - t0
+
+
+def reference_cuda_numbers(bs, dtype_name="bf16", n_iter=5):
+    """The reference's vendored CUDA kernels (oracle/_ref, built from the unmodified sources for
+    sm_100a) on this GPU: (a) selective_scan_cuda.fwd and causal_conv1d_fwd at the layer shape of the
+    workload in the reference's own layout, (b) one denoiser evaluation through the reference's
+    (restated) PyTorch glue around those kernels.  Returns None when oracle/_ref is absent."""
+    import torch
+    from oracle import ref_cuda, zigma_oracle as zo
+    if not (ref_cuda.available() and torch.cuda.is_available()):
+        return None
+    from zigma_b200 import synth, ZigMa, rms_norm_fn
+    dev = torch.device("cuda", torch.cuda.current_device())
+    dtype = torch.bfloat16 if dtype_name == "bf16" else torch.float32
+    E, N, L = 2 * CFG["embed_dim"], 16, L_TOKENS
+
+    def timeit(fn, n=n_iter, warm=2):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(n):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / n
+    gen = torch.Generator(device=dev).manual_seed(0)
+    xz = torch.randn(bs, 2 * E, L, device=dev, generator=gen).to(dtype)
+    u, z = xz[:, :E], xz[:, E:]
+    delta = (0.5 * torch.rand(E, bs * L, device=dev, generator=gen)).to(dtype).reshape(E, bs, L).transpose(0, 1)   # view like :323
+    Bm = torch.randn(bs, 1, N, L, device=dev, generator=gen).to(dtype)
+    Cm = torch.randn(bs, 1, N, L, device=dev, generator=gen).to(dtype)
+    A = -0.5 * torch.rand(E, N, device=dev, generator=gen)
+    Dp, bias = torch.randn(E, device=dev, generator=gen), 0.5 * torch.rand(E, device=dev, generator=gen)
+    cw, cb = torch.randn(E, 4, device=dev, generator=gen).to(dtype), torch.randn(E, device=dev, generator=gen).to(dtype)
+    out = {"scan_fwd_ms": timeit(lambda: ref_cuda.scan_fwd(u, delta, A, Bm, Cm, Dp, z, bias, True), 10),
+           "conv_fwd_ms": timeit(lambda: ref_cuda.conv_fwd(u, cw, cb, True), 10)}
+    from zigma_b200 import selective_scan_fn, causal_conv1d_fn
+    out["ours_same_layout_scan_fwd_ms"] = timeit(lambda: selective_scan_fn(u, delta, A, Bm, Cm, Dp, z=z, delta_bias=bias, delta_softplus=True), 10)
+    out["ours_same_layout_conv_fwd_ms"] = timeit(lambda: causal_conv1d_fn(u, cw, cb, "silu"), 10)
+    # whole denoiser evaluation: restated reference glue + reference kernels
+    shapes = {k: tuple(v.shape) for k, v in ZigMa(device="cpu", **CFG).state_dict().items()}
+    sd = {k: v.to(dev) for k, v in synth.synth_state_dict(shapes, seed=0, dtype=dtype).items()}
+    norm = lambda x, w, b, residual=None, prenorm=False, residual_in_fp32=False, eps=1e-6: rms_norm_fn(
+        x, w, b, residual=residual, prenorm=prenorm, residual_in_fp32=residual_in_fp32, eps=eps)
+    zo.BACKEND = ref_cuda.backend(norm)
+    x = torch.randn(bs, 4, 32, 32, device=dev, generator=gen).to(dtype)
+    t = torch.full((bs,), 0.5, device=dev, dtype=dtype)
+    cfg = dict(CFG, norm_epsilon=1e-5)
+    try:
+        with torch.no_grad():
+            ms = timeit(lambda: zo.zigma_forward(sd, cfg, x, t), n_iter)
+    finally:
+        zo.BACKEND = {}
+    out.update({"denoiser_eval_ms": ms, "tokens_per_s": bs * L / (ms * 1e-3), "bs": bs, "dtype": dtype_name,
+                "what": "reference dis_mamba/dis_causal_conv1d CUDA kernels (sm_100a build of the unmodified sources) + the reference's PyTorch glue (restated), eager"})
+    return out
 
 
 def run_reference(args, rank):
@@ -122,6 +180,10 @@ def run_reference(args, rank):
         "e2e": {"value": val, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    try:
+        line["reference_cuda"] = reference_cuda_numbers(BS_PER_GPU)
+    except Exception as ex:   # the CUDA baseline is extra information; the arm's contract is the CPU number
+        line["reference_cuda"] = {"error": repr(ex)[:300]}
     print(json.dumps(line))
 
 
@@ -134,6 +196,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--bs", type=int, default=BS_PER_GPU, help="batch per GPU (BASELINE config: 64)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-ref-cuda", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch kernels eagerly (for ncu launch lists)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -196,12 +259,14 @@ def main():
             clocks.start()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
+        torch.cuda.profiler.start()     # no-op unless run under `ncu --profile-from-start off`
         e0.record()
         for i in range(K):
             x = euler_step(x, W + i)
         full = gather_latents(x, bs * world, world)      # the single collective of the sampling job
         e1.record()
         barrier()
+        torch.cuda.profiler.stop()
         ms = e0.elapsed_time(e1)
         clk = clocks.stop() if rank == 0 else None
         if world > 1:
@@ -297,6 +362,14 @@ def main():
         "gpu_launches_per_eval": per_eval,
         "roofline": roof,
     }
+    if not args.no_ref_cuda:
+        try:
+            rc = reference_cuda_numbers(bs)
+        except Exception as ex:
+            rc = {"error": repr(ex)[:300]}
+        line["reference_cuda"] = rc
+        if rc and "denoiser_eval_ms" in rc:
+            line["speedup_vs_reference_cuda"] = rc["denoiser_eval_ms"] / (ms / K)
     if not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
         dt = cpu_reference_eval(cores, 2)

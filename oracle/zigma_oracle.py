@@ -21,6 +21,11 @@ import torch
 import torch.nn.functional as F
 
 USE_C_SCAN = False   # route mamba_inner's scan through the plain-C port (fp32 only)
+# Optional op backends for mamba_inner / zigma_forward: {"conv": f(x, w, b) -> silu(conv),
+# "scan": f(u, delta, A, B, C, D, z, delta_bias) -> y * silu(z), "norm": add_norm-like}.  Used by
+# oracle/ref_cuda.py to drive the SAME restated glue with the reference's compiled CUDA kernels
+# (the "reference vendored CUDA path" baseline of bench.py).  None = the CPU restatements below.
+BACKEND = {}
 
 # ------------------------------------------------------------------------------------------------
 # a1. scan-path tables (integer, bit exact)
@@ -115,9 +120,19 @@ def hilbert_path(N):
     return [np.ascontiguousarray(o).reshape(-1) for o in out]
 
 
+_BUILD_CACHE = {}
+
+
 def build_scan_tables(scan_type, depth, num_patches, video_frames=0):
     """Per-layer (perm, perm_rev, st_order) lists as ZigMa.__init__ builds them.
-    model_zigma.py:689-794."""
+    model_zigma.py:689-794.  Memoised (the reference builds them once in the constructor)."""
+    key = (scan_type, depth, num_patches, video_frames)
+    if key not in _BUILD_CACHE:
+        _BUILD_CACHE[key] = _build_scan_tables(scan_type, depth, num_patches, video_frames)
+    return _BUILD_CACHE[key]
+
+
+def _build_scan_tables(scan_type, depth, num_patches, video_frames=0):
     side = int(math.sqrt(num_patches))
     if scan_type.startswith("zigzagN") or scan_type.startswith("hilbertN"):
         n = int(scan_type.replace("zigzagN", "").replace("hilbertN", ""))
@@ -260,12 +275,17 @@ def mamba_inner(xz, conv_w, conv_b, x_proj_w, dt_proj_w, out_proj_w, out_proj_b,
     R = dt_proj_w.shape[1]
     N = A.shape[1]
     x, z = xz[:, :E], xz[:, E:]
-    xc = causal_conv1d(x, conv_w.reshape(E, -1), conv_b, "silu")
+    if "conv" in BACKEND:
+        xc = BACKEND["conv"](x, conv_w.reshape(E, -1), conv_b)
+    else:
+        xc = causal_conv1d(x, conv_w.reshape(E, -1), conv_b, "silu")
     x_dbl = F.linear(xc.transpose(1, 2).reshape(Bt * L, E), x_proj_w)           # (Bt*L, R+2N)
     delta = (dt_proj_w @ x_dbl[:, :R].t()).reshape(E, Bt, L).transpose(0, 1)    # (Bt, E, L)
     Bm = x_dbl[:, R:R + N].reshape(Bt, L, N).transpose(1, 2)                    # (Bt, N, L)
     Cm = x_dbl[:, R + N:].reshape(Bt, L, N).transpose(1, 2)
-    if USE_C_SCAN and xz.dtype == torch.float32:
+    if "scan" in BACKEND:
+        y = BACKEND["scan"](xc, delta, A, Bm, Cm, D, z, delta_bias)
+    elif USE_C_SCAN and xz.dtype == torch.float32:
         # same recurrence through oracle/scan_oracle.c (OpenMP over (batch, channel)): used where the
         # python time loop is too slow (bench cpu_baseline, full-size model checks)
         from . import c_oracle
@@ -282,6 +302,17 @@ def mamba_inner(xz, conv_w, conv_b, x_proj_w, dt_proj_w, out_proj_w, out_proj_b,
 # ------------------------------------------------------------------------------------------------
 # a6. Mamba mixer with the ZigMa scan-type dispatch
 # ------------------------------------------------------------------------------------------------
+
+_TABLE_CACHE = {}
+
+
+def _dev_table(a, device):
+    """int64 index tensor of a path table on `device`, cached (the reference keeps them resident too)."""
+    key = (id(a), str(device))
+    if key not in _TABLE_CACHE:
+        _TABLE_CACHE[key] = (a, torch.as_tensor(a, dtype=torch.long).to(device))   # keep `a` alive: id() stays unique
+    return _TABLE_CACHE[key][1]
+
 
 def mamba_mixer(h, p, scan_type, perm=None, perm_rev=None, st=None, video_frames=0):
     """h (Bt, L, Dm); p: dict of the mixer's parameters (reference state-dict names without the
@@ -302,8 +333,7 @@ def mamba_mixer(h, p, scan_type, perm=None, perm_rev=None, st=None, video_frames
                     delta_bias=p["dt_proj_b.bias"].float())
         yb = mamba_inner(xz.flip(-1), no_out_proj=True, **argb)
         return F.linear((yf + yb.flip(-1)).transpose(1, 2), p["out_proj.weight"], None)
-    perm_t = torch.as_tensor(perm, dtype=torch.long)
-    rev_t = torch.as_tensor(perm_rev, dtype=torch.long)
+    perm_t, rev_t = _dev_table(perm, h.device), _dev_table(perm_rev, h.device)
     if st is None:  # zigzagN / hilbertN / randomN (:356-395)
         out = mamba_inner(xz[:, :, perm_t].contiguous(), **args)
         return out[:, rev_t, :].contiguous()
@@ -327,7 +357,7 @@ def mamba_mixer(h, p, scan_type, perm=None, perm_rev=None, st=None, video_frames
 def timestep_embedding(t, dim, dtype, max_period=10000):
     """model_zigma.py:247-268 -- NB the frequency table is computed in the MODEL dtype."""
     half = dim // 2
-    freqs = torch.exp(-math.log(max_period) * torch.arange(0, half, dtype=dtype) / half)
+    freqs = torch.exp(-math.log(max_period) * torch.arange(0, half, dtype=dtype) / half).to(t.device)
     args = t[:, None].float() * freqs[None]
     return torch.cat([torch.cos(args), torch.sin(args)], dim=-1)
 
@@ -369,8 +399,8 @@ def zigma_forward(sd, cfg, x, t, y=None):
     residual = None
     for i in range(depth):
         pre = f"blocks.{i}."
-        hs, residual = add_norm(hs, sd[pre + "norm.weight"], None, residual, prenorm=True,
-                                residual_in_fp32=True, eps=eps)
+        hs, residual = BACKEND.get("norm", add_norm)(hs, sd[pre + "norm.weight"], None, residual, prenorm=True,
+                                                     residual_in_fp32=True, eps=eps)
         mod = F.linear(F.silu(c), sd[pre + "adaLN_modulation.1.weight"], sd[pre + "adaLN_modulation.1.bias"])
         shift, scale, gate = mod.chunk(3, dim=1)
         mp = {k[len(pre + "mixer."):]: v for k, v in sd.items() if k.startswith(pre + "mixer.")}
@@ -378,7 +408,7 @@ def zigma_forward(sd, cfg, x, t, y=None):
                             None if fwd is None else fwd[i], None if rev is None else rev[i],
                             None if st is None else st[i], vf)
         hs = hs + gate.unsqueeze(1) * mixed
-    hs = add_norm(hs, sd["norm_f.weight"], None, residual, prenorm=False, residual_in_fp32=True, eps=eps)
+    hs = BACKEND.get("norm", add_norm)(hs, sd["norm_f.weight"], None, residual, prenorm=False, residual_in_fp32=True, eps=eps)
     hs = F.layer_norm(hs, (D,), None, None, 1e-6)
     hs = F.linear(hs, sd["final_layer.linear.weight"], sd["final_layer.linear.bias"])
     C = cfg["in_channels"]

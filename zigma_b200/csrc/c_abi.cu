@@ -66,11 +66,6 @@ int zg_selective_scan_fwd(const zg_scan_params *pp, void *stream) {
 }  // extern "C"
 
 // ---- entry points implemented in later files fall back to a loud error until they exist -------------
-#ifndef ZG_HAVE_SCAN_BWD
-extern "C" int zg_selective_scan_bwd(const zg_scan_bwd_params *, void *) {
-    return zg_set_error("selective_scan_bwd: not built into this library");
-}
-#endif
 #ifndef ZG_HAVE_GEMM
 extern "C" int zg_gemm_bf16_tn(const zg_gemm_params *, void *) {
     return zg_set_error("gemm_bf16_tn: not built into this library");

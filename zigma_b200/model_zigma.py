@@ -40,7 +40,16 @@ class PatchEmbed(nn.Module):
         self.proj = nn.Conv2d(in_chans, embed_dim, kernel_size=patch_size, stride=patch_size, bias=bias)
 
     def forward(self, x):
-        return self.proj(x).flatten(2).transpose(1, 2)
+        # kernel == stride: the strided Conv2d is a per-patch linear map.  Done as unfold + GEMM so the
+        # fp32 path stays exact fp32 (cuDNN convolutions default to TF32: torch.backends.cudnn.allow_tf32)
+        # and the bf16 path goes through the same library GEMM as every other projection.
+        B, C, H, W = x.shape
+        p = self.patch_size[0]
+        if p == 1:
+            tokens = x.flatten(2).transpose(1, 2)                                   # (B, H*W, C)
+        else:
+            tokens = (x.reshape(B, C, H // p, p, W // p, p).permute(0, 2, 4, 1, 3, 5).reshape(B, (H // p) * (W // p), C * p * p))
+        return F.linear(tokens, self.proj.weight.reshape(self.proj.weight.shape[0], -1), self.proj.bias)
 
 
 class PatchEmbed_Video(PatchEmbed):

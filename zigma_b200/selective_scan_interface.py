@@ -15,7 +15,7 @@ import torch.nn.functional as F
 from . import _lib
 from .causal_conv1d_interface import _conv_fwd, _conv_bwd
 
-CKPT_EVERY = 64  # recompute-seed spacing handed to the backward kernel (multiple of 16)
+CKPT_EVERY = 16  # recompute-seed spacing: the backward kernel re-runs 16-step chunks from these states
 
 
 def _strides3(t):
