@@ -35,12 +35,12 @@ def test_selective_scan_bwd_bf16():
     from zigma_b200 import selective_scan_fn
     Bt, E, L, N = 2, 96, 150, 16
     inp = synth.synth_scan_inputs(Bt, E, L, N, 1, seed=21)
-    lo = {k: (v.bfloat16() if k in ("u", "delta", "z", "B", "C") else v) for k, v in inp.items()}
+    lo = {k: (v.bfloat16() if k in ("u", "delta", "z", "B", "C") else v.clone()) for k, v in inp.items()}
     gout = torch.randn(Bt, E, L).bfloat16()
-    ref_in = {k: v.float().requires_grad_() for k, v in lo.items()}
+    ref_in = {k: v.float().clone().requires_grad_() for k, v in lo.items()}
     out_ref = zo.selective_scan(ref_in["u"], ref_in["delta"], ref_in["A"], ref_in["B"], ref_in["C"], ref_in["D"], ref_in["z"], ref_in["delta_bias"], True)
     out_ref.backward(gout.float())
-    d = {k: v.to(DEV).requires_grad_() for k, v in lo.items()}
+    d = {k: v.detach().to(DEV).requires_grad_() for k, v in lo.items()}
     out = selective_scan_fn(d["u"], d["delta"], d["A"], d["B"], d["C"], d["D"], z=d["z"], delta_bias=d["delta_bias"], delta_softplus=True)
     out.backward(gout.to(DEV))
     for k in ("u", "delta", "z"):

@@ -285,8 +285,9 @@ def test_add_norm_backward_vs_autograd_oracle():
         gy, gr = torch.randn(M, N, device=DEV), torch.randn(M, N, device=DEV)
         fn = rms_norm_fn if rms else layer_norm_fn
         y, r = fn(x, w, b, residual=res, prenorm=True, residual_in_fp32=True, eps=1e-5)
-        (y * gy).sum().backward(retain_graph=True)
-        (r * gr).sum().backward()
+        # one backward call: like the reference (layernorm.py:441-447) dx and dresidual share storage, which
+        # is only safe for autograd's in-place accumulation when both are produced in the same call
+        ((y * gy).sum() + (r * gr).sum()).backward()
         xr, rr, wr = x.detach().cpu().requires_grad_(), res.detach().cpu().requires_grad_(), w.detach().cpu().requires_grad_()
         br = None if b is None else b.detach().cpu().requires_grad_()
         y2, r2 = zo.add_norm(xr, wr, br, rr, True, True, 1e-5, rms)

@@ -20,11 +20,21 @@
 //                (the zigzag permutation) so no permuted copy of xz is ever materialised.
 #pragma once
 #include "zg_common.cuh"
+#include <stdlib.h>
 
 namespace zg {
 
 constexpr int SCAN_CH = 64;      // channels (= threads) per CTA
 constexpr int SCAN_TL = 16;      // time steps per pipeline stage
+#ifndef ZG_SCAN_NPOLY_DEFAULT
+#define ZG_SCAN_NPOLY_DEFAULT 0
+#endif
+constexpr int SCAN_SB = 4;       // time steps processed together by the packed inner loop
+// The register file is split per SMSP (16384 x 32-bit each): 5 warps per SMSP need <= 96 registers per
+// thread.  At bs=64, E=1280 the grid has 2560 warps = 17.3 per SM; with 4 warps per SMSP (100+
+// registers) only 16 fit and a second, 8%-full wave doubles the kernel time (ncu round 1:
+// launch__waves_per_multiprocessor 1.08).  Asking for 10 CTAs of 64 threads caps ptxas at 96.
+constexpr int SCAN_MIN_CTAS = 10;
 
 template <typename T, bool SEQ> struct ScanSmem {
     static constexpr int VEC = 16 / sizeof(T);
@@ -52,8 +62,9 @@ __device__ __forceinline__ void copy_chunk(T *sdst, const T *gsrc, int nvalid) {
     }
 }
 
-template <typename T, int NS, bool SEQ, bool CONSTBC>
-__global__ void __launch_bounds__(SCAN_CH) scan_fwd_kernel(const zg_scan_params p) {
+// NPOLY: how many of the NS/2 state PAIRS take their exp2 from the FMA-pipe polynomial instead of MUFU
+template <typename T, int NS, bool SEQ, bool CONSTBC, int NPOLY>
+__global__ void __launch_bounds__(SCAN_CH, (NS <= 16 && !CONSTBC) ? SCAN_MIN_CTAS : 1) scan_fwd_kernel(const zg_scan_params p) {
     using SM = ScanSmem<T, SEQ>;
     constexpr int VEC = SM::VEC;
     constexpr int TL = SCAN_TL, CH = SCAN_CH, NSTAGE = SM::NSTAGE;
@@ -85,13 +96,22 @@ __global__ void __launch_bounds__(SCAN_CH) scan_fwd_kernel(const zg_scan_params 
     T *gout = reinterpret_cast<T *>(p.out) + (int64_t)b * p.out_sb;
 
     // ---- per-thread constants and state --------------------------------------------------------
-    float Al2[NS], h[NS];
+    // states live in registers as fp32x2 PAIRS (n, n+1): every FMA-pipe instruction of the inner loop
+    // is a packed FFMA2/FMUL2, halving the issue slots of the recurrence.
+    constexpr int NP = NS / 2;
+    zg_f2 Al2p[NP], h2[NP];
     float Bc[CONSTBC ? NS : 1], Cc[CONSTBC ? NS : 1];
 #pragma unroll
-    for (int n = 0; n < NS; ++n) {
-        Al2[n] = (active && n < N) ? p.A[(int64_t)e * N + n] * ZG_LOG2E : 0.f;
-        h[n] = 0.f;
-        if (CONSTBC) {
+    for (int q = 0; q < NP; ++q) {
+        const int n = 2 * q;
+        const float a0 = (active && n < N) ? p.A[(int64_t)e * N + n] * ZG_LOG2E : 0.f;
+        const float a1 = (active && n + 1 < N) ? p.A[(int64_t)e * N + n + 1] * ZG_LOG2E : 0.f;
+        Al2p[q] = zg_pack2(a0, a1);
+        h2[q] = zg_pack2(0.f, 0.f);
+    }
+    if (CONSTBC) {
+#pragma unroll
+        for (int n = 0; n < NS; ++n) {
             Bc[n] = (!varB && active && n < N) ? reinterpret_cast<const float *>(p.B)[(int64_t)e * N + n] : 0.f;
             Cc[n] = (!varC && active && n < N) ? reinterpret_cast<const float *>(p.C)[(int64_t)e * N + n] : 0.f;
         }
@@ -173,31 +193,59 @@ __global__ void __launch_bounds__(SCAN_CH) scan_fwd_kernel(const zg_scan_params 
         zg_cp_async_commit();
     };
 
-    // ---- one recurrence step --------------------------------------------------------------------
-    auto step = [&](int t, float uu, float dd, float zz) -> float {
-        float dl = dd + bias;
-        if (softplus) dl = zg_softplus20(dl);
-        const float du = dl * uu;
-        float y = Dv * uu;
-        const float4 *bc4 = reinterpret_cast<const float4 *>(bcf + t * 2 * NS);
+    // ---- SB consecutive recurrence steps (t0 .. t0+SB-1 of the current stage) ------------------------
+    // uu/dd/zz: raw inputs of the SB steps; y: results.  The per-step scalars (softplus, delta*u) of the
+    // SB steps are independent, so their MUFU latency overlaps; the state update is 4 packed
+    // instructions + 2 exp2 per state PAIR and step:
+    //     x = dl * A'      a = 2^x      h = a * h + (dl*u) * B      y += C * h
+    // The first NPOLY pairs take 2^x from the FMA-pipe polynomial (zg_ex2_poly2), the rest from MUFU.
+    auto block = [&](int t0, const float (&uu)[SCAN_SB], const float (&dd)[SCAN_SB], const float (&zz)[SCAN_SB],
+                     float (&y)[SCAN_SB]) {
+        zg_f2 dl2[SCAN_SB], du2[SCAN_SB], y2[SCAN_SB];
 #pragma unroll
-        for (int q = 0; q < NS / 4; ++q) {
-            float4 Bv = bc4[q], Cv = bc4[NS / 4 + q];
-            float Bn[4] = {Bv.x, Bv.y, Bv.z, Bv.w}, Cn[4] = {Cv.x, Cv.y, Cv.z, Cv.w};
+        for (int i = 0; i < SCAN_SB; ++i) {
+            float dl = dd[i] + bias;
+            if (softplus) dl = zg_softplus20(dl);
+            const float du = dl * uu[i];
+            dl2[i] = zg_pack2(dl, dl);
+            du2[i] = zg_pack2(du, du);
+            y2[i] = zg_pack2(Dv * uu[i], 0.f);
+        }
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int n = q * 4 + i;
+        for (int q = 0; q < NP; ++q) {
+#pragma unroll
+            for (int i = 0; i < SCAN_SB; ++i) {
+                const float2 *bc = reinterpret_cast<const float2 *>(bcf + (t0 + i) * 2 * NS);
+                float2 Bv = bc[q], Cv = bc[NP + q];
                 if (CONSTBC) {
-                    if (!varB) Bn[i] = Bc[n];
-                    if (!varC) Cn[i] = Cc[n];
+                    if (!varB) Bv = make_float2(Bc[2 * q], Bc[2 * q + 1]);
+                    if (!varC) Cv = make_float2(Cc[2 * q], Cc[2 * q + 1]);
                 }
-                const float a = zg_ex2(dl * Al2[n]);
-                h[n] = fmaf(a, h[n], du * Bn[i]);
-                y = fmaf(Cn[i], h[n], y);
+                const zg_f2 x = zg_mul2(dl2[i], Al2p[q]);
+                const zg_f2 a = (q < NPOLY) ? zg_ex2_poly2(x) : zg_ex2_mufu2(x);
+                h2[q] = zg_fma2(a, h2[q], zg_mul2(du2[i], zg_pack2(Bv.x, Bv.y)));
+                y2[i] = zg_fma2(zg_pack2(Cv.x, Cv.y), h2[q], y2[i]);
             }
         }
-        if (has_z) y *= zg_silu(zz);
-        return y;
+#pragma unroll
+        for (int i = 0; i < SCAN_SB; ++i) {
+            float lo, hi;
+            zg_unpack2(y2[i], lo, hi);
+            float v = lo + hi;
+            if (has_z) v *= zg_silu(zz[i]);
+            y[i] = v;
+        }
+    };
+    // a partial block at the ragged end of the sequence: inputs beyond nb are the identity step
+    // (delta' = 0 -> a = 1, b = 0), selective_scan_fwd_kernel.cuh:218-222
+    auto store_state = [&](float *dst) {
+#pragma unroll
+        for (int q = 0; q < NP; ++q) {
+            float lo, hi;
+            zg_unpack2(h2[q], lo, hi);
+            if (2 * q < N) dst[2 * q] = lo;
+            if (2 * q + 1 < N) dst[2 * q + 1] = hi;
+        }
     };
 
     // ---- pipeline -------------------------------------------------------------------------------
@@ -231,6 +279,7 @@ __global__ void __launch_bounds__(SCAN_CH) scan_fwd_kernel(const zg_scan_params 
 
         if (active) {
             if (SEQ) {
+                // a thread reads 16-byte vectors (VEC steps) along its own smem row; VEC is 4 (fp32) or 8
                 const unsigned char *ru = st + 0 * SM::ACT_BYTES + tid * SM::ACT_ROW_BYTES;
                 const unsigned char *rd = st + 1 * SM::ACT_BYTES + tid * SM::ACT_ROW_BYTES;
                 const unsigned char *rz = st + 2 * SM::ACT_BYTES + tid * SM::ACT_ROW_BYTES;
@@ -243,12 +292,21 @@ __global__ void __launch_bounds__(SCAN_CH) scan_fwd_kernel(const zg_scan_params 
                     Dl.v = *reinterpret_cast<const uint4 *>(rd + tv * 16);
                     if (has_z) Z.v = *reinterpret_cast<const uint4 *>(rz + tv * 16);
 #pragma unroll
-                    for (int i = 0; i < VEC; ++i) {
-                        const int t = tv * VEC + i;
-                        float y = 0.f;
-                        if (t < nsteps)
-                            y = step(t, zg_to_float<T>(U.e[i]), zg_to_float<T>(Dl.e[i]), has_z ? zg_to_float<T>(Z.e[i]) : 0.f);
-                        O.e[i] = zg_from_float<T>(y);
+                    for (int sb = 0; sb < VEC / SCAN_SB; ++sb) {
+                        const int t0 = tv * VEC + sb * SCAN_SB;
+                        if (t0 < nsteps) {
+                            float uu[SCAN_SB], dd[SCAN_SB], zz[SCAN_SB], y[SCAN_SB];
+#pragma unroll
+                            for (int i = 0; i < SCAN_SB; ++i) {
+                                const bool ok = t0 + i < nsteps;      // beyond L: identity step
+                                uu[i] = ok ? zg_to_float<T>(U.e[sb * SCAN_SB + i]) : 0.f;
+                                dd[i] = ok ? zg_to_float<T>(Dl.e[sb * SCAN_SB + i]) : (softplus ? -1e30f : 0.f) - bias;
+                                zz[i] = (ok && has_z) ? zg_to_float<T>(Z.e[sb * SCAN_SB + i]) : 0.f;
+                            }
+                            block(t0, uu, dd, zz, y);
+#pragma unroll
+                            for (int i = 0; i < SCAN_SB; ++i) O.e[sb * SCAN_SB + i] = zg_from_float<T>(y[i]);
+                        }
                     }
                     T *dst = orow + tv * VEC;
                     if (tv * VEC + VEC <= nsteps && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
@@ -264,19 +322,20 @@ __global__ void __launch_bounds__(SCAN_CH) scan_fwd_kernel(const zg_scan_params 
                 const T *sd = reinterpret_cast<const T *>(st + 1 * SM::ACT_BYTES) + tid;
                 const T *sz = reinterpret_cast<const T *>(st + 2 * SM::ACT_BYTES) + tid;
                 T *ocol = gout + (int64_t)l0 * p.out_sl + e;
-                if (nsteps == TL) {
-#pragma unroll 4
-                    for (int t = 0; t < TL; ++t) {
-                        const float y = step(t, zg_to_float<T>(su[t * CH]), zg_to_float<T>(sd[t * CH]),
-                                             has_z ? zg_to_float<T>(sz[t * CH]) : 0.f);
-                        ocol[(int64_t)t * p.out_sl] = zg_from_float<T>(y);
+#pragma unroll 1
+                for (int t0 = 0; t0 < nsteps; t0 += SCAN_SB) {
+                    float uu[SCAN_SB], dd[SCAN_SB], zz[SCAN_SB], y[SCAN_SB];
+#pragma unroll
+                    for (int i = 0; i < SCAN_SB; ++i) {
+                        const bool ok = t0 + i < nsteps;
+                        uu[i] = ok ? zg_to_float<T>(su[(t0 + i) * CH]) : 0.f;
+                        dd[i] = ok ? zg_to_float<T>(sd[(t0 + i) * CH]) : (softplus ? -1e30f : 0.f) - bias;
+                        zz[i] = (ok && has_z) ? zg_to_float<T>(sz[(t0 + i) * CH]) : 0.f;
                     }
-                } else {
-                    for (int t = 0; t < nsteps; ++t) {
-                        const float y = step(t, zg_to_float<T>(su[t * CH]), zg_to_float<T>(sd[t * CH]),
-                                             has_z ? zg_to_float<T>(sz[t * CH]) : 0.f);
-                        ocol[(int64_t)t * p.out_sl] = zg_from_float<T>(y);
-                    }
+                    block(t0, uu, dd, zz, y);
+#pragma unroll
+                    for (int i = 0; i < SCAN_SB; ++i)
+                        if (t0 + i < nsteps) ocol[(int64_t)(t0 + i) * p.out_sl] = zg_from_float<T>(y[i]);
                 }
             }
             // recompute seeds for the backward pass
@@ -285,35 +344,29 @@ __global__ void __launch_bounds__(SCAN_CH) scan_fwd_kernel(const zg_scan_params 
                 if (lend % p.ckpt_every == 0 || lend == L) {
                     const int k = (lend - 1) / p.ckpt_every;
                     const int nck = (L + p.ckpt_every - 1) / p.ckpt_every;
-                    float *dst = p.ckpt + (((int64_t)b * E + e) * nck + k) * N;
-#pragma unroll
-                    for (int n = 0; n < NS; ++n)
-                        if (n < N) dst[n] = h[n];
+                    store_state(p.ckpt + (((int64_t)b * E + e) * nck + k) * N);
                 }
             }
         }
         __syncthreads();   // stage buffer and bcf are recycled by the next iteration
     }
 
-    if (active && p.last_state) {
-        float *dst = p.last_state + ((int64_t)b * E + e) * N;
-#pragma unroll
-        for (int n = 0; n < NS; ++n)
-            if (n < N) dst[n] = h[n];
-    }
+    if (active && p.last_state) store_state(p.last_state + ((int64_t)b * E + e) * N);
 }
 
-template <typename T, int NS, bool SEQ, bool CONSTBC>
+template <typename T, int NS, bool SEQ, bool CONSTBC, int NPOLY = 0>
 int launch_scan_fwd(const zg_scan_params &p, cudaStream_t stream) {
     using SM = ScanSmem<T, SEQ>;
     const int per_group = p.dim / p.ngroups;
     const int tiles = p.ngroups * ((per_group + SCAN_CH - 1) / SCAN_CH);
     const int smem = SM::total_bytes(NS);
-    auto kern = scan_fwd_kernel<T, NS, SEQ, CONSTBC>;
+    auto kern = scan_fwd_kernel<T, NS, SEQ, CONSTBC, NPOLY>;
     static bool attr_set = false;   // per instantiation
     if (!attr_set) {
         cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (err != cudaSuccess) return zg_set_error("scan_fwd: cudaFuncSetAttribute(%d B smem): %s", smem, cudaGetErrorString(err));
+        // all of the SM's unified L1/shared array as shared memory: 9-10 CTAs x (stage ring + 1 KB) must fit
+        cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         attr_set = true;
     }
     const long long nblk = (long long)tiles * p.batch;
@@ -324,13 +377,37 @@ int launch_scan_fwd(const zg_scan_params &p, cudaStream_t stream) {
     return zg_check_launch("scan_fwd");
 }
 
+// How many state pairs use the polynomial exp2 (tuning knob; default chosen from the B200 measurements
+// in DESIGN.md).  ZG_SCAN_NPOLY in the environment overrides it (read once).
+inline int scan_npoly_setting() {
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("ZG_SCAN_NPOLY");
+        v = e ? atoi(e) : ZG_SCAN_NPOLY_DEFAULT;
+        if (v != 0 && v != 2 && v != 3 && v != 4) v = ZG_SCAN_NPOLY_DEFAULT;
+    }
+    return v;
+}
+
 // one translation unit per I/O dtype (parallel compilation)
+template <typename T, int NS, bool SEQ> int launch_scan_fwd_npoly(const zg_scan_params &p, cudaStream_t stream) {
+    if (NS == 16) {
+        switch (scan_npoly_setting()) {
+            case 2: return launch_scan_fwd<T, NS, SEQ, false, (NS == 16 ? 2 : 0)>(p, stream);
+            case 3: return launch_scan_fwd<T, NS, SEQ, false, (NS == 16 ? 3 : 0)>(p, stream);
+            case 4: return launch_scan_fwd<T, NS, SEQ, false, (NS == 16 ? 4 : 0)>(p, stream);
+            default: break;
+        }
+    }
+    return launch_scan_fwd<T, NS, SEQ, false, 0>(p, stream);
+}
+
 template <typename T> int dispatch_scan_fwd(const zg_scan_params &p, bool seq, bool constbc, cudaStream_t stream) {
     const int N = p.dstate;
 #define ZG_SCAN_CASE(NSV)                                                                   \
     if (N <= NSV) {                                                                         \
-        if (seq) return launch_scan_fwd<T, NSV, true, false>(p, stream);                    \
-        return launch_scan_fwd<T, NSV, false, false>(p, stream);                            \
+        if (seq) return launch_scan_fwd_npoly<T, NSV, true>(p, stream);                     \
+        return launch_scan_fwd_npoly<T, NSV, false>(p, stream);                             \
     }
     if (constbc) {
         if (N <= 8) return seq ? launch_scan_fwd<T, 8, true, true>(p, stream) : launch_scan_fwd<T, 8, false, true>(p, stream);

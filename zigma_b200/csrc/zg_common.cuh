@@ -67,6 +67,65 @@ __device__ __forceinline__ float zg_softplus20(float x) {
 __device__ __forceinline__ float zg_sigmoid(float x) { return zg_rcp(1.f + zg_ex2(-x * ZG_LOG2E)); }
 __device__ __forceinline__ float zg_silu(float x) { return x * zg_sigmoid(x); }
 
+// ---- packed fp32x2 arithmetic (FFMA2 / FMUL2 / FADD2 on sm_100a: one issue slot, two results) ----
+typedef unsigned long long zg_f2;
+__device__ __forceinline__ zg_f2 zg_pack2(float lo, float hi) {
+    zg_f2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void zg_unpack2(zg_f2 v, float &lo, float &hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ zg_f2 zg_fma2(zg_f2 a, zg_f2 b, zg_f2 c) {
+    zg_f2 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ zg_f2 zg_mul2(zg_f2 a, zg_f2 b) {
+    zg_f2 d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ zg_f2 zg_add2(zg_f2 a, zg_f2 b) {
+    zg_f2 d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+// 2^x for two lanes at once via MUFU.EX2 (2 MUFU issues)
+__device__ __forceinline__ zg_f2 zg_ex2_mufu2(zg_f2 x) {
+    float a, b;
+    zg_unpack2(x, a, b);
+    return zg_pack2(zg_ex2(a), zg_ex2(b));
+}
+// 2^x for two lanes on the FMA/ALU pipes only (no MUFU): Cody-Waite split x = i + f, |f| <= 0.5,
+// 2^f by a degree-5 minimax polynomial (max relative error 2.3e-7 in fp32 Horner form -- the same as
+// ex2.approx's 2^-22), 2^i by adding i to the exponent field.  x is clamped to [-126, 126].
+// Used to take part of the exp load off the 16-lane/SM MUFU pipe, which bounds the selective scan.
+__device__ __forceinline__ zg_f2 zg_ex2_poly2(zg_f2 x) {
+    float a, b;
+    zg_unpack2(x, a, b);
+    a = fminf(fmaxf(a, -126.f), 126.f);
+    b = fminf(fmaxf(b, -126.f), 126.f);
+    x = zg_pack2(a, b);
+    const zg_f2 magic = zg_pack2(12582912.f, 12582912.f);          // 1.5 * 2^23: low mantissa bits = round(x)
+    const zg_f2 r = zg_add2(x, magic);
+    const zg_f2 xi = zg_add2(r, zg_pack2(-12582912.f, -12582912.f));
+    const zg_f2 f = zg_fma2(xi, zg_pack2(-1.f, -1.f), x);
+    zg_f2 p = zg_pack2(0.001327647129073739f, 0.001327647129073739f);
+    p = zg_fma2(p, f, zg_pack2(0.009675540961325169f, 0.009675540961325169f));
+    p = zg_fma2(p, f, zg_pack2(0.05550713092088699f, 0.05550713092088699f));
+    p = zg_fma2(p, f, zg_pack2(0.24022120237350464f, 0.24022120237350464f));
+    p = zg_fma2(p, f, zg_pack2(0.6931469440460205f, 0.6931469440460205f));
+    p = zg_fma2(p, f, zg_pack2(1.0000001192092896f, 1.0000001192092896f));
+    float p0, p1, r0, r1;
+    zg_unpack2(p, p0, p1);
+    zg_unpack2(r, r0, r1);
+    p0 = __int_as_float(__float_as_int(p0) + (__float_as_int(r0) << 23));
+    p1 = __int_as_float(__float_as_int(p1) + (__float_as_int(r1) << 23));
+    return zg_pack2(p0, p1);
+}
+
 // cp.async (LDGSTS) 16-byte copy global -> shared, L2 only (streamed data, no L1 allocation)
 __device__ __forceinline__ void zg_cp_async16(void *smem_dst, const void *gmem_src) {
     const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
