@@ -4,7 +4,7 @@ mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw,memory.total --format=csv > gpurun_out/nvidia_smi.txt 2>&1
 nproc > gpurun_out/host.txt; free -g >> gpurun_out/host.txt
 echo "== debug"; [ -n "$DEBUG_SCRIPT" ] && timeout 300 python $DEBUG_SCRIPT > gpurun_out/debug.log 2>&1; [ -n "$DEBUG_SCRIPT" ] && tail -20 gpurun_out/debug.log
-if [ -n "$DO_SWEEP" ]; then echo "== scan sweep"; for n in 0 2 3 4; do ZG_SCAN_NPOLY=$n timeout 300 python scripts/scan_sweep.py 2>&1 | tail -1; done | tee gpurun_out/scan_sweep.log; fi
+if [ -n "$DO_SWEEP" ]; then echo "== scan sweep"; for n in ${SWEEP_SET:-0 2 3 4}; do ZG_SCAN_NPOLY=$n timeout 300 python scripts/scan_sweep.py 2>&1 | tail -1; done | tee gpurun_out/scan_sweep.log; fi
 echo "== smoke"; timeout 600 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?"; tail -5 gpurun_out/smoke.log
 echo "== pytest -m gpu"; timeout 2400 python -m pytest tests -m gpu -q -rA -p no:cacheprovider --timeout=900 ${PYTEST_EXTRA} > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"
 grep -E "^(PASSED|FAILED|ERROR)|passed|failed" gpurun_out/pytest_gpu.log | tail -100
@@ -15,6 +15,6 @@ if [ -n "$DO_NCU_LIST" ]; then
 echo "== ncu launch list"; timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off -c 400 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-ref-cuda --no-graph > gpurun_out/ncu_list.log 2>&1; echo "ncu rc=$?"
 fi
 if [ -n "$DO_NCU_FULL" ]; then
-echo "== ncu full (scan kernel)"; timeout 900 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:scan_fwd_kernel -c 2 -o gpurun_out/scan_fwd python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-ref-cuda --no-graph > gpurun_out/ncu_full.log 2>&1; echo "ncu full rc=$?"
+echo "== ncu full (scan kernel)"; timeout 900 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:${NCU_KERNEL:-scan_fwd_kernel} -c ${NCU_COUNT:-2} -o gpurun_out/${NCU_OUT:-scan_fwd} python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-ref-cuda --no-graph > gpurun_out/ncu_full.log 2>&1; echo "ncu full rc=$?"
 fi
 echo done

@@ -14,6 +14,7 @@
 namespace zg {
 
 constexpr int CONV_LCH = 32;   // tokens per thread, dim-contiguous kernels
+constexpr int CONV_RB = 8;     // rows fetched per batch of independent loads
 
 template <typename T, int VEC> struct VecT;  // VEC elements of T
 template <typename T> struct VecT<T, 1> { T e[1]; };
@@ -70,35 +71,48 @@ __global__ void __launch_bounds__(128) conv_fwd_dimc_kernel(const zg_conv_params
         for (int k = 0; k < 4; ++k)   // w[k] multiplies x[l - k]  (weight index W-1-k)
             w[k][i] = (ok && k < W) ? load_w_dt(p.weight, (int64_t)(e0 + i) * W + (W - 1 - k), p.wdtype) : 0.f;
     }
+    // rows are fetched in batches of CONV_RB: all CONV_RB 16-byte loads are issued before the first one is
+    // consumed (memory-level parallelism; the kernel streams ~335 MB per call at BASELINE config 2)
+    auto row_ptr = [&](int l) -> const T * {
+        const int64_t row = p.x_rowmap ? p.x_rowmap[l] : l;
+        return x + row * p.x_sl;
+    };
     auto load_row = [&](int l, float (&dst)[VEC]) {
         if (l < 0 || l >= L) {
 #pragma unroll
             for (int i = 0; i < VEC; ++i) dst[i] = 0.f;
             return;
         }
-        const int64_t row = p.x_rowmap ? p.x_rowmap[l] : l;
-        load_vec<T, VEC>(dst, x + row * p.x_sl);
+        load_vec<T, VEC>(dst, row_ptr(l));
     };
-    float x1[VEC], x2[VEC], x3[VEC], x0[VEC];   // x[l-1], x[l-2], x[l-3], x[l]
+    float x1[VEC], x2[VEC], x3[VEC];   // x[l-1], x[l-2], x[l-3]
     load_row(l0 - 1, x1);
     load_row(l0 - 2, x2);
     load_row(l0 - 3, x3);
     const int lend = min(l0 + CONV_LCH, L);
-#pragma unroll 4
-    for (int l = l0; l < lend; ++l) {
-        load_row(l, x0);
-        float o[VEC];
+    for (int lb = l0; lb < lend; lb += CONV_RB) {
+        VecT<T, VEC> raw[CONV_RB];
 #pragma unroll
-        for (int i = 0; i < VEC; ++i) {
-            float acc = bias[i];
-            acc = fmaf(w[3][i], x3[i], acc);
-            acc = fmaf(w[2][i], x2[i], acc);
-            acc = fmaf(w[1][i], x1[i], acc);
-            acc = fmaf(w[0][i], x0[i], acc);
-            o[i] = p.silu ? zg_silu(acc) : acc;
-            x3[i] = x2[i]; x2[i] = x1[i]; x1[i] = x0[i];
+        for (int j = 0; j < CONV_RB; ++j)
+            if (lb + j < lend) raw[j] = *reinterpret_cast<const VecT<T, VEC> *>(row_ptr(lb + j));
+#pragma unroll
+        for (int j = 0; j < CONV_RB; ++j) {
+            if (lb + j < lend) {
+                float o[VEC];
+#pragma unroll
+                for (int i = 0; i < VEC; ++i) {
+                    const float x0 = zg_to_float<T>(raw[j].e[i]);
+                    float acc = bias[i];
+                    acc = fmaf(w[3][i], x3[i], acc);
+                    acc = fmaf(w[2][i], x2[i], acc);
+                    acc = fmaf(w[1][i], x1[i], acc);
+                    acc = fmaf(w[0][i], x0, acc);
+                    o[i] = p.silu ? zg_silu(acc) : acc;
+                    x3[i] = x2[i]; x2[i] = x1[i]; x1[i] = x0;
+                }
+                store_vec<T, VEC>(out + (int64_t)(lb + j) * p.out_sl, o);
+            }
         }
-        store_vec<T, VEC>(out + (int64_t)l * p.out_sl, o);
     }
 }
 

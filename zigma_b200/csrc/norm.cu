@@ -184,7 +184,31 @@ __global__ void __launch_bounds__(128) add_norm_bwd_kernel(const zg_norm_bwd_par
 
 // ------------------------------------------------------------------------------------------------
 // Block tail (see include/zigma_b200.h).  One warp per token; all row operands are read exactly once.
-template <typename T>
+// MAXQ = quads (4 elements) per lane: D <= 128 * MAXQ.  The row operands are first pulled into registers
+// as RAW 8/16-byte vectors (all loads of a row in flight together -- the kernel is pure HBM streaming,
+// ~670 MB per call at BASELINE config 2), only then converted and combined.
+template <typename T> struct Raw4 { uint2 v; };                 // 4 x 16-bit
+template <> struct Raw4<float> { float4 v; };
+template <typename T> __device__ __forceinline__ Raw4<T> ldraw(const T *p, int64_t i) {
+    Raw4<T> r;
+    r.v = *reinterpret_cast<const decltype(r.v) *>(p + i);
+    return r;
+}
+template <typename T> __device__ __forceinline__ void cvt4(const Raw4<T> &r, float (&o)[4]);
+template <> __device__ __forceinline__ void cvt4<float>(const Raw4<float> &r, float (&o)[4]) {
+    o[0] = r.v.x; o[1] = r.v.y; o[2] = r.v.z; o[3] = r.v.w;
+}
+template <> __device__ __forceinline__ void cvt4<__nv_bfloat16>(const Raw4<__nv_bfloat16> &r, float (&o)[4]) {
+    o[0] = __uint_as_float(r.v.x << 16); o[1] = __uint_as_float(r.v.x & 0xffff0000u);
+    o[2] = __uint_as_float(r.v.y << 16); o[3] = __uint_as_float(r.v.y & 0xffff0000u);
+}
+template <> __device__ __forceinline__ void cvt4<__half>(const Raw4<__half> &r, float (&o)[4]) {
+    uint2 v = r.v;
+    float2 a = __half22float2(*reinterpret_cast<__half2 *>(&v.x)), b = __half22float2(*reinterpret_cast<__half2 *>(&v.y));
+    o[0] = a.x; o[1] = a.y; o[2] = b.x; o[3] = b.y;
+}
+
+template <typename T, int MAXQ>
 __global__ void __launch_bounds__(128) block_tail_kernel(const zg_block_tail_params p) {
     const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
@@ -207,26 +231,36 @@ __global__ void __launch_bounds__(128) block_tail_kernel(const zg_block_tail_par
     T *normed = reinterpret_cast<T *>(p.normed) + row * D;
     T *modded = p.modded ? reinterpret_cast<T *>(p.modded) + row * D : nullptr;
 
-    float r[NORM_MAXQ][4];
-    float sumsq = 0.f;
+    // ---- phase 1: every streaming load of the row, back to back ---------------------------------------
+    Raw4<T> rx[MAXQ], rm[MAXQ];
+    float4 rr[MAXQ];
 #pragma unroll
-    for (int k = 0; k < NORM_MAXQ; ++k) {
+    for (int k = 0; k < MAXQ; ++k) {
         const int q = lane + 32 * k;
         if (q < nq) {
-            ld4<T>(x, 4 * q, r[k]);
+            rx[k] = ldraw<T>(x, 4 * q);
+            if (mix) rm[k] = ldraw<T>(mix, 4 * q);
+            if (res) rr[k] = *reinterpret_cast<const float4 *>(res + 4 * q);
+        }
+    }
+    // ---- phase 2: hidden = x + gate * mix; r = residual + hidden; statistics -------------------------
+    float r[MAXQ][4];
+    float sumsq = 0.f;
+#pragma unroll
+    for (int k = 0; k < MAXQ; ++k) {
+        const int q = lane + 32 * k;
+        if (q < nq) {
+            cvt4<T>(rx[k], r[k]);
             if (mix) {
                 float m[4], g[4];
-                ld4<T>(mix, 4 * q, m);
+                cvt4<T>(rm[k], m);
                 ld4<T>(gate, 4 * q, g);
 #pragma unroll
                 for (int i = 0; i < 4; ++i)   // x + gate * mixer(...)  each op rounded to T as in eager torch
                     r[k][i] = round_to<T>(r[k][i] + round_to<T>(g[i] * m[i]));
             }
             if (res) {
-                float t[4];
-                ld4<float>(res, 4 * q, t);
-#pragma unroll
-                for (int i = 0; i < 4; ++i) r[k][i] += t[i];
+                r[k][0] += rr[k].x; r[k][1] += rr[k].y; r[k][2] += rr[k].z; r[k][3] += rr[k].w;
             }
             if (rout) st4<float>(rout, 4 * q, r[k]);
 #pragma unroll
@@ -236,7 +270,7 @@ __global__ void __launch_bounds__(128) block_tail_kernel(const zg_block_tail_par
     const float rstd = 1.f / sqrtf(zg_warp_sum(sumsq) / D + p.eps);
     float sum2 = 0.f;
 #pragma unroll
-    for (int k = 0; k < NORM_MAXQ; ++k) {
+    for (int k = 0; k < MAXQ; ++k) {
         const int q = lane + 32 * k;
         if (q < nq) {
             float w[4];
@@ -253,13 +287,13 @@ __global__ void __launch_bounds__(128) block_tail_kernel(const zg_block_tail_par
         const float mean = zg_warp_sum(sum2) / D;
         float s2 = 0.f;
 #pragma unroll
-        for (int k = 0; k < NORM_MAXQ; ++k)
+        for (int k = 0; k < MAXQ; ++k)
             if (lane + 32 * k < nq)
 #pragma unroll
                 for (int i = 0; i < 4; ++i) { const float d = r[k][i] - mean; s2 += d * d; }
         const float rstd2 = 1.f / sqrtf(zg_warp_sum(s2) / D + 1e-6f);
 #pragma unroll
-        for (int k = 0; k < NORM_MAXQ; ++k) {
+        for (int k = 0; k < MAXQ; ++k) {
             const int q = lane + 32 * k;
             if (q < nq) {
                 float o[4];
@@ -271,7 +305,7 @@ __global__ void __launch_bounds__(128) block_tail_kernel(const zg_block_tail_par
         return;
     }
 #pragma unroll
-    for (int k = 0; k < NORM_MAXQ; ++k) {
+    for (int k = 0; k < MAXQ; ++k) {
         const int q = lane + 32 * k;
         if (q < nq) {
             st4<T>(normed, 4 * q, r[k]);
@@ -286,6 +320,16 @@ __global__ void __launch_bounds__(128) block_tail_kernel(const zg_block_tail_par
             }
         }
     }
+}
+
+template <typename T> static int block_tail_t(const zg_block_tail_params &p, cudaStream_t s) {
+    const int64_t nrows = (int64_t)p.batch * p.seqlen;
+    const unsigned grid = (unsigned)((nrows * 32 + 127) / 128);
+    if (p.dim <= 512) block_tail_kernel<T, 4><<<grid, 128, 0, s>>>(p);
+    else if (p.dim <= 1024) block_tail_kernel<T, 8><<<grid, 128, 0, s>>>(p);
+    else block_tail_kernel<T, NORM_MAXQ><<<grid, 128, 0, s>>>(p);
+    zg_count_launch();
+    return zg_check_launch("block_tail_fwd");
 }
 
 template <typename T, typename R> static int norm_fwd_tr(const zg_norm_params &p, cudaStream_t s) {
@@ -363,13 +407,10 @@ extern "C" int zg_block_tail_fwd(const zg_block_tail_params *pp, void *stream) {
     const int64_t nrows = (int64_t)p.batch * p.seqlen;
     if (nrows == 0) return 0;
     cudaStream_t s = (cudaStream_t)stream;
-    const unsigned grid = (unsigned)((nrows * 32 + 127) / 128);
     switch (p.dtype) {
-        case ZG_F32: zg::block_tail_kernel<float><<<grid, 128, 0, s>>>(p); break;
-        case ZG_F16: zg::block_tail_kernel<__half><<<grid, 128, 0, s>>>(p); break;
-        case ZG_BF16: zg::block_tail_kernel<__nv_bfloat16><<<grid, 128, 0, s>>>(p); break;
-        default: return zg_set_error("block_tail_fwd: bad dtype %d", p.dtype);
+        case ZG_F32: return zg::block_tail_t<float>(p, s);
+        case ZG_F16: return zg::block_tail_t<__half>(p, s);
+        case ZG_BF16: return zg::block_tail_t<__nv_bfloat16>(p, s);
     }
-    zg_count_launch();
-    return zg_check_launch("block_tail_fwd");
+    return zg_set_error("block_tail_fwd: bad dtype %d", p.dtype);
 }

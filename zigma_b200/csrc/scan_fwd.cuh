@@ -67,7 +67,7 @@ template <typename T, int NS, bool SEQ, bool CONSTBC, int NPOLY>
 __global__ void __launch_bounds__(SCAN_CH, (NS <= 16 && !CONSTBC) ? SCAN_MIN_CTAS : 1) scan_fwd_kernel(const zg_scan_params p) {
     using SM = ScanSmem<T, SEQ>;
     constexpr int VEC = SM::VEC;
-    constexpr int TL = SCAN_TL, CH = SCAN_CH, NSTAGE = SM::NSTAGE;
+    constexpr int TL = SCAN_TL, CH = SCAN_CH, NSTAGE = SM::NSTAGE, SB = SCAN_SB, NP = NS / 2;
     extern __shared__ __align__(16) unsigned char smem[];
     float *bcf = reinterpret_cast<float *>(smem + NSTAGE * SM::stage_bytes(NS));   // [TL][2*NS]
 
@@ -98,16 +98,14 @@ __global__ void __launch_bounds__(SCAN_CH, (NS <= 16 && !CONSTBC) ? SCAN_MIN_CTA
     // ---- per-thread constants and state --------------------------------------------------------
     // states live in registers as fp32x2 PAIRS (n, n+1): every FMA-pipe instruction of the inner loop
     // is a packed FFMA2/FMUL2, halving the issue slots of the recurrence.
-    constexpr int NP = NS / 2;
     zg_f2 Al2p[NP], h2[NP];
     float Bc[CONSTBC ? NS : 1], Cc[CONSTBC ? NS : 1];
 #pragma unroll
     for (int q = 0; q < NP; ++q) {
         const int n = 2 * q;
-        const float a0 = (active && n < N) ? p.A[(int64_t)e * N + n] * ZG_LOG2E : 0.f;
-        const float a1 = (active && n + 1 < N) ? p.A[(int64_t)e * N + n + 1] * ZG_LOG2E : 0.f;
-        Al2p[q] = zg_pack2(a0, a1);
-        h2[q] = zg_pack2(0.f, 0.f);
+        Al2p[q].x = (active && n < N) ? p.A[(int64_t)e * N + n] * ZG_LOG2E : 0.f;
+        Al2p[q].y = (active && n + 1 < N) ? p.A[(int64_t)e * N + n + 1] * ZG_LOG2E : 0.f;
+        h2[q] = zg_splat2(0.f);
     }
     if (CONSTBC) {
 #pragma unroll
@@ -121,11 +119,25 @@ __global__ void __launch_bounds__(SCAN_CH, (NS <= 16 && !CONSTBC) ? SCAN_MIN_CTA
 
     const int nstages = (L + TL - 1) / TL;
 
+    // The streaming loads have a fast form (every 16-byte chunk complete and aligned -> bare cp.async,
+    // no per-chunk checks) chosen once per CTA, and a generic form for ragged / unaligned tensors.
+    bool fast;
+    {
+        const uintptr_t al = reinterpret_cast<uintptr_t>(p.u) | reinterpret_cast<uintptr_t>(p.delta) | reinterpret_cast<uintptr_t>(p.z) |
+                             (varB ? reinterpret_cast<uintptr_t>(p.B) : 0) | (varC ? reinterpret_cast<uintptr_t>(p.C) : 0);
+        const int64_t st_or = p.u_sb | p.delta_sb | (has_z ? p.z_sb : 0) | (varB ? (p.B_sb | p.B_sg) : 0) | (varC ? (p.C_sb | p.C_sg) : 0) |
+                              (SEQ ? (p.u_sd | p.delta_sd | (has_z ? p.z_sd : 0) | (varB ? p.B_sn : 0) | (varC ? p.C_sn : 0))
+                                   : (p.u_sl | p.delta_sl | (has_z ? p.z_sl : 0) | (varB ? p.B_sl : 0) | (varC ? p.C_sl : 0)));
+        fast = (al % 16 == 0) && (st_or % VEC == 0) && (e_end - e0 == CH) && (e0 % VEC == 0) && varB && varC &&
+               (SEQ ? true : (N == NS));
+    }
+
     // ---- stage loader ---------------------------------------------------------------------------
     auto issue_stage = [&](int s) {
         if (s < nstages) {
             unsigned char *st = smem + (s % NSTAGE) * SM::stage_bytes(NS);
             const int l0 = s * TL;
+            const bool full = fast && (l0 + TL <= L);
             if (SEQ) {
                 constexpr int CPR = TL * (int)sizeof(T) / 16;      // 16-byte chunks per row
                 const int nk = has_z ? 3 : 2;
@@ -133,14 +145,18 @@ __global__ void __launch_bounds__(SCAN_CH, (NS <= 16 && !CONSTBC) ? SCAN_MIN_CTA
                     const int k = it / (CH * CPR), rem = it % (CH * CPR);
                     const int c = rem / CPR, j = rem % CPR;
                     const int ee = e0 + c;
-                    if (ee >= e_end) continue;
                     const int l = l0 + j * VEC;
-                    const int nvalid = min(L - l, VEC);
-                    if (nvalid <= 0) continue;
                     const T *src = (k == 0) ? gu + (int64_t)ee * p.u_sd + l
                                  : (k == 1) ? gd + (int64_t)ee * p.delta_sd + l
                                             : gz + (int64_t)ee * p.z_sd + l;
-                    copy_chunk<T>(reinterpret_cast<T *>(st + k * SM::ACT_BYTES + c * SM::ACT_ROW_BYTES + j * 16), src, nvalid);
+                    T *dst = reinterpret_cast<T *>(st + k * SM::ACT_BYTES + c * SM::ACT_ROW_BYTES + j * 16);
+                    if (full) {
+                        zg_cp_async16(dst, src);
+                    } else {
+                        if (ee >= e_end) continue;
+                        const int nvalid = min(L - l, VEC);
+                        if (nvalid > 0) copy_chunk<T>(dst, src, nvalid);
+                    }
                 }
                 // B / C rows: raw[n][TL]
                 const int nbc = (varB ? 1 : 0) + (varC ? 1 : 0);
@@ -149,11 +165,14 @@ __global__ void __launch_bounds__(SCAN_CH, (NS <= 16 && !CONSTBC) ? SCAN_MIN_CTA
                     const int n = rem / CPR, j = rem % CPR;
                     const bool isB = varB && (w == 0);
                     const int l = l0 + j * VEC;
-                    const int nvalid = min(L - l, VEC);
-                    if (nvalid <= 0) continue;
                     const T *src = isB ? gB + (int64_t)n * p.B_sn + l : gC + (int64_t)n * p.C_sn + l;
                     T *dst = reinterpret_cast<T *>(st + 3 * SM::ACT_BYTES + (isB ? 0 : SM::raw_bc_bytes(NS))) + n * TL + j * VEC;
-                    copy_chunk<T>(dst, src, nvalid);
+                    if (full) {
+                        zg_cp_async16(dst, src);
+                    } else {
+                        const int nvalid = min(L - l, VEC);
+                        if (nvalid > 0) copy_chunk<T>(dst, src, nvalid);
+                    }
                 }
             } else {
                 constexpr int CPR = CH * (int)sizeof(T) / 16;      // chunks per token row
@@ -162,15 +181,19 @@ __global__ void __launch_bounds__(SCAN_CH, (NS <= 16 && !CONSTBC) ? SCAN_MIN_CTA
                     const int k = it / (TL * CPR), rem = it % (TL * CPR);
                     const int t = rem / CPR, j = rem % CPR;
                     const int l = l0 + t;
-                    if (l >= L) continue;
+                    if (!full && l >= L) continue;
                     const int ee = e0 + j * VEC;
-                    const int nvalid = min(e_end - ee, VEC);
-                    if (nvalid <= 0) continue;
                     const T *src;
                     if (k == 0) src = gu + (int64_t)l * p.u_sl + ee;
                     else if (k == 1) src = gd + (int64_t)l * p.delta_sl + ee;
                     else src = gz + (int64_t)(p.z_rowmap ? p.z_rowmap[l] : l) * p.z_sl + ee;
-                    copy_chunk<T>(reinterpret_cast<T *>(st + k * SM::ACT_BYTES + t * SM::ACT_ROW_BYTES + j * 16), src, nvalid);
+                    T *dst = reinterpret_cast<T *>(st + k * SM::ACT_BYTES + t * SM::ACT_ROW_BYTES + j * 16);
+                    if (full) {
+                        zg_cp_async16(dst, src);
+                    } else {
+                        const int nvalid = min(e_end - ee, VEC);
+                        if (nvalid > 0) copy_chunk<T>(dst, src, nvalid);
+                    }
                 }
                 // B / C: raw[t][NS] (state contiguous)
                 constexpr int BPR = (NS * (int)sizeof(T) + 15) / 16;
@@ -180,13 +203,16 @@ __global__ void __launch_bounds__(SCAN_CH, (NS <= 16 && !CONSTBC) ? SCAN_MIN_CTA
                     const int t = rem / BPR, j = rem % BPR;
                     const bool isB = varB && (w == 0);
                     const int l = l0 + t;
-                    if (l >= L) continue;
+                    if (!full && l >= L) continue;
                     const int n0 = j * VEC;
-                    const int nvalid = min(N - n0, VEC);
-                    if (nvalid <= 0) continue;
                     const T *src = isB ? gB + (int64_t)l * p.B_sl + n0 : gC + (int64_t)l * p.C_sl + n0;
                     T *dst = reinterpret_cast<T *>(st + 3 * SM::ACT_BYTES + (isB ? 0 : SM::raw_bc_bytes(NS))) + t * NS + n0;
-                    copy_chunk<T>(dst, src, nvalid);
+                    if (full) {
+                        zg_cp_async16(dst, src);
+                    } else {
+                        const int nvalid = min(N - n0, VEC);
+                        if (nvalid > 0) copy_chunk<T>(dst, src, nvalid);
+                    }
                 }
             }
         }
@@ -199,22 +225,20 @@ __global__ void __launch_bounds__(SCAN_CH, (NS <= 16 && !CONSTBC) ? SCAN_MIN_CTA
     // instructions + 2 exp2 per state PAIR and step:
     //     x = dl * A'      a = 2^x      h = a * h + (dl*u) * B      y += C * h
     // The first NPOLY pairs take 2^x from the FMA-pipe polynomial (zg_ex2_poly2), the rest from MUFU.
-    auto block = [&](int t0, const float (&uu)[SCAN_SB], const float (&dd)[SCAN_SB], const float (&zz)[SCAN_SB],
-                     float (&y)[SCAN_SB]) {
-        zg_f2 dl2[SCAN_SB], du2[SCAN_SB], y2[SCAN_SB];
+    auto block = [&](int t0, const float (&uu)[SB], const float (&dd)[SB], const float (&zz)[SB], float (&y)[SB]) {
+        zg_f2 dl2[SB], du2[SB], y2[SB];
 #pragma unroll
-        for (int i = 0; i < SCAN_SB; ++i) {
+        for (int i = 0; i < SB; ++i) {
             float dl = dd[i] + bias;
             if (softplus) dl = zg_softplus20(dl);
-            const float du = dl * uu[i];
-            dl2[i] = zg_pack2(dl, dl);
-            du2[i] = zg_pack2(du, du);
+            dl2[i] = zg_splat2(dl);
+            du2[i] = zg_splat2(dl * uu[i]);
             y2[i] = zg_pack2(Dv * uu[i], 0.f);
         }
 #pragma unroll
         for (int q = 0; q < NP; ++q) {
 #pragma unroll
-            for (int i = 0; i < SCAN_SB; ++i) {
+            for (int i = 0; i < SB; ++i) {
                 const float2 *bc = reinterpret_cast<const float2 *>(bcf + (t0 + i) * 2 * NS);
                 float2 Bv = bc[q], Cv = bc[NP + q];
                 if (CONSTBC) {
@@ -223,30 +247,27 @@ __global__ void __launch_bounds__(SCAN_CH, (NS <= 16 && !CONSTBC) ? SCAN_MIN_CTA
                 }
                 const zg_f2 x = zg_mul2(dl2[i], Al2p[q]);
                 const zg_f2 a = (q < NPOLY) ? zg_ex2_poly2(x) : zg_ex2_mufu2(x);
-                h2[q] = zg_fma2(a, h2[q], zg_mul2(du2[i], zg_pack2(Bv.x, Bv.y)));
-                y2[i] = zg_fma2(zg_pack2(Cv.x, Cv.y), h2[q], y2[i]);
+                h2[q] = zg_fma2(a, h2[q], zg_mul2(du2[i], Bv));
+                y2[i] = zg_fma2(Cv, h2[q], y2[i]);
             }
         }
 #pragma unroll
-        for (int i = 0; i < SCAN_SB; ++i) {
-            float lo, hi;
-            zg_unpack2(y2[i], lo, hi);
-            float v = lo + hi;
+        for (int i = 0; i < SB; ++i) {
+            float v = y2[i].x + y2[i].y;
             if (has_z) v *= zg_silu(zz[i]);
             y[i] = v;
         }
     };
-    // a partial block at the ragged end of the sequence: inputs beyond nb are the identity step
-    // (delta' = 0 -> a = 1, b = 0), selective_scan_fwd_kernel.cuh:218-222
     auto store_state = [&](float *dst) {
 #pragma unroll
         for (int q = 0; q < NP; ++q) {
-            float lo, hi;
-            zg_unpack2(h2[q], lo, hi);
-            if (2 * q < N) dst[2 * q] = lo;
-            if (2 * q + 1 < N) dst[2 * q + 1] = hi;
+            if (2 * q < N) dst[2 * q] = h2[q].x;
+            if (2 * q + 1 < N) dst[2 * q + 1] = h2[q].y;
         }
     };
+    // a step beyond the end of the sequence inside a partial block is the identity (delta' = 0 -> a = 1,
+    // b = 0), selective_scan_fwd_kernel.cuh:218-222
+    const float pad_delta = (softplus ? -1e30f : 0.f) - bias;
 
     // ---- pipeline -------------------------------------------------------------------------------
 #pragma unroll
@@ -259,20 +280,33 @@ __global__ void __launch_bounds__(SCAN_CH, (NS <= 16 && !CONSTBC) ? SCAN_MIN_CTA
         unsigned char *st = smem + (s % NSTAGE) * SM::stage_bytes(NS);
         const int l0 = s * TL;
         const int nsteps = min(TL, L - l0);
+        const bool full = fast && nsteps == TL;
         // raw B/C (I/O dtype) -> fp32 [t][B0..B(NS-1) C0..C(NS-1)], zero padded
         {
             const T *rawB = reinterpret_cast<const T *>(st + 3 * SM::ACT_BYTES);
             const T *rawC = reinterpret_cast<const T *>(st + 3 * SM::ACT_BYTES + SM::raw_bc_bytes(NS));
-            for (int it = tid; it < 2 * TL * NS; it += CH) {
-                const int w = it / (TL * NS), rem = it % (TL * NS);
-                int t, n;
-                if (SEQ) { n = rem / TL; t = rem % TL; } else { t = rem / NS; n = rem % NS; }
-                float v = 0.f;
-                if (n < N && t < nsteps) {
-                    if (w == 0 && varB) v = zg_to_float<T>(SEQ ? rawB[n * TL + t] : rawB[t * NS + n]);
-                    if (w == 1 && varC) v = zg_to_float<T>(SEQ ? rawC[n * TL + t] : rawC[t * NS + n]);
+            if (!SEQ && full && sizeof(T) == 2 && NS == 16) {
+                // one 16-byte chunk (8 states of one step) per thread: 2 (B, C) x 16 steps x 2 halves = 64
+                const int w = tid >> 5, t = (tid >> 1) & 15, hf = tid & 1;
+                union { uint4 v; T e[8]; } R;
+                R.v = *reinterpret_cast<const uint4 *>((w ? rawC : rawB) + t * NS + hf * 8);
+                float4 o0, o1;
+                o0.x = zg_to_float<T>(R.e[0]); o0.y = zg_to_float<T>(R.e[1]); o0.z = zg_to_float<T>(R.e[2]); o0.w = zg_to_float<T>(R.e[3]);
+                o1.x = zg_to_float<T>(R.e[4]); o1.y = zg_to_float<T>(R.e[5]); o1.z = zg_to_float<T>(R.e[6]); o1.w = zg_to_float<T>(R.e[7]);
+                float4 *d4 = reinterpret_cast<float4 *>(bcf + t * 2 * NS + w * NS + hf * 8);
+                d4[0] = o0; d4[1] = o1;
+            } else {
+                for (int it = tid; it < 2 * TL * NS; it += CH) {
+                    const int w = it / (TL * NS), rem = it % (TL * NS);
+                    int t, n;
+                    if (SEQ) { n = rem / TL; t = rem % TL; } else { t = rem / NS; n = rem % NS; }
+                    float v = 0.f;
+                    if (n < N && t < nsteps) {
+                        if (w == 0 && varB) v = zg_to_float<T>(SEQ ? rawB[n * TL + t] : rawB[t * NS + n]);
+                        if (w == 1 && varC) v = zg_to_float<T>(SEQ ? rawC[n * TL + t] : rawC[t * NS + n]);
+                    }
+                    bcf[t * 2 * NS + w * NS + n] = v;
                 }
-                bcf[t * 2 * NS + w * NS + n] = v;
             }
         }
         __syncthreads();
@@ -292,24 +326,32 @@ __global__ void __launch_bounds__(SCAN_CH, (NS <= 16 && !CONSTBC) ? SCAN_MIN_CTA
                     Dl.v = *reinterpret_cast<const uint4 *>(rd + tv * 16);
                     if (has_z) Z.v = *reinterpret_cast<const uint4 *>(rz + tv * 16);
 #pragma unroll
-                    for (int sb = 0; sb < VEC / SCAN_SB; ++sb) {
-                        const int t0 = tv * VEC + sb * SCAN_SB;
-                        if (t0 < nsteps) {
-                            float uu[SCAN_SB], dd[SCAN_SB], zz[SCAN_SB], y[SCAN_SB];
+                    for (int sb = 0; sb < VEC / SB; ++sb) {
+                        const int t0 = tv * VEC + sb * SB;
+                        float uu[SB], dd[SB], zz[SB], y[SB];
+                        if (full) {
 #pragma unroll
-                            for (int i = 0; i < SCAN_SB; ++i) {
-                                const bool ok = t0 + i < nsteps;      // beyond L: identity step
-                                uu[i] = ok ? zg_to_float<T>(U.e[sb * SCAN_SB + i]) : 0.f;
-                                dd[i] = ok ? zg_to_float<T>(Dl.e[sb * SCAN_SB + i]) : (softplus ? -1e30f : 0.f) - bias;
-                                zz[i] = (ok && has_z) ? zg_to_float<T>(Z.e[sb * SCAN_SB + i]) : 0.f;
+                            for (int i = 0; i < SB; ++i) {
+                                uu[i] = zg_to_float<T>(U.e[sb * SB + i]);
+                                dd[i] = zg_to_float<T>(Dl.e[sb * SB + i]);
+                                zz[i] = has_z ? zg_to_float<T>(Z.e[sb * SB + i]) : 0.f;
                             }
-                            block(t0, uu, dd, zz, y);
+                        } else {
+                            if (t0 >= nsteps) continue;
 #pragma unroll
-                            for (int i = 0; i < SCAN_SB; ++i) O.e[sb * SCAN_SB + i] = zg_from_float<T>(y[i]);
+                            for (int i = 0; i < SB; ++i) {
+                                const bool ok = t0 + i < nsteps;
+                                uu[i] = ok ? zg_to_float<T>(U.e[sb * SB + i]) : 0.f;
+                                dd[i] = ok ? zg_to_float<T>(Dl.e[sb * SB + i]) : pad_delta;
+                                zz[i] = (ok && has_z) ? zg_to_float<T>(Z.e[sb * SB + i]) : 0.f;
+                            }
                         }
+                        block(t0, uu, dd, zz, y);
+#pragma unroll
+                        for (int i = 0; i < SB; ++i) O.e[sb * SB + i] = zg_from_float<T>(y[i]);
                     }
                     T *dst = orow + tv * VEC;
-                    if (tv * VEC + VEC <= nsteps && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+                    if (full || (tv * VEC + VEC <= nsteps && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0))) {
                         *reinterpret_cast<uint4 *>(dst) = O.v;
                     } else {
 #pragma unroll
@@ -322,20 +364,36 @@ __global__ void __launch_bounds__(SCAN_CH, (NS <= 16 && !CONSTBC) ? SCAN_MIN_CTA
                 const T *sd = reinterpret_cast<const T *>(st + 1 * SM::ACT_BYTES) + tid;
                 const T *sz = reinterpret_cast<const T *>(st + 2 * SM::ACT_BYTES) + tid;
                 T *ocol = gout + (int64_t)l0 * p.out_sl + e;
+                if (nsteps == TL) {
 #pragma unroll 1
-                for (int t0 = 0; t0 < nsteps; t0 += SCAN_SB) {
-                    float uu[SCAN_SB], dd[SCAN_SB], zz[SCAN_SB], y[SCAN_SB];
+                    for (int t0 = 0; t0 < TL; t0 += SB) {
+                        float uu[SB], dd[SB], zz[SB], y[SB];
 #pragma unroll
-                    for (int i = 0; i < SCAN_SB; ++i) {
-                        const bool ok = t0 + i < nsteps;
-                        uu[i] = ok ? zg_to_float<T>(su[(t0 + i) * CH]) : 0.f;
-                        dd[i] = ok ? zg_to_float<T>(sd[(t0 + i) * CH]) : (softplus ? -1e30f : 0.f) - bias;
-                        zz[i] = (ok && has_z) ? zg_to_float<T>(sz[(t0 + i) * CH]) : 0.f;
+                        for (int i = 0; i < SB; ++i) {
+                            uu[i] = zg_to_float<T>(su[(t0 + i) * CH]);
+                            dd[i] = zg_to_float<T>(sd[(t0 + i) * CH]);
+                            zz[i] = has_z ? zg_to_float<T>(sz[(t0 + i) * CH]) : 0.f;
+                        }
+                        block(t0, uu, dd, zz, y);
+#pragma unroll
+                        for (int i = 0; i < SB; ++i) ocol[(int64_t)(t0 + i) * p.out_sl] = zg_from_float<T>(y[i]);
                     }
-                    block(t0, uu, dd, zz, y);
+                } else {
+#pragma unroll 1
+                    for (int t0 = 0; t0 < nsteps; t0 += SB) {
+                        float uu[SB], dd[SB], zz[SB], y[SB];
 #pragma unroll
-                    for (int i = 0; i < SCAN_SB; ++i)
-                        if (t0 + i < nsteps) ocol[(int64_t)(t0 + i) * p.out_sl] = zg_from_float<T>(y[i]);
+                        for (int i = 0; i < SB; ++i) {
+                            const bool ok = t0 + i < nsteps;
+                            uu[i] = ok ? zg_to_float<T>(su[(t0 + i) * CH]) : 0.f;
+                            dd[i] = ok ? zg_to_float<T>(sd[(t0 + i) * CH]) : pad_delta;
+                            zz[i] = (ok && has_z) ? zg_to_float<T>(sz[(t0 + i) * CH]) : 0.f;
+                        }
+                        block(t0, uu, dd, zz, y);
+#pragma unroll
+                        for (int i = 0; i < SB; ++i)
+                            if (t0 + i < nsteps) ocol[(int64_t)(t0 + i) * p.out_sl] = zg_from_float<T>(y[i]);
+                    }
                 }
             }
             // recompute seeds for the backward pass

@@ -55,75 +55,47 @@ __device__ __forceinline__ float zg_rcp(float x) {
 // log1p(exp(x)) : x.  exp via MUFU.EX2; log1p via a series for tiny e (where lg2.approx of 1+e has
 // no relative accuracy) and MUFU.LG2 otherwise.  Relative error < 2e-6 over the whole range.
 __device__ __forceinline__ float zg_softplus20(float x) {
-    if (x > 20.f) return x;
-    const float e = zg_ex2(x * ZG_LOG2E);
-    if (e < 0.03125f) {
-        // log1p(e) = e - e^2/2 + e^3/3 - e^4/4 + e^5/5   (|err| < e^6/6 < 2e-10 * e)
-        return e * (1.f + e * (-0.5f + e * (0.33333334f + e * (-0.25f + e * 0.2f))));
-    }
-    return zg_lg2(1.f + e) * ZG_LN2;
+    // branch free (selects): the scan's inner loop must not pay divergence bookkeeping per step
+    const float e = zg_ex2(fminf(x, 20.f) * ZG_LOG2E);
+    // log1p(e) = e - e^2/2 + e^3/3 - e^4/4 + e^5/5   (|err| < e^6/6 < 2e-10 * e for e < 1/32)
+    const float series = e * (1.f + e * (-0.5f + e * (0.33333334f + e * (-0.25f + e * 0.2f))));
+    const float viaLog = zg_lg2(1.f + e) * ZG_LN2;
+    const float sp = (e < 0.03125f) ? series : viaLog;
+    return (x > 20.f) ? x : sp;
 }
 
 __device__ __forceinline__ float zg_sigmoid(float x) { return zg_rcp(1.f + zg_ex2(-x * ZG_LOG2E)); }
 __device__ __forceinline__ float zg_silu(float x) { return x * zg_sigmoid(x); }
 
 // ---- packed fp32x2 arithmetic (FFMA2 / FMUL2 / FADD2 on sm_100a: one issue slot, two results) ----
-typedef unsigned long long zg_f2;
-__device__ __forceinline__ zg_f2 zg_pack2(float lo, float hi) {
-    zg_f2 r;
-    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-    return r;
-}
-__device__ __forceinline__ void zg_unpack2(zg_f2 v, float &lo, float &hi) {
-    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
-}
-__device__ __forceinline__ zg_f2 zg_fma2(zg_f2 a, zg_f2 b, zg_f2 c) {
-    zg_f2 d;
-    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
-    return d;
-}
-__device__ __forceinline__ zg_f2 zg_mul2(zg_f2 a, zg_f2 b) {
-    zg_f2 d;
-    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-    return d;
-}
-__device__ __forceinline__ zg_f2 zg_add2(zg_f2 a, zg_f2 b) {
-    zg_f2 d;
-    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-    return d;
-}
+// float2 + the CUDA 12.8+ sm_100 intrinsics, so ptxas allocates the aligned register pairs itself.
+typedef float2 zg_f2;
+__device__ __forceinline__ zg_f2 zg_pack2(float lo, float hi) { return make_float2(lo, hi); }
+__device__ __forceinline__ zg_f2 zg_splat2(float v) { return make_float2(v, v); }
+__device__ __forceinline__ zg_f2 zg_fma2(zg_f2 a, zg_f2 b, zg_f2 c) { return __ffma2_rn(a, b, c); }
+__device__ __forceinline__ zg_f2 zg_mul2(zg_f2 a, zg_f2 b) { return __fmul2_rn(a, b); }
+__device__ __forceinline__ zg_f2 zg_add2(zg_f2 a, zg_f2 b) { return __fadd2_rn(a, b); }
 // 2^x for two lanes at once via MUFU.EX2 (2 MUFU issues)
-__device__ __forceinline__ zg_f2 zg_ex2_mufu2(zg_f2 x) {
-    float a, b;
-    zg_unpack2(x, a, b);
-    return zg_pack2(zg_ex2(a), zg_ex2(b));
-}
+__device__ __forceinline__ zg_f2 zg_ex2_mufu2(zg_f2 x) { return make_float2(zg_ex2(x.x), zg_ex2(x.y)); }
 // 2^x for two lanes on the FMA/ALU pipes only (no MUFU): Cody-Waite split x = i + f, |f| <= 0.5,
 // 2^f by a degree-5 minimax polynomial (max relative error 2.3e-7 in fp32 Horner form -- the same as
 // ex2.approx's 2^-22), 2^i by adding i to the exponent field.  x is clamped to [-126, 126].
-// Used to take part of the exp load off the 16-lane/SM MUFU pipe, which bounds the selective scan.
+// Used to take part of the exp load off the 16-lane/SM MUFU pipe when that pipe bounds the scan.
 __device__ __forceinline__ zg_f2 zg_ex2_poly2(zg_f2 x) {
-    float a, b;
-    zg_unpack2(x, a, b);
-    a = fminf(fmaxf(a, -126.f), 126.f);
-    b = fminf(fmaxf(b, -126.f), 126.f);
-    x = zg_pack2(a, b);
-    const zg_f2 magic = zg_pack2(12582912.f, 12582912.f);          // 1.5 * 2^23: low mantissa bits = round(x)
-    const zg_f2 r = zg_add2(x, magic);
-    const zg_f2 xi = zg_add2(r, zg_pack2(-12582912.f, -12582912.f));
-    const zg_f2 f = zg_fma2(xi, zg_pack2(-1.f, -1.f), x);
-    zg_f2 p = zg_pack2(0.001327647129073739f, 0.001327647129073739f);
-    p = zg_fma2(p, f, zg_pack2(0.009675540961325169f, 0.009675540961325169f));
-    p = zg_fma2(p, f, zg_pack2(0.05550713092088699f, 0.05550713092088699f));
-    p = zg_fma2(p, f, zg_pack2(0.24022120237350464f, 0.24022120237350464f));
-    p = zg_fma2(p, f, zg_pack2(0.6931469440460205f, 0.6931469440460205f));
-    p = zg_fma2(p, f, zg_pack2(1.0000001192092896f, 1.0000001192092896f));
-    float p0, p1, r0, r1;
-    zg_unpack2(p, p0, p1);
-    zg_unpack2(r, r0, r1);
-    p0 = __int_as_float(__float_as_int(p0) + (__float_as_int(r0) << 23));
-    p1 = __int_as_float(__float_as_int(p1) + (__float_as_int(r1) << 23));
-    return zg_pack2(p0, p1);
+    x.x = fminf(fmaxf(x.x, -126.f), 126.f);
+    x.y = fminf(fmaxf(x.y, -126.f), 126.f);
+    const zg_f2 r = zg_add2(x, zg_splat2(12582912.f));              // 1.5 * 2^23: low mantissa bits = round(x)
+    const zg_f2 xi = zg_add2(r, zg_splat2(-12582912.f));
+    const zg_f2 f = zg_fma2(xi, zg_splat2(-1.f), x);
+    zg_f2 p = zg_splat2(0.001327647129073739f);
+    p = zg_fma2(p, f, zg_splat2(0.009675540961325169f));
+    p = zg_fma2(p, f, zg_splat2(0.05550713092088699f));
+    p = zg_fma2(p, f, zg_splat2(0.24022120237350464f));
+    p = zg_fma2(p, f, zg_splat2(0.6931469440460205f));
+    p = zg_fma2(p, f, zg_splat2(1.0000001192092896f));
+    p.x = __int_as_float(__float_as_int(p.x) + (__float_as_int(r.x) << 23));
+    p.y = __int_as_float(__float_as_int(p.y) + (__float_as_int(r.y) << 23));
+    return p;
 }
 
 // cp.async (LDGSTS) 16-byte copy global -> shared, L2 only (streamed data, no L1 allocation)
