@@ -1,0 +1,25 @@
+"""Prints the judged subset of an `ncu --set full` report (one block per profiled launch)."""
+import csv, subprocess, sys
+KEYS = ["Kernel Name", "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+        "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+        "launch__grid_size", "launch__block_size", "launch__registers_per_thread", "launch__waves_per_multiprocessor",
+        "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem", "sm__warps_active.avg.pct_of_peak_sustained_active",
+        "smsp__warps_active.avg.per_cycle_active", "smsp__warps_eligible.avg.per_cycle_active",
+        "smsp__inst_executed.sum", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active", "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active",
+        "sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
+        "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
+        "smsp__cycles_active.avg", "lts__t_sector_hit_rate.pct"]
+rep = sys.argv[1]
+out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+rows = list(csv.reader(out.splitlines()))
+h, units = rows[0], rows[1]
+for r in rows[2:]:
+    print("-" * 100)
+    for k in KEYS:
+        if k in h:
+            i = h.index(k)
+            print(f"{k:75s} {r[i]:>22s} {units[i]}")
+    stalls = sorted(((float(r[i].replace(',', '') or 0), k) for i, k in enumerate(h) if "warp_issue_stalled" in k and k.endswith("_per_warp_active.pct")), reverse=True)
+    for v, k in stalls[:6]:
+        print(f"  stall {k.replace('smsp__warp_issue_stalled_', '').replace('_per_warp_active.pct', ''):40s} {v:8.2f} %")

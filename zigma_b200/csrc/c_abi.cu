@@ -65,9 +65,3 @@ int zg_selective_scan_fwd(const zg_scan_params *pp, void *stream) {
 
 }  // extern "C"
 
-// ---- entry points implemented in later files fall back to a loud error until they exist -------------
-#ifndef ZG_HAVE_GEMM
-extern "C" int zg_gemm_bf16_tn(const zg_gemm_params *, void *) {
-    return zg_set_error("gemm_bf16_tn: not built into this library");
-}
-#endif

@@ -21,6 +21,8 @@ template <typename T> struct VecT<T, 1> { T e[1]; };
 template <> struct alignas(16) VecT<float, 4> { float e[4]; };
 template <> struct alignas(16) VecT<__half, 8> { __half e[8]; };
 template <> struct alignas(16) VecT<__nv_bfloat16, 8> { __nv_bfloat16 e[8]; };
+template <> struct alignas(8) VecT<__half, 4> { __half e[4]; };
+template <> struct alignas(8) VecT<__nv_bfloat16, 4> { __nv_bfloat16 e[4]; };
 
 template <typename T, int VEC>
 __device__ __forceinline__ void load_vec(float (&dst)[VEC], const T *src) {
@@ -48,7 +50,7 @@ __device__ __forceinline__ float load_w_dt(const void *p, int64_t i, int wdtype)
 // ------------------------------------------------------------------------------------------------
 // forward, dim-contiguous
 template <typename T, int VEC>
-__global__ void __launch_bounds__(128) conv_fwd_dimc_kernel(const zg_conv_params p) {
+__global__ void __launch_bounds__(128, 5) conv_fwd_dimc_kernel(const zg_conv_params p) {
     const int E = p.dim, L = p.seqlen, W = p.width;
     const int nvec = (E + VEC - 1) / VEC;
     const int nchunk = (L + CONV_LCH - 1) / CONV_LCH;
@@ -222,12 +224,17 @@ template <typename T> static int conv_fwd_t(const zg_conv_params &p, bool seq, c
             conv_fwd_seqc_kernel<T, 1><<<(unsigned)((n + 127) / 128), 128, 0, s>>>(p);
         }
     } else {
-        const bool vec_ok = (p.dim % VEC == 0) && (align_bits % 16 == 0) && (p.x_sb % VEC == 0) && (p.x_sl % VEC == 0) &&
-                            (p.out_sb % VEC == 0) && (p.out_sl % VEC == 0);
+        // token-major: a thread owns DV adjacent channels.  4 channels (8-byte vectors for 16-bit types) keep the
+        // kernel at ~70 registers -> 6+ CTAs/SM; 8 channels needed 128-182 registers (ncu round 1: 12 % occupancy,
+        // 202 us for 335 MB).
+        constexpr int DV = 4;
+        constexpr int DB = DV * (int)sizeof(T);
+        const bool vec_ok = (p.dim % DV == 0) && (align_bits % DB == 0) && (p.x_sb % DV == 0) && (p.x_sl % DV == 0) &&
+                            (p.out_sb % DV == 0) && (p.out_sl % DV == 0);
         const int nchunk = (p.seqlen + CONV_LCH - 1) / CONV_LCH;
         if (vec_ok) {
-            const int64_t n = (int64_t)p.batch * nchunk * (p.dim / VEC);
-            conv_fwd_dimc_kernel<T, VEC><<<(unsigned)((n + 127) / 128), 128, 0, s>>>(p);
+            const int64_t n = (int64_t)p.batch * nchunk * (p.dim / DV);
+            conv_fwd_dimc_kernel<T, DV><<<(unsigned)((n + 127) / 128), 128, 0, s>>>(p);
         } else {
             const int64_t n = (int64_t)p.batch * nchunk * p.dim;
             conv_fwd_dimc_kernel<T, 1><<<(unsigned)((n + 127) / 128), 128, 0, s>>>(p);

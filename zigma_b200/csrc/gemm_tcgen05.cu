@@ -1,0 +1,321 @@
+// bf16 GEMM on the 5th-generation tensor cores (tcgen05 + TMEM + TMA), hand written for sm_100a.
+//
+//     C[M, N] = A[M, K] * B[N, K]^T (+ bias[N])        A, B, C row-major bf16, fp32 accumulation in TMEM
+//
+// This is the shape of every dense projection on the ZigMa hot path in the token-major layout (DESIGN.md
+// section 3): in_proj (mamba_simple.py:290-294), x_proj / dt_proj (selective_scan_interface.py:322-323)
+// and out_proj (:365) -- activations (B*L, K) times an nn.Linear weight (N, K).  The reference leaves them
+// to cuBLAS behind F.linear / `@`.
+//
+// Structure (one CTA per SM, persistent over output tiles; 192 threads):
+//   warp 0   TMA producer: one elected lane issues cp.async.bulk.tensor loads of the A (128 x 64) and
+//            B (BN x 64) k-blocks into a 4-stage shared-memory ring (128-byte swizzle), mbarrier tx-count
+//   warp 1   MMA issuer: one elected lane issues tcgen05.mma.cta_group::1.kind::f16 (M=128, N=BN, K=16),
+//            4 per k-block, accumulating into one of two TMEM accumulator buffers; tcgen05.commit releases
+//            the smem stage / signals the epilogue.  Also owns tcgen05.alloc / dealloc.
+//   warps 2-5 epilogue: tcgen05.ld (32 lanes x 32 columns per instruction) -> registers -> (+bias) ->
+//            bf16 -> 16-byte global stores, optionally through `out_rowmap` (row scatter of the out_proj
+//            result back to raster order, mamba_simple.py:388-394).  Runs one tile behind the MMA warp.
+// K, M, N remainders are handled by TMA out-of-bounds zero fill (loads) and predicated stores.
+#include "zg_common.cuh"
+#include <cuda.h>
+
+namespace zg {
+
+constexpr int G_BM = 128, G_BK = 64, G_STAGES = 4, G_UMMA_K = 16, G_THREADS = 192;
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra WAIT_DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "WAIT_DONE:\n\t"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(dst)),
+                 "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}\n"
+        : "=r"(pred));
+    return pred != 0;
+}
+// shared-memory matrix descriptor: K-major operand, 128-byte swizzle, rows of 64 bf16 (128 B), 8-row groups
+// 1024 B apart (cute/arch/mma_sm100_desc.hpp: start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46), version=1
+// [46,48), layout_type SWIZZLE_128B=2 [61,64)).
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3ffff) >> 4);
+    d |= (uint64_t)1 << 16;                 // LBO (unused for swizzled K-major), canonical value 1
+    d |= (uint64_t)(1024 >> 4) << 32;       // SBO
+    d |= (uint64_t)1 << 46;                 // descriptor version (Blackwell)
+    d |= (uint64_t)2 << 61;                 // SWIZZLE_128B
+    return d;
+}
+// instruction descriptor, kind::f16: D = fp32, A = B = bf16, both K-major, N >> 3 at [17,23), M >> 4 at [24,29)
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_c, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_c), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+          "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+          "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+          "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+struct GemmArgs {
+    __nv_bfloat16 *C;
+    const __nv_bfloat16 *bias;
+    const int32_t *out_rowmap;
+    int64_t ldc;
+    int M, N, K, rows_per_batch;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(G_THREADS, 1)
+gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmArgs g) {
+    constexpr int BM = G_BM, BK = G_BK, STAGES = G_STAGES;
+    constexpr uint32_t A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
+    constexpr uint32_t TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
+    extern __shared__ __align__(1024) unsigned char gsm[];
+    unsigned char *tiles = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(gsm) + 1023) & ~(uintptr_t)1023);
+    uint64_t *full_bar = reinterpret_cast<uint64_t *>(tiles + STAGES * STAGE_BYTES);
+    uint64_t *empty_bar = full_bar + STAGES;
+    uint64_t *tfull_bar = empty_bar + STAGES;     // [2] accumulator ready
+    uint64_t *tempty_bar = tfull_bar + 2;         // [2] accumulator drained
+    uint32_t *tmem_base_slot = reinterpret_cast<uint32_t *>(tempty_bar + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m_tiles = (g.M + BM - 1) / BM, n_tiles = (g.N + BN - 1) / BN;
+    const int num_tiles = m_tiles * n_tiles;
+    const int k_blocks = (g.K + BK - 1) / BK;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+        for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 128); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_slot)), "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_base_slot;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (elect_one()) {
+            uint32_t it = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
+                for (int kb = 0; kb < k_blocks; ++kb, ++it) {
+                    const int st = it % STAGES;
+                    const uint32_t ph = (it / STAGES) & 1;
+                    mbar_wait(&empty_bar[st], ph ^ 1);
+                    mbar_expect_tx(&full_bar[st], STAGE_BYTES);
+                    unsigned char *sa = tiles + st * STAGE_BYTES;
+                    tma_load_2d(sa, &tmA, &full_bar[st], kb * BK, m_blk * BM);
+                    tma_load_2d(sa + A_BYTES, &tmB, &full_bar[st], kb * BK, n_blk * BN);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (elect_one()) {
+            constexpr uint32_t idesc = make_idesc(BM, BN);
+            uint32_t it = 0, tcount = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcount) {
+                const int acc = tcount & 1;
+                const uint32_t aph = (tcount >> 1) & 1;
+                mbar_wait(&tempty_bar[acc], aph ^ 1);            // epilogue has drained this accumulator
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t tmem_c = tmem_base + acc * BN;
+                for (int kb = 0; kb < k_blocks; ++kb, ++it) {
+                    const int st = it % STAGES;
+                    const uint32_t ph = (it / STAGES) & 1;
+                    mbar_wait(&full_bar[st], ph);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t sa = smem_u32(tiles + st * STAGE_BYTES);
+                    const uint64_t adesc = make_smem_desc(sa), bdesc = make_smem_desc(sa + A_BYTES);
+#pragma unroll
+                    for (int k = 0; k < BK / G_UMMA_K; ++k)      // +32 B per K=16 step inside the 128-byte swizzle atom
+                        umma_f16(tmem_c, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
+                    umma_commit(&empty_bar[st]);                 // smem stage free once these MMAs retire
+                }
+                umma_commit(&tfull_bar[acc]);                    // accumulator complete
+            }
+        }
+    } else {
+        // ===== epilogue warps 2..5: TMEM lane quadrant = warp % 4 =====
+        const int quad = warp & 3;
+        uint32_t tcount = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcount) {
+            const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
+            const int acc = tcount & 1;
+            const uint32_t aph = (tcount >> 1) & 1;
+            mbar_wait(&tfull_bar[acc], aph);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const int row = m_blk * BM + quad * 32 + lane;
+            int64_t drow = row;
+            if (g.out_rowmap && row < g.M) {
+                const int bidx = row / g.rows_per_batch;
+                drow = (int64_t)bidx * g.rows_per_batch + g.out_rowmap[row - bidx * g.rows_per_batch];
+            }
+            __nv_bfloat16 *crow = g.C + drow * g.ldc;
+#pragma unroll 1
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                uint32_t v[32];
+                tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + c0), v);
+                const int col0 = n_blk * BN + c0;
+                if (row < g.M && col0 < g.N) {
+                    if (col0 + 32 <= g.N && ((reinterpret_cast<uintptr_t>(crow + col0) & 15) == 0)) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            uint32_t o[4];
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                float a = __uint_as_float(v[j * 8 + 2 * i]), b2 = __uint_as_float(v[j * 8 + 2 * i + 1]);
+                                if (g.bias) {
+                                    a += __bfloat162float(g.bias[col0 + j * 8 + 2 * i]);
+                                    b2 += __bfloat162float(g.bias[col0 + j * 8 + 2 * i + 1]);
+                                }
+                                __nv_bfloat162 h = __floats2bfloat162_rn(a, b2);
+                                o[i] = *reinterpret_cast<uint32_t *>(&h);
+                            }
+                            *reinterpret_cast<uint4 *>(crow + col0 + j * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+                        }
+                    } else {
+                        for (int i = 0; i < 32; ++i)
+                            if (col0 + i < g.N) {
+                                float a = __uint_as_float(v[i]);
+                                if (g.bias) a += __bfloat162float(g.bias[col0 + i]);
+                                crow[col0 + i] = __float2bfloat16_rn(a);
+                            }
+                    }
+                }
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            mbar_arrive(&tempty_bar[acc]);
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+// 2-D row-major bf16 matrix (rows x cols, leading dimension ld elements) -> tensor map with a (box_rows x 64) box
+static int make_map(CUtensorMap *m, const void *base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) return zg_set_error("gemm_bf16_tn: cuTensorMapEncodeTiled not available from the driver");
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+    cuuint32_t box[2] = {(cuuint32_t)G_BK, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return zg_set_error("gemm_bf16_tn: cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return 0;
+}
+
+template <int BN> static int launch_gemm(const zg_gemm_params &p, cudaStream_t s) {
+    CUtensorMap tmA, tmB;
+    if (int rc = make_map(&tmA, p.A, p.M, p.K, p.lda, G_BM)) return rc;
+    if (int rc = make_map(&tmB, p.B, p.N, p.K, p.ldb, BN)) return rc;
+    GemmArgs g{reinterpret_cast<__nv_bfloat16 *>(p.C), reinterpret_cast<const __nv_bfloat16 *>(p.bias), p.out_rowmap, p.ldc, p.M, p.N, p.K,
+               p.rows_per_batch > 0 ? p.rows_per_batch : p.M};
+    const int smem = G_STAGES * (G_BM * G_BK * 2 + BN * G_BK * 2) + 1024 + 256;
+    auto kern = gemm_bf16_tn_kernel<BN>;
+    static bool attr = false;
+    if (!attr) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return zg_set_error("gemm_bf16_tn: cudaFuncSetAttribute(%d): %s", smem, cudaGetErrorString(e));
+        attr = true;
+    }
+    static int sms = 0;
+    if (!sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    }
+    const int tiles = ((p.M + G_BM - 1) / G_BM) * ((p.N + BN - 1) / BN);
+    const int grid = tiles < sms ? tiles : sms;
+    kern<<<grid, G_THREADS, smem, s>>>(tmA, tmB, g);
+    zg_count_launch();
+    return zg_check_launch("gemm_bf16_tn");
+}
+
+}  // namespace zg
+
+extern "C" int zg_gemm_bf16_tn(const zg_gemm_params *pp, void *stream) {
+    ZG_REQUIRE(pp != nullptr, "gemm_bf16_tn: null params");
+    const zg_gemm_params &p = *pp;
+    ZG_REQUIRE(p.A && p.B && p.C, "gemm_bf16_tn: null tensor pointer");
+    ZG_REQUIRE(p.M > 0 && p.N > 0 && p.K > 0, "gemm_bf16_tn: bad shape (%d, %d, %d)", p.M, p.N, p.K);
+    ZG_REQUIRE(p.lda % 8 == 0 && p.ldb % 8 == 0 && p.lda >= p.K && p.ldb >= p.K && p.ldc >= p.N, "gemm_bf16_tn: leading dimensions must be multiples of 8 elements");
+    ZG_REQUIRE((reinterpret_cast<uintptr_t>(p.A) & 15) == 0 && (reinterpret_cast<uintptr_t>(p.B) & 15) == 0, "gemm_bf16_tn: A and B must be 16-byte aligned");
+    ZG_REQUIRE(!p.out_rowmap || (p.rows_per_batch > 0 && p.M % p.rows_per_batch == 0), "gemm_bf16_tn: out_rowmap needs rows_per_batch dividing M");
+    cudaStream_t s = (cudaStream_t)stream;
+    if (p.N > 128) return zg::launch_gemm<256>(p, s);
+    if (p.N > 64) return zg::launch_gemm<128>(p, s);
+    return zg::launch_gemm<64>(p, s);
+}

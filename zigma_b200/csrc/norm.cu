@@ -209,7 +209,7 @@ template <> __device__ __forceinline__ void cvt4<__half>(const Raw4<__half> &r, 
 }
 
 template <typename T, int MAXQ>
-__global__ void __launch_bounds__(128) block_tail_kernel(const zg_block_tail_params p) {
+__global__ void __launch_bounds__(128, (MAXQ <= 6) ? 6 : 1) block_tail_kernel(const zg_block_tail_params p) {
     const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     const int64_t nrows = (int64_t)p.batch * p.seqlen;
@@ -325,8 +325,14 @@ __global__ void __launch_bounds__(128) block_tail_kernel(const zg_block_tail_par
 template <typename T> static int block_tail_t(const zg_block_tail_params &p, cudaStream_t s) {
     const int64_t nrows = (int64_t)p.batch * p.seqlen;
     const unsigned grid = (unsigned)((nrows * 32 + 127) / 128);
+    // MAXQ = ceil(D / 128) exactly for the model widths of the reference zoo (368, 640, 768, 1024, 1536): the raw
+    // operand vectors of a row live in registers, so an over-sized MAXQ costs occupancy (ncu round 1: 92 registers at
+    // MAXQ = 8 for D = 640 -> 5 CTAs/SM, 49 % of the HBM roofline)
     if (p.dim <= 512) block_tail_kernel<T, 4><<<grid, 128, 0, s>>>(p);
+    else if (p.dim <= 640) block_tail_kernel<T, 5><<<grid, 128, 0, s>>>(p);
+    else if (p.dim <= 768) block_tail_kernel<T, 6><<<grid, 128, 0, s>>>(p);
     else if (p.dim <= 1024) block_tail_kernel<T, 8><<<grid, 128, 0, s>>>(p);
+    else if (p.dim <= 1536) block_tail_kernel<T, 12><<<grid, 128, 0, s>>>(p);
     else block_tail_kernel<T, NORM_MAXQ><<<grid, 128, 0, s>>>(p);
     zg_count_launch();
     return zg_check_launch("block_tail_fwd");

@@ -31,6 +31,15 @@ def _i32(t):
     return t.to(torch.int32).contiguous()
 
 
+def _linear(x2d, weight, bias=None):
+    """(M, K) @ (N, K)^T.  bf16 goes to the hand-written tcgen05 kernel when ZIGMA_TCGEN05=1, else (and for
+    fp32 / fp16) to the library GEMM."""
+    if x2d.dtype == torch.bfloat16 and os.environ.get("ZIGMA_TCGEN05", "0") == "1" and x2d.stride(0) % 8 == 0 and weight.stride(0) % 8 == 0:
+        from .gemm import linear_bf16
+        return linear_bf16(x2d, weight, bias)
+    return F.linear(x2d, weight, bias)
+
+
 def block_tail(x, mix, gate, shift, scale, norm_w, residual, rowmap, eps, final=False, mod_div=1, want_modded=True):
     """zg_block_tail_fwd wrapper.  x: (Bt, L, D) contiguous; gate/shift/scale: (Bt // mod_div, D)
     views with a common row stride.  Returns residual_out (fp32), normed, modded."""
@@ -126,8 +135,8 @@ class ZigMaEngine:
         z_log = xz3[:, :, E:].transpose(1, 2)
         xc = _conv_fwd(x_log, w["conv_w"], w["conv_b"], True, x_rowmap=rowmap)           # logical (Bt, E, L), token-major memory
         xc_flat = xc.transpose(1, 2).reshape(Bt * L, E)
-        x_dbl = xc_flat @ w["x_proj"].t()                                                  # (Bt*L, R + 2N)
-        delta = x_dbl[:, :R] @ w["dt_proj"].t()                                            # (Bt*L, E)
+        x_dbl = _linear(xc_flat, w["x_proj"])                                              # (Bt*L, R + 2N)
+        delta = _linear(x_dbl[:, :R], w["dt_proj"])                                        # (Bt*L, E)
         d_log = delta.view(Bt, L, E).transpose(1, 2)
         xd3 = x_dbl.view(Bt, L, R + 2 * N)
         B_log = xd3[:, :, R:R + N].permute(0, 2, 1).unsqueeze(1)                           # (Bt, 1, N, L) view
@@ -140,9 +149,7 @@ class ZigMaEngine:
         """modded: (B, L, D) -> (mix (Bt', L', D) token-major in SCAN order, tail rowmap, fold info)."""
         B, L, D = modded.shape
         E = lay["E"]
-        xz = modded.reshape(B * L, D) @ lay["in_proj"].t()
-        if lay["in_bias"] is not None:
-            xz = xz + lay["in_bias"]
+        xz = _linear(modded.reshape(B * L, D), lay["in_proj"], lay["in_bias"])
         st = lay["st"]
         if st == "v1":
             y = self._core(xz, B, L, lay, lay["fwd"], None)
@@ -160,15 +167,15 @@ class ZigMaEngine:
             K = L // T
             if lay["s_or_t"] == "s":      # (b t) sequences of K tokens: a pure re-view of token-major memory
                 y = self._core(xz, B * T, K, lay, lay["fwd"], lay["perm"])
-                mix = F.linear(y.reshape(B * T * K, E), lay["out_proj"], lay["out_bias"]).view(B * T, K, D)
+                mix = _linear(y.reshape(B * T * K, E), lay["out_proj"], lay["out_bias"]).view(B * T, K, D)
                 return mix, lay["perm_rev"], T
             # (b k) sequences of T tokens: strided in token-major memory -> explicit transposes
             xz_t = xz.view(B, T, K, 2 * E).permute(0, 2, 1, 3).reshape(B * K * T, 2 * E)
             y = self._core(xz_t, B * K, T, lay, lay["fwd"], lay["perm"])
-            mix = F.linear(y.reshape(B * K * T, E), lay["out_proj"], lay["out_bias"]).view(B * K, T, D)
+            mix = _linear(y.reshape(B * K * T, E), lay["out_proj"], lay["out_bias"]).view(B * K, T, D)
             mix = mix[:, lay["perm_rev64"], :].reshape(B, K, T, D).permute(0, 2, 1, 3).reshape(B, L, D)
             return mix, None, 1
-        mix = F.linear(y.reshape(B * L, E), lay["out_proj"], lay["out_bias"]).view(B, L, D)
+        mix = _linear(y.reshape(B * L, E), lay["out_proj"], lay["out_bias"]).view(B, L, D)
         return mix, rowmap, 1
 
     # ---- whole forward -----------------------------------------------------------------------------
