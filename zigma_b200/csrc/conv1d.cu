@@ -10,6 +10,7 @@
 //   seq-contiguous ("channel first", reference layout): a thread owns VEC consecutive positions of
 //     one (batch, channel) row and reads the preceding vector for the halo.
 #include "zg_common.cuh"
+#include <stdlib.h>
 
 namespace zg {
 
@@ -21,6 +22,9 @@ template <typename T> struct VecT<T, 1> { T e[1]; };
 template <> struct alignas(16) VecT<float, 4> { float e[4]; };
 template <> struct alignas(16) VecT<__half, 8> { __half e[8]; };
 template <> struct alignas(16) VecT<__nv_bfloat16, 8> { __nv_bfloat16 e[8]; };
+template <> struct alignas(4) VecT<__half, 2> { __half e[2]; };
+template <> struct alignas(4) VecT<__nv_bfloat16, 2> { __nv_bfloat16 e[2]; };
+template <> struct alignas(8) VecT<float, 2> { float e[2]; };
 template <> struct alignas(8) VecT<__half, 4> { __half e[4]; };
 template <> struct alignas(8) VecT<__nv_bfloat16, 4> { __nv_bfloat16 e[4]; };
 
@@ -227,6 +231,21 @@ template <typename T> static int conv_fwd_t(const zg_conv_params &p, bool seq, c
         // token-major: a thread owns DV adjacent channels.  4 channels (8-byte vectors for 16-bit types) keep the
         // kernel at ~70 registers -> 6+ CTAs/SM; 8 channels needed 128-182 registers (ncu round 1: 12 % occupancy,
         // 202 us for 335 MB).
+        static int dv_env = -1;        // tuning knob: channels per thread (ZG_CONV_VEC = 2 | 4 | 8)
+        if (dv_env < 0) { const char *e = getenv("ZG_CONV_VEC"); dv_env = e ? atoi(e) : 0; }
+        if (dv_env == 2 || (dv_env == 8 && sizeof(T) == 2)) {
+            const int dv = dv_env;
+            const bool ok = (p.dim % dv == 0) && (align_bits % (dv * sizeof(T)) == 0) && (p.x_sb % dv == 0) && (p.x_sl % dv == 0) &&
+                            (p.out_sb % dv == 0) && (p.out_sl % dv == 0);
+            if (ok) {
+                const int nchunk2 = (p.seqlen + CONV_LCH - 1) / CONV_LCH;
+                const int64_t n = (int64_t)p.batch * nchunk2 * (p.dim / dv);
+                if (dv == 2) conv_fwd_dimc_kernel<T, 2><<<(unsigned)((n + 127) / 128), 128, 0, s>>>(p);
+                else conv_fwd_dimc_kernel<T, (sizeof(T) == 2 ? 8 : 4)><<<(unsigned)((n + 127) / 128), 128, 0, s>>>(p);
+                zg_count_launch();
+                return zg_check_launch("causal_conv1d_fwd");
+            }
+        }
         constexpr int DV = 4;
         constexpr int DB = DV * (int)sizeof(T);
         const bool vec_ok = (p.dim % DV == 0) && (align_bits % DB == 0) && (p.x_sb % DV == 0) && (p.x_sl % DV == 0) &&
