@@ -460,8 +460,16 @@ template <typename T, int NS, bool SEQ> int launch_scan_fwd_npoly(const zg_scan_
     return launch_scan_fwd<T, NS, SEQ, false, 0>(p, stream);
 }
 
+template <typename T> int try_launch_scan_fwd_tpc2(const zg_scan_params &p, cudaStream_t stream);   // scan_fwd_tpc2.cuh
+
 template <typename T> int dispatch_scan_fwd(const zg_scan_params &p, bool seq, bool constbc, cudaStream_t stream) {
     const int N = p.dstate;
+    if constexpr (sizeof(T) == 2) {
+        if (!seq && !constbc) {     // hot-path specialisation (two threads per channel), when the call fits it
+            const int rc = try_launch_scan_fwd_tpc2<T>(p, stream);
+            if (rc >= 0) return rc;
+        }
+    }
 #define ZG_SCAN_CASE(NSV)                                                                   \
     if (N <= NSV) {                                                                         \
         if (seq) return launch_scan_fwd_npoly<T, NSV, true>(p, stream);                     \
