@@ -5,7 +5,7 @@ nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw,memory.total --fo
 nproc > gpurun_out/host.txt; free -g >> gpurun_out/host.txt
 echo "== debug"; [ -n "$DEBUG_SCRIPT" ] && timeout 300 python $DEBUG_SCRIPT > gpurun_out/debug.log 2>&1; [ -n "$DEBUG_SCRIPT" ] && tail -20 gpurun_out/debug.log
 if [ -n "$DO_SWEEP" ]; then echo "== scan sweep"; for n in ${SWEEP_SET:-0 2 3 4}; do ZG_SCAN_NPOLY=$n timeout 300 python scripts/scan_sweep.py 2>&1 | tail -1; done | tee gpurun_out/scan_sweep.log; fi
-if [ -n "$DO_MICRO" ]; then echo "== micro"; (timeout 300 python scripts/gemm_bench.py; for v in 2 4 8; do ZG_CONV_VEC=$v timeout 200 python scripts/conv_sweep.py | tail -1; done) 2>&1 | tee gpurun_out/micro.log; fi
+if [ -n "$DO_MICRO" ]; then echo "== micro"; (if [ -z "$SKIP_GEMM_BENCH" ]; then timeout 300 python scripts/gemm_bench.py; fi; for v in ${CONV_SET:-0 4}; do ZG_CONV_VEC=$v timeout 200 python scripts/conv_sweep.py | tail -1; done; for n in ${TPC2_NPOLY_SET:-0 1 2}; do ZG_SCAN_TPC2_NPOLY=$n timeout 200 python scripts/scan_sweep.py | tail -1; done) 2>&1 | tee gpurun_out/micro.log; fi
 echo "== smoke"; timeout 600 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?"; tail -5 gpurun_out/smoke.log
 echo "== pytest -m gpu"; timeout 2400 python -m pytest tests -m gpu -q -rA -p no:cacheprovider --timeout=900 ${PYTEST_EXTRA} > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"
 grep -E "^(PASSED|FAILED|ERROR)|passed|failed" gpurun_out/pytest_gpu.log | tail -100

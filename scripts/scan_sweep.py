@@ -37,4 +37,4 @@ tok(); seq()
 ref = outs.float()
 err = (outb.float() - torch.gather(ref, 2, torch.zeros(1, dtype=torch.long, device=dev).expand(1, 1, 1).expand(bs, E, 1)) * 0).abs().max().item()  # (layouts use different z order: no cross-check)
 abytes = 4 * 2 * bs * E * L + 2 * 2 * bs * N * L + 4 * (E * N + 2 * E)
-print(f"NPOLY={os.environ.get('ZG_SCAN_NPOLY', 'default')} token-major {t_tok:.4f} ms ({abytes / t_tok / 1e6:.0f} GB/s)  seq {t_seq:.4f} ms ({abytes / t_seq / 1e6:.0f} GB/s)")
+print(f"NPOLY={os.environ.get('ZG_SCAN_NPOLY', 'default')} TPC2={os.environ.get('ZG_SCAN_TPC2', '1')} TPC2_NPOLY={os.environ.get('ZG_SCAN_TPC2_NPOLY', '0')} token-major {t_tok:.4f} ms ({abytes / t_tok / 1e6:.0f} GB/s)  seq {t_seq:.4f} ms ({abytes / t_seq / 1e6:.0f} GB/s)")

@@ -104,3 +104,65 @@ def test_euler_sampling_loop_matches_oracle():
     ocfg = dict(cfg, norm_epsilon=1e-5)
     want = zo.sample_ode_fixed(lambda x, t: zo.zigma_forward(sd, ocfg, x, t), x0, num_steps=6)
     check_close(got, want, "5-step Euler sampling", atol=5e-5)
+
+
+# ---- the other BASELINE.json configs at their real widths (parity-test cases, not bench lines) ---------------
+def _oracle_forward(cfg, sd, x, t, y=None):
+    """CPU oracle with the plain-C scan (fp32): seconds at bs=1 even for L = 4096."""
+    zo.USE_C_SCAN = True
+    try:
+        return zo.zigma_forward(sd, dict(cfg, norm_epsilon=1e-5), x, t, y)
+    finally:
+        zo.USE_C_SCAN = False
+
+
+FULL_WIDTH_CASES = {
+    # BASELINE configs[2]: sweep2_b1 (scan_type "v2": two directional scans per layer, separate parameters)
+    "config3_sweep2_b1": (dict(in_channels=4, embed_dim=640, depth=18, img_dim=32, patch_size=1, scan_type="v2", use_pe=2), (1, 4, 32, 32)),
+    # BASELINE configs[3]: FacesHQ-1024 shape -- D=768, 128x128 latent, patch 2 -> L = 4096, zigzag tables of side 64
+    # (depth cut from 24 to 4 to bound the CPU oracle's time; widths, L and tables are the real ones)
+    "config4_faceshq1024": (dict(in_channels=4, embed_dim=768, depth=4, img_dim=128, patch_size=2, scan_type="zigzagN8", use_pe=0), (1, 4, 128, 128)),
+    # BASELINE configs[4]: UCF101 3d_zigzag8sst_b2 shape -- 16 frames x (32/2)^2 tokens, s/s/t factorised scans,
+    # 101 classes (depth cut from 24 to 6 = two s,s,t rounds)
+    "config5_ucf101_sst": (dict(in_channels=4, embed_dim=768, depth=6, img_dim=32, patch_size=2, scan_type="zzvideo_sst", use_pe=2,
+                                video_frames=16, tpe=True, num_classes=101), (1, 16, 4, 32, 32)),
+}
+
+
+@pytest.mark.parametrize("name", list(FULL_WIDTH_CASES))
+def test_other_baseline_configs_fp32_vs_oracle(name):
+    from zigma_b200 import ZigMa
+    cfg, xshape = FULL_WIDTH_CASES[name]
+    m = ZigMa(device=DEV, **cfg).eval()
+    shapes = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+    sd = synth.synth_state_dict(shapes, seed=0)
+    m.load_state_dict(sd)
+    x = synth.synth_latents(xshape, seed=11)
+    tt = torch.tensor([0.37])
+    y = torch.tensor([42]) if cfg.get("num_classes", -1) > 0 else None
+    with torch.no_grad():
+        got = m(x.to(DEV), tt.to(DEV), None if y is None else y.to(DEV))
+    want = _oracle_forward(cfg, sd, x, tt, y)
+    check_close(got, want, f"{name} fp32 engine vs CPU oracle", atol=2e-5)
+
+
+@pytest.mark.parametrize("name", ["config4_faceshq1024", "config5_ucf101_sst"])
+def test_other_baseline_configs_bf16_batch(name):
+    """bf16 at a multi-sample batch: finite, each sample equal to its bs=1 run, close to the fp32 oracle."""
+    from zigma_b200 import ZigMa
+    cfg, xshape = FULL_WIDTH_CASES[name]
+    m = ZigMa(device=DEV, dtype=torch.bfloat16, **cfg).eval()
+    shapes = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+    sd = synth.synth_state_dict(shapes, seed=0)
+    m.load_state_dict({k: v.bfloat16() for k, v in sd.items()})
+    bs = 3
+    x = synth.synth_latents((bs,) + xshape[1:], seed=12)
+    tt = torch.tensor([0.2, 0.5, 0.8])
+    y = torch.tensor([3, 50, 100]) if cfg.get("num_classes", -1) > 0 else None
+    with torch.no_grad():
+        out = m(x.to(DEV).bfloat16(), tt.to(DEV).bfloat16(), None if y is None else y.to(DEV))
+        one = m(x[1:2].to(DEV).bfloat16(), tt[1:2].to(DEV).bfloat16(), None if y is None else y[1:2].to(DEV))
+    assert torch.isfinite(out.float()).all()
+    check_close(out[1:2], one, f"{name} bf16 bs=3 vs bs=1", rtol=2e-2, atol=2e-2, scale_atol=False, max_strict_viol=1.0)
+    want = _oracle_forward(cfg, sd, x[1:2], tt[1:2], None if y is None else y[1:2])
+    check_close(one, want, f"{name} bf16 vs fp32 oracle", rtol=8e-2, atol=8e-2, scale_atol=False, max_strict_viol=1.0)

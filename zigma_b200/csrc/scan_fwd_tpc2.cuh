@@ -15,8 +15,12 @@
 namespace zg {
 
 constexpr int TPC2_THREADS = 128;   // 64 channels x 2 threads
+#ifndef ZG_SCAN_TPC2_NPOLY_DEFAULT
+#define ZG_SCAN_TPC2_NPOLY_DEFAULT 0
+#endif
 
-template <typename T>
+// NPOLY of each thread's 4 state pairs take exp2 from the FMA-pipe polynomial (zg_ex2_poly2) instead of MUFU
+template <typename T, int NPOLY>
 __global__ void __launch_bounds__(TPC2_THREADS, 9) scan_fwd_tpc2_kernel(const zg_scan_params p) {
     static_assert(sizeof(T) == 2, "16-bit I/O only");
     constexpr int NS = 16, CH = SCAN_CH, TL = SCAN_TL, NSTAGE = 3, VEC = 8;
@@ -124,7 +128,8 @@ __global__ void __launch_bounds__(TPC2_THREADS, 9) scan_fwd_tpc2_kernel(const zg
                 const zg_f2 Cp[4] = {make_float2(C0.x, C0.y), make_float2(C0.z, C0.w), make_float2(C1.x, C1.y), make_float2(C1.z, C1.w)};
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
-                    const zg_f2 a = zg_ex2_mufu2(zg_mul2(dl2[i], Al2p[q]));
+                    const zg_f2 x = zg_mul2(dl2[i], Al2p[q]);
+                    const zg_f2 a = (q < NPOLY) ? zg_ex2_poly2(x) : zg_ex2_mufu2(x);
                     h2[q] = zg_fma2(a, h2[q], zg_mul2(du2[i], Bp[q]));
                     y2[i] = zg_fma2(Cp[q], h2[q], y2[i]);
                 }
@@ -174,16 +179,22 @@ template <typename T> int try_launch_scan_fwd_tpc2(const zg_scan_params &p, cuda
         (int64_t)p.seqlen * p.out_sl > lim || (int64_t)p.seqlen * p.B_sl > lim || (int64_t)p.seqlen * p.C_sl > lim)
         return -1;
     constexpr int smem = 3 * (3 * SCAN_TL * SCAN_CH * 2 + 2 * SCAN_TL * 16 * 2) + SCAN_TL * 32 * 4;
-    auto kern = scan_fwd_tpc2_kernel<T>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        attr_set = true;
-    }
     const long long nblk = (long long)(p.dim / SCAN_CH) * p.batch;
     if (nblk > 0x7fffffffLL) return -1;
-    kern<<<(unsigned)nblk, TPC2_THREADS, smem, stream>>>(p);
+    static int npoly = -1;
+    if (npoly < 0) { const char *e = getenv("ZG_SCAN_TPC2_NPOLY"); npoly = e ? atoi(e) : ZG_SCAN_TPC2_NPOLY_DEFAULT; if (npoly < 0 || npoly > 2) npoly = 0; }
+    auto launch = [&](auto kern) {
+        static bool attr_set = false;
+        if (!attr_set) {
+            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+            cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            attr_set = true;
+        }
+        kern<<<(unsigned)nblk, TPC2_THREADS, smem, stream>>>(p);
+    };
+    if (npoly == 1) launch(scan_fwd_tpc2_kernel<T, 1>);
+    else if (npoly == 2) launch(scan_fwd_tpc2_kernel<T, 2>);
+    else launch(scan_fwd_tpc2_kernel<T, 0>);
     zg_count_launch();
     return zg_check_launch("scan_fwd(tpc2)");
 }
