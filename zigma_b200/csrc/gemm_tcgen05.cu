@@ -17,12 +17,22 @@
 //            bf16 -> 16-byte global stores, optionally through `out_rowmap` (row scatter of the out_proj
 //            result back to raster order, mamba_simple.py:388-394).  Runs one tile behind the MMA warp.
 // K, M, N remainders are handled by TMA out-of-bounds zero fill (loads) and predicated stores.
+//
+// Thread-block clusters (CL = 2 or 4 CTAs along M): at the projection shapes of this model the single-CTA
+// kernel is bound by L2 -> SM bandwidth, not by the tensor pipe (round-1 measurement: in_proj 214 us = 2.46 GB
+// of operand tiles at ~11.5 TB/s): every 128 x 256 output tile re-reads its 256 x K
+// weight tile from L2.  The CTAs of a cluster work on CL vertically adjacent output tiles that share the
+// weight tile; each CTA fetches 1/CL of it and TMA-multicasts the slice into the shared memory of all CL CTAs,
+// cutting the per-CTA L2 traffic per k-block from 48 KB to 16 + 32/CL KB.  A stage may only be overwritten
+// once EVERY CTA of the cluster has consumed it, so each CTA runs a relay warp that forwards its local
+// "stage consumed" (tcgen05.commit) to a `free` barrier in all CTAs with remote mbarrier arrives.
 #include "zg_common.cuh"
 #include <cuda.h>
+#include <stdlib.h>
 
 namespace zg {
 
-constexpr int G_BM = 128, G_BK = 64, G_STAGES = 4, G_UMMA_K = 16, G_THREADS = 192;
+constexpr int G_BM = 128, G_BK = 64, G_STAGES = 4, G_UMMA_K = 16, G_THREADS = 224;   // 7 warps: TMA, MMA, 4 epilogue, relay
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -50,6 +60,26 @@ __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, u
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(dst)),
                  "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
                  : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_mc(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, uint16_t mask) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(
+                     smem_u32(dst)),
+                 "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask)
+                 : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t *bar, uint32_t cta) {
+    uint32_t ra;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(smem_u32(bar)), "r"(cta));
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(ra) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 __device__ __forceinline__ bool elect_one() {
     uint32_t pred;
@@ -110,7 +140,7 @@ struct GemmArgs {
     int M, N, K, rows_per_batch;
 };
 
-template <int BN>
+template <int BN, int CL>
 __global__ void __launch_bounds__(G_THREADS, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmArgs g) {
     constexpr int BM = G_BM, BK = G_BK, STAGES = G_STAGES;
@@ -122,17 +152,21 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     uint64_t *empty_bar = full_bar + STAGES;
     uint64_t *tfull_bar = empty_bar + STAGES;     // [2] accumulator ready
     uint64_t *tempty_bar = tfull_bar + 2;         // [2] accumulator drained
-    uint32_t *tmem_base_slot = reinterpret_cast<uint32_t *>(tempty_bar + 2);
+    uint64_t *free_bar = tempty_bar + 2;          // [STAGES] stage consumed by every CTA of the cluster (CL > 1)
+    uint32_t *tmem_base_slot = reinterpret_cast<uint32_t *>(free_bar + STAGES);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = (CL > 1) ? cluster_ctarank() : 0u;
+    const int cluster_id = blockIdx.x / CL, num_clusters = gridDim.x / CL;
     const int m_tiles = (g.M + BM - 1) / BM, n_tiles = (g.N + BN - 1) / BN;
-    const int num_tiles = m_tiles * n_tiles;
+    const int sm_tiles = (m_tiles + CL - 1) / CL;             // super tiles of CL vertically adjacent output tiles
+    const int num_tiles = sm_tiles * n_tiles;                 // per cluster work list (identical for all its CTAs)
     const int k_blocks = (g.K + BK - 1) / BK;
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
-        for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+        for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); mbar_init(&free_bar[i], CL); }
         for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 128); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -142,6 +176,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    if (CL > 1) cluster_sync_all();          // every CTA's barriers are initialised before any remote arrive / multicast
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_base_slot;
 
@@ -149,16 +184,22 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         // ===== TMA producer =====
         if (elect_one()) {
             uint32_t it = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
+            for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+                const int m_blk = (tile / n_tiles) * CL + (int)rank, n_blk = tile % n_tiles;
                 for (int kb = 0; kb < k_blocks; ++kb, ++it) {
                     const int st = it % STAGES;
                     const uint32_t ph = (it / STAGES) & 1;
-                    mbar_wait(&empty_bar[st], ph ^ 1);
+                    mbar_wait(CL > 1 ? &free_bar[st] : &empty_bar[st], ph ^ 1);
                     mbar_expect_tx(&full_bar[st], STAGE_BYTES);
                     unsigned char *sa = tiles + st * STAGE_BYTES;
                     tma_load_2d(sa, &tmA, &full_bar[st], kb * BK, m_blk * BM);
-                    tma_load_2d(sa + A_BYTES, &tmB, &full_bar[st], kb * BK, n_blk * BN);
+                    if (CL > 1) {   // my 1/CL slice of the weight tile, multicast to the whole cluster
+                        constexpr int SL = BN / CL;
+                        tma_load_2d_mc(sa + A_BYTES + rank * (SL * BK * 2), &tmB, &full_bar[st], kb * BK, n_blk * BN + (int)rank * SL,
+                                       (uint16_t)((1u << CL) - 1));
+                    } else {
+                        tma_load_2d(sa + A_BYTES, &tmB, &full_bar[st], kb * BK, n_blk * BN);
+                    }
                 }
             }
         }
@@ -167,7 +208,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         if (elect_one()) {
             constexpr uint32_t idesc = make_idesc(BM, BN);
             uint32_t it = 0, tcount = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcount) {
+            for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++tcount) {
                 const int acc = tcount & 1;
                 const uint32_t aph = (tcount >> 1) & 1;
                 mbar_wait(&tempty_bar[acc], aph ^ 1);            // epilogue has drained this accumulator
@@ -188,12 +229,23 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 umma_commit(&tfull_bar[acc]);                    // accumulator complete
             }
         }
+    } else if (warp == 6) {
+        // ===== relay: local "stage consumed" -> free barrier of every CTA in the cluster =====
+        if (CL > 1 && elect_one()) {
+            uint32_t it = 0;
+            for (int tile = cluster_id; tile < num_tiles; tile += num_clusters)
+                for (int kb = 0; kb < k_blocks; ++kb, ++it) {
+                    const int st = it % STAGES;
+                    mbar_wait(&empty_bar[st], (it / STAGES) & 1);
+                    for (uint32_t r = 0; r < (uint32_t)CL; ++r) mbar_arrive_remote(&free_bar[st], r);
+                }
+        }
     } else {
         // ===== epilogue warps 2..5: TMEM lane quadrant = warp % 4 =====
         const int quad = warp & 3;
         uint32_t tcount = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcount) {
-            const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
+        for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++tcount) {
+            const int m_blk = (tile / n_tiles) * CL + (int)rank, n_blk = tile % n_tiles;
             const int acc = tcount & 1;
             const uint32_t aph = (tcount >> 1) & 1;
             mbar_wait(&tfull_bar[acc], aph);
@@ -243,6 +295,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    if (CL > 1) cluster_sync_all();          // no CTA leaves while a peer may still multicast into it / arrive on its barriers
     if (warp == 1) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
     }
@@ -277,14 +330,14 @@ static int make_map(CUtensorMap *m, const void *base, int64_t rows, int64_t cols
     return 0;
 }
 
-template <int BN> static int launch_gemm(const zg_gemm_params &p, cudaStream_t s) {
+template <int BN, int CL> static int launch_gemm(const zg_gemm_params &p, cudaStream_t s) {
     CUtensorMap tmA, tmB;
     if (int rc = make_map(&tmA, p.A, p.M, p.K, p.lda, G_BM)) return rc;
-    if (int rc = make_map(&tmB, p.B, p.N, p.K, p.ldb, BN)) return rc;
+    if (int rc = make_map(&tmB, p.B, p.N, p.K, p.ldb, BN / CL)) return rc;
     GemmArgs g{reinterpret_cast<__nv_bfloat16 *>(p.C), reinterpret_cast<const __nv_bfloat16 *>(p.bias), p.out_rowmap, p.ldc, p.M, p.N, p.K,
                p.rows_per_batch > 0 ? p.rows_per_batch : p.M};
     const int smem = G_STAGES * (G_BM * G_BK * 2 + BN * G_BK * 2) + 1024 + 256;
-    auto kern = gemm_bf16_tn_kernel<BN>;
+    auto kern = gemm_bf16_tn_kernel<BN, CL>;
     static bool attr = false;
     if (!attr) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -297,11 +350,46 @@ template <int BN> static int launch_gemm(const zg_gemm_params &p, cudaStream_t s
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     }
-    const int tiles = ((p.M + G_BM - 1) / G_BM) * ((p.N + BN - 1) / BN);
-    const int grid = tiles < sms ? tiles : sms;
-    kern<<<grid, G_THREADS, smem, s>>>(tmA, tmB, g);
+    const int m_tiles = (p.M + G_BM - 1) / G_BM, n_tiles = (p.N + BN - 1) / BN;
+    const int work = ((m_tiles + CL - 1) / CL) * n_tiles;          // cluster work items
+    int clusters = sms / CL;
+    if (work < clusters) clusters = work;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(clusters * CL);
+    cfg.blockDim = dim3(G_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = CL;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmA, tmB, g);
     zg_count_launch();
+    if (e != cudaSuccess) return zg_set_error("gemm_bf16_tn: launch failed: %s", cudaGetErrorString(e));
     return zg_check_launch("gemm_bf16_tn");
+}
+
+// cluster size: ZG_GEMM_CLUSTER = 1 | 2 | 4 (default 2 when the problem has at least that many row tiles)
+static int gemm_cluster_setting() {
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("ZG_GEMM_CLUSTER");
+        v = e ? atoi(e) : 2;
+        if (v != 1 && v != 2 && v != 4) v = 2;
+    }
+    return v;
+}
+
+template <int BN> static int launch_gemm_cl(const zg_gemm_params &p, cudaStream_t s) {
+    int cl = gemm_cluster_setting();
+    const int m_tiles = (p.M + G_BM - 1) / G_BM;
+    while (cl > 1 && m_tiles < cl) cl >>= 1;
+    if (cl == 4) return launch_gemm<BN, 4>(p, s);
+    if (cl == 2) return launch_gemm<BN, 2>(p, s);
+    return launch_gemm<BN, 1>(p, s);
 }
 
 }  // namespace zg
@@ -315,7 +403,7 @@ extern "C" int zg_gemm_bf16_tn(const zg_gemm_params *pp, void *stream) {
     ZG_REQUIRE((reinterpret_cast<uintptr_t>(p.A) & 15) == 0 && (reinterpret_cast<uintptr_t>(p.B) & 15) == 0, "gemm_bf16_tn: A and B must be 16-byte aligned");
     ZG_REQUIRE(!p.out_rowmap || (p.rows_per_batch > 0 && p.M % p.rows_per_batch == 0), "gemm_bf16_tn: out_rowmap needs rows_per_batch dividing M");
     cudaStream_t s = (cudaStream_t)stream;
-    if (p.N > 128) return zg::launch_gemm<256>(p, s);
-    if (p.N > 64) return zg::launch_gemm<128>(p, s);
-    return zg::launch_gemm<64>(p, s);
+    if (p.N > 128) return zg::launch_gemm_cl<256>(p, s);
+    if (p.N > 64) return zg::launch_gemm_cl<128>(p, s);
+    return zg::launch_gemm_cl<64>(p, s);
 }
