@@ -24,15 +24,16 @@
 // weight tile from L2.  The CTAs of a cluster work on CL vertically adjacent output tiles that share the
 // weight tile; each CTA fetches 1/CL of it and TMA-multicasts the slice into the shared memory of all CL CTAs,
 // cutting the per-CTA L2 traffic per k-block from 48 KB to 16 + 32/CL KB.  A stage may only be overwritten
-// once EVERY CTA of the cluster has consumed it, so each CTA runs a relay warp that forwards its local
-// "stage consumed" (tcgen05.commit) to a `free` barrier in all CTAs with remote mbarrier arrives.
+// once EVERY CTA of the cluster has consumed it: each CTA's MMA warp signals "stage consumed" with a MULTICAST
+// tcgen05.commit to the `free` barrier (arrival count CL) of all CTAs.  (A first version relayed the local commit
+// with remote mbarrier arrives from a helper warp: correct but 2.2x / 5.6x slower at CL = 2 / 4, round-1 run 10.)
 #include "zg_common.cuh"
 #include <cuda.h>
 #include <stdlib.h>
 
 namespace zg {
 
-constexpr int G_BM = 128, G_BK = 64, G_STAGES = 4, G_UMMA_K = 16, G_THREADS = 224;   // 7 warps: TMA, MMA, 4 epilogue, relay
+constexpr int G_BM = 128, G_BK = 64, G_STAGES = 4, G_UMMA_K = 16, G_THREADS = 192;   // 6 warps: TMA, MMA, 4 epilogue
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -118,6 +119,12 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_c, uint64_t adesc, uint64
 }
 __device__ __forceinline__ void umma_commit(uint64_t *bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// the same completion signalled to the barrier at this offset in EVERY CTA of `mask` (hardware multicast:
+// no software relay on the stage-release path)
+__device__ __forceinline__ void umma_commit_mc(uint64_t *bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)), "h"(mask)
+                 : "memory");
 }
 __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&v)[32]) {
     asm volatile(
@@ -224,23 +231,14 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
                     for (int k = 0; k < BK / G_UMMA_K; ++k)      // +32 B per K=16 step inside the 128-byte swizzle atom
                         umma_f16(tmem_c, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
-                    umma_commit(&empty_bar[st]);                 // smem stage free once these MMAs retire
+                    // smem stage free once these MMAs retire; with clusters every CTA of the cluster is told
+                    if (CL > 1) umma_commit_mc(&free_bar[st], (uint16_t)((1u << CL) - 1));
+                    else umma_commit(&empty_bar[st]);
                 }
                 umma_commit(&tfull_bar[acc]);                    // accumulator complete
             }
         }
-    } else if (warp == 6) {
-        // ===== relay: local "stage consumed" -> free barrier of every CTA in the cluster =====
-        if (CL > 1 && elect_one()) {
-            uint32_t it = 0;
-            for (int tile = cluster_id; tile < num_tiles; tile += num_clusters)
-                for (int kb = 0; kb < k_blocks; ++kb, ++it) {
-                    const int st = it % STAGES;
-                    mbar_wait(&empty_bar[st], (it / STAGES) & 1);
-                    for (uint32_t r = 0; r < (uint32_t)CL; ++r) mbar_arrive_remote(&free_bar[st], r);
-                }
-        }
-    } else {
+    } else if (warp < 6) {
         // ===== epilogue warps 2..5: TMEM lane quadrant = warp % 4 =====
         const int quad = warp & 3;
         uint32_t tcount = 0;
