@@ -145,17 +145,22 @@ struct GemmArgs {
     const int32_t *out_rowmap;
     int64_t ldc;
     int M, N, K, rows_per_batch;
+    int tma_store;      // 1: epilogue goes through smem + TMA store (needs 16-byte aligned C rows)
 };
 
 template <int BN, int CL>
 __global__ void __launch_bounds__(G_THREADS, 1)
-gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmArgs g) {
+gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const __grid_constant__ CUtensorMap tmC, const GemmArgs g) {
     constexpr int BM = G_BM, BK = G_BK, STAGES = G_STAGES;
     constexpr uint32_t A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
     constexpr uint32_t TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
     extern __shared__ __align__(1024) unsigned char gsm[];
     unsigned char *tiles = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(gsm) + 1023) & ~(uintptr_t)1023);
-    uint64_t *full_bar = reinterpret_cast<uint64_t *>(tiles + STAGES * STAGE_BYTES);
+    // epilogue staging: per epilogue warp two (32 rows x 128 B) swizzled buffers for the TMA store
+    constexpr uint32_t EPI_BYTES = 4 * 2 * 32 * 128;
+    unsigned char *epi = tiles + STAGES * STAGE_BYTES;
+    uint64_t *full_bar = reinterpret_cast<uint64_t *>(epi + EPI_BYTES);
     uint64_t *empty_bar = full_bar + STAGES;
     uint64_t *tfull_bar = empty_bar + STAGES;     // [2] accumulator ready
     uint64_t *tempty_bar = tfull_bar + 2;         // [2] accumulator drained
@@ -255,13 +260,24 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 drow = (int64_t)bidx * g.rows_per_batch + g.out_rowmap[row - bidx * g.rows_per_batch];
             }
             __nv_bfloat16 *crow = g.C + drow * g.ldc;
+            if (g.tma_store) {
+                // ---- coalesced path: TMEM -> registers -> bf16 -> swizzled smem -> TMA store (clips M/N edges) ----
+                unsigned char *ebuf = epi + (warp - 2) * (2 * 32 * 128);
 #pragma unroll 1
-            for (int c0 = 0; c0 < BN; c0 += 32) {
-                uint32_t v[32];
-                tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + c0), v);
-                const int col0 = n_blk * BN + c0;
-                if (row < g.M && col0 < g.N) {
-                    if (col0 + 32 <= g.N && ((reinterpret_cast<uintptr_t>(crow + col0) & 15) == 0)) {
+                for (int c0 = 0; c0 < BN; c0 += 64) {
+                    if (n_blk * BN + c0 >= g.N) break;                     // whole chunk outside the matrix
+                    unsigned char *buf = ebuf + ((c0 >> 6) & 1) * (32 * 128);
+                    // the TMA store that last read this buffer (two chunks ago) must have finished reading it
+                    if (lane == 0) {
+                        if (BN >= 128) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                        else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");     // one chunk per tile: same buffer every time
+                    }
+                    __syncwarp();
+#pragma unroll
+                    for (int hh = 0; hh < 2; ++hh) {
+                        uint32_t v[32];
+                        tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + c0 + hh * 32), v);
+                        const int col0 = n_blk * BN + c0 + hh * 32;
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
                             uint32_t o[4];
@@ -269,21 +285,59 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                             for (int i = 0; i < 4; ++i) {
                                 float a = __uint_as_float(v[j * 8 + 2 * i]), b2 = __uint_as_float(v[j * 8 + 2 * i + 1]);
                                 if (g.bias) {
-                                    a += __bfloat162float(g.bias[col0 + j * 8 + 2 * i]);
-                                    b2 += __bfloat162float(g.bias[col0 + j * 8 + 2 * i + 1]);
+                                    const int cc = col0 + j * 8 + 2 * i;
+                                    if (cc < g.N) a += __bfloat162float(g.bias[cc]);
+                                    if (cc + 1 < g.N) b2 += __bfloat162float(g.bias[cc + 1]);
                                 }
                                 __nv_bfloat162 h = __floats2bfloat162_rn(a, b2);
                                 o[i] = *reinterpret_cast<uint32_t *>(&h);
                             }
-                            *reinterpret_cast<uint4 *>(crow + col0 + j * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+                            // row = lane, 16-byte chunk index (hh * 4 + j) XOR (row % 8): the 128-byte swizzle the TMA expects
+                            const int chunk = (hh * 4 + j) ^ (lane & 7);
+                            *reinterpret_cast<uint4 *>(buf + lane * 128 + chunk * 16) = make_uint4(o[0], o[1], o[2], o[3]);
                         }
-                    } else {
-                        for (int i = 0; i < 32; ++i)
-                            if (col0 + i < g.N) {
-                                float a = __uint_as_float(v[i]);
-                                if (g.bias) a += __bfloat162float(g.bias[col0 + i]);
-                                crow[col0 + i] = __float2bfloat16_rn(a);
+                    }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> async proxy
+                    __syncwarp();
+                    if (lane == 0) {
+                        asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(&tmC), "r"(smem_u32(buf)),
+                                     "r"(n_blk * BN + c0), "r"(m_blk * BM + quad * 32)
+                                     : "memory");
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    }
+                }
+            } else {
+                // ---- direct path (row scatter through out_rowmap, or unaligned C): per-thread 16-byte stores ----
+#pragma unroll 1
+                for (int c0 = 0; c0 < BN; c0 += 32) {
+                    uint32_t v[32];
+                    tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + c0), v);
+                    const int col0 = n_blk * BN + c0;
+                    if (row < g.M && col0 < g.N) {
+                        if (col0 + 32 <= g.N && ((reinterpret_cast<uintptr_t>(crow + col0) & 15) == 0)) {
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                uint32_t o[4];
+#pragma unroll
+                                for (int i = 0; i < 4; ++i) {
+                                    float a = __uint_as_float(v[j * 8 + 2 * i]), b2 = __uint_as_float(v[j * 8 + 2 * i + 1]);
+                                    if (g.bias) {
+                                        a += __bfloat162float(g.bias[col0 + j * 8 + 2 * i]);
+                                        b2 += __bfloat162float(g.bias[col0 + j * 8 + 2 * i + 1]);
+                                    }
+                                    __nv_bfloat162 h = __floats2bfloat162_rn(a, b2);
+                                    o[i] = *reinterpret_cast<uint32_t *>(&h);
+                                }
+                                *reinterpret_cast<uint4 *>(crow + col0 + j * 8) = make_uint4(o[0], o[1], o[2], o[3]);
                             }
+                        } else {
+                            for (int i = 0; i < 32; ++i)
+                                if (col0 + i < g.N) {
+                                    float a = __uint_as_float(v[i]);
+                                    if (g.bias) a += __bfloat162float(g.bias[col0 + i]);
+                                    crow[col0 + i] = __float2bfloat16_rn(a);
+                                }
+                        }
                     }
                 }
             }
@@ -291,6 +345,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             mbar_arrive(&tempty_bar[acc]);
         }
     }
+    if (warp >= 2 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // my TMA stores have landed
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (CL > 1) cluster_sync_all();          // no CTA leaves while a peer may still multicast into it / arrive on its barriers
@@ -315,7 +370,7 @@ static EncodeTiledFn get_encode() {
 }
 
 // 2-D row-major bf16 matrix (rows x cols, leading dimension ld elements) -> tensor map with a (box_rows x 64) box
-static int make_map(CUtensorMap *m, const void *base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+static int make_map(CUtensorMap *m, const void *base, int64_t rows, int64_t cols, int64_t ld, int box_rows, bool l2_promote = true) {
     EncodeTiledFn enc = get_encode();
     if (!enc) return zg_set_error("gemm_bf16_tn: cuTensorMapEncodeTiled not available from the driver");
     cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
@@ -323,18 +378,25 @@ static int make_map(CUtensorMap *m, const void *base, int64_t rows, int64_t cols
     cuuint32_t box[2] = {(cuuint32_t)G_BK, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                     CU_TENSOR_MAP_SWIZZLE_128B, l2_promote ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return zg_set_error("gemm_bf16_tn: cuTensorMapEncodeTiled failed (%d)", (int)r);
     return 0;
 }
 
 template <int BN, int CL> static int launch_gemm(const zg_gemm_params &p, cudaStream_t s) {
-    CUtensorMap tmA, tmB;
+    CUtensorMap tmA, tmB, tmC;
     if (int rc = make_map(&tmA, p.A, p.M, p.K, p.lda, G_BM)) return rc;
     if (int rc = make_map(&tmB, p.B, p.N, p.K, p.ldb, BN / CL)) return rc;
+    const bool tma_store_ok = !p.out_rowmap && p.ldc % 8 == 0 && (reinterpret_cast<uintptr_t>(p.C) & 15) == 0;
+    if (tma_store_ok) {
+        if (int rc = make_map(&tmC, p.C, p.M, p.N, p.ldc, 32, false)) return rc;
+    } else {
+        tmC = tmA;     // unused by the direct-store epilogue
+    }
     GemmArgs g{reinterpret_cast<__nv_bfloat16 *>(p.C), reinterpret_cast<const __nv_bfloat16 *>(p.bias), p.out_rowmap, p.ldc, p.M, p.N, p.K,
-               p.rows_per_batch > 0 ? p.rows_per_batch : p.M};
-    const int smem = G_STAGES * (G_BM * G_BK * 2 + BN * G_BK * 2) + 1024 + 256;
+               p.rows_per_batch > 0 ? p.rows_per_batch : p.M, tma_store_ok ? 1 : 0};
+    const int smem = G_STAGES * (G_BM * G_BK * 2 + BN * G_BK * 2) + 4 * 2 * 32 * 128 + 1024 + 256;
     auto kern = gemm_bf16_tn_kernel<BN, CL>;
     static bool attr = false;
     if (!attr) {
@@ -364,7 +426,7 @@ template <int BN, int CL> static int launch_gemm(const zg_gemm_params &p, cudaSt
     at[0].val.clusterDim.z = 1;
     cfg.attrs = at;
     cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmA, tmB, g);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmC, g);
     zg_count_launch();
     if (e != cudaSuccess) return zg_set_error("gemm_bf16_tn: launch failed: %s", cudaGetErrorString(e));
     return zg_check_launch("gemm_bf16_tn");
