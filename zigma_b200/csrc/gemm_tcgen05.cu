@@ -33,7 +33,9 @@
 
 namespace zg {
 
-constexpr int G_BM = 128, G_BK = 64, G_STAGES = 4, G_UMMA_K = 16, G_THREADS = 192;   // 6 warps: TMA, MMA, 4 epilogue
+constexpr int G_BM = 128, G_BK = 64, G_UMMA_K = 16, G_THREADS = 192;   // 6 warps: TMA, MMA, 4 epilogue
+// smem ring depth: as many (128 + BN) x 64 bf16 stages as fit next to the 32 KB epilogue staging
+__host__ __device__ constexpr int gemm_stages(int BN) { return BN == 256 ? 4 : (BN == 128 ? 6 : 8); }
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -152,7 +154,7 @@ template <int BN, int CL>
 __global__ void __launch_bounds__(G_THREADS, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmC, const GemmArgs g) {
-    constexpr int BM = G_BM, BK = G_BK, STAGES = G_STAGES;
+    constexpr int BM = G_BM, BK = G_BK, STAGES = gemm_stages(BN);
     constexpr uint32_t A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
     constexpr uint32_t TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
     extern __shared__ __align__(1024) unsigned char gsm[];
@@ -396,7 +398,7 @@ template <int BN, int CL> static int launch_gemm(const zg_gemm_params &p, cudaSt
     }
     GemmArgs g{reinterpret_cast<__nv_bfloat16 *>(p.C), reinterpret_cast<const __nv_bfloat16 *>(p.bias), p.out_rowmap, p.ldc, p.M, p.N, p.K,
                p.rows_per_batch > 0 ? p.rows_per_batch : p.M, tma_store_ok ? 1 : 0};
-    const int smem = G_STAGES * (G_BM * G_BK * 2 + BN * G_BK * 2) + 4 * 2 * 32 * 128 + 1024 + 256;
+    const int smem = gemm_stages(BN) * (G_BM * G_BK * 2 + BN * G_BK * 2) + 4 * 2 * 32 * 128 + 1024 + 512;
     auto kern = gemm_bf16_tn_kernel<BN, CL>;
     static bool attr = false;
     if (!attr) {
@@ -463,7 +465,17 @@ extern "C" int zg_gemm_bf16_tn(const zg_gemm_params *pp, void *stream) {
     ZG_REQUIRE((reinterpret_cast<uintptr_t>(p.A) & 15) == 0 && (reinterpret_cast<uintptr_t>(p.B) & 15) == 0, "gemm_bf16_tn: A and B must be 16-byte aligned");
     ZG_REQUIRE(!p.out_rowmap || (p.rows_per_batch > 0 && p.M % p.rows_per_batch == 0), "gemm_bf16_tn: out_rowmap needs rows_per_batch dividing M");
     cudaStream_t s = (cudaStream_t)stream;
-    if (p.N > 128) return zg::launch_gemm_cl<256>(p, s);
-    if (p.N > 64) return zg::launch_gemm_cl<128>(p, s);
+    // tile width: the candidate wasting the least MMA work on the ragged last column tile (ties -> wider tile)
+    static int bn_env = -1;
+    if (bn_env < 0) { const char *e = getenv("ZG_GEMM_BN"); bn_env = e ? atoi(e) : 0; }
+    int bn = bn_env;
+    if (bn != 64 && bn != 128 && bn != 256) {
+        auto padded = [&](int b) { return ((p.N + b - 1) / b) * b; };
+        bn = 256;
+        if (padded(128) < padded(bn)) bn = 128;
+        if (padded(64) < padded(bn)) bn = 64;
+    }
+    if (bn == 256) return zg::launch_gemm_cl<256>(p, s);
+    if (bn == 128) return zg::launch_gemm_cl<128>(p, s);
     return zg::launch_gemm_cl<64>(p, s);
 }
