@@ -353,7 +353,8 @@ def main():
         "config": {"workload": f"zigzag8_b1: ZigMa D=640 depth=18 img 32 patch 1 zigzagN8, bs={bs}/GPU, fixed-grid Euler (linspace(0,1,50))",
                    "global_batch": bs * world, "seq_len": L_TOKENS, "parallelism": f"dp{world}",
                    "l2_policy": "no flush: per-step working set (xz alone 335 MB per layer) >> 126 MB L2",
-                   "denoiser_steps_per_s": K / (ms * 1e-3), "cuda_graph": not args.no_graph, "collective": "one all_gather of final latents, inside the timed region"},
+                   "denoiser_steps_per_s": K / (ms * 1e-3), "cuda_graph": not args.no_graph,
+                   "gemm": "hand-written tcgen05 (zg_gemm_bf16_tn)" if os.environ.get("ZIGMA_TCGEN05", "1") == "1" else "library (cuBLAS)", "collective": "one all_gather of final latents, inside the timed region"},
         "clocks": clk,
         "e2e": {"value": bs * world * L_TOKENS * K / (e2e_ms * 1e-3), "unit": "tokens/s",
                 "h2d_bytes_per_step": z0.numel() * z0.element_size() + bs * 2, "d2h_bytes_per_step": z0.numel() * z0.element_size(),

@@ -14,8 +14,9 @@ What the reference executes per block and what repla
 
 Numerics follow the reference's bf16 path rounding for rounding (every tensor the reference
 materialises in bf16 is rounded to bf16 at the same point), so results agree with the reference
-to fp32-accumulation-order noise.  The dense projections are library GEMMs (cuBLAS through
-torch.matmul) unless ``ZIGMA_TCGEN05=1`` routes the bf16 ones through ``zg_gemm_bf16_tn``.
+to fp32-accumulation-order noise.  The dense bf16 projections run on the hand-written tcgen05 kernel
+``zg_gemm_bf16_tn`` (``ZIGMA_TCGEN05=0`` switches them to the library GEMM for A/B timing; fp32 models always
+use the library GEMM -- the tensor-core kernel is bf16 only).
 """
 import os
 
@@ -32,9 +33,9 @@ def _i32(t):
 
 
 def _linear(x2d, weight, bias=None):
-    """(M, K) @ (N, K)^T.  bf16 goes to the hand-written tcgen05 kernel when ZIGMA_TCGEN05=1, else (and for
-    fp32 / fp16) to the library GEMM."""
-    if x2d.dtype == torch.bfloat16 and os.environ.get("ZIGMA_TCGEN05", "0") == "1" and x2d.stride(0) % 8 == 0 and weight.stride(0) % 8 == 0:
+    """(M, K) @ (N, K)^T.  bf16 goes to the hand-written tcgen05 kernel (zg_gemm_bf16_tn; ZIGMA_TCGEN05=0 routes
+    it to the library GEMM instead, e.g. for A/B timing); fp32 / fp16 always use the library GEMM."""
+    if x2d.dtype == torch.bfloat16 and os.environ.get("ZIGMA_TCGEN05", "1") == "1" and x2d.stride(0) % 8 == 0 and weight.stride(0) % 8 == 0:
         from .gemm import linear_bf16
         return linear_bf16(x2d, weight, bias)
     return F.linear(x2d, weight, bias)
