@@ -210,11 +210,12 @@ template <> __device__ __forceinline__ void cvt4<__half>(const Raw4<__half> &r, 
 
 template <typename T, int MAXQ>
 __global__ void __launch_bounds__(128, (MAXQ <= 6) ? 6 : 1) block_tail_kernel(const zg_block_tail_params p) {
-    const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    // persistent warps: a warp walks rows with a grid stride (no CTA relaunch between rows)
     const int lane = threadIdx.x & 31;
     const int64_t nrows = (int64_t)p.batch * p.seqlen;
-    if (row >= nrows) return;
+    const int64_t wstride = ((int64_t)gridDim.x * blockDim.x) >> 5;
     const int D = p.dim, nq = D >> 2;
+    for (int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < nrows; row += wstride) {
     const int b = (int)(row / p.seqlen), l = (int)(row % p.seqlen);
     const T *x = p.x ? reinterpret_cast<const T *>(p.x) + row * D : nullptr;
     const T *xw = reinterpret_cast<const T *>(p.x_norm_w);
@@ -324,7 +325,7 @@ __global__ void __launch_bounds__(128, (MAXQ <= 6) ? 6 : 1) block_tail_kernel(co
                 st4<T>(normed, 4 * q, o);
             }
         }
-        return;
+        continue;
     }
 #pragma unroll
     for (int k = 0; k < MAXQ; ++k) {
@@ -341,6 +342,7 @@ __global__ void __launch_bounds__(128, (MAXQ <= 6) ? 6 : 1) block_tail_kernel(co
                 st4<T>(modded, 4 * q, o);
             }
         }
+    }
     }
 }
 
