@@ -177,11 +177,6 @@ int zg_add_norm_bwd(const zg_norm_bwd_params *p, void *stream);
  * gate/shift/scale are (batch, dim) with row stride mod_rs (views into adaLN's (batch, 3*dim)).
  * With final != 0 the last two lines become the model tail (model_zigma.py:971-984,335):
  *     normed = LayerNorm_noaffine(normed, eps=1e-6) and modded is not written.
- * x may be NULL when x_norm_w is given: x is then RECOMPUTED as the previous block's norm output,
- *     x = round(residual * rsqrt(mean(residual^2) + x_eps) * x_norm_w),
- * from the residual row the kernel reads anyway -- bit identical to the `normed` the previous call would have
- * written, and 25 % less HBM traffic (the (batch, seqlen, dim) `normed` tensor is neither written nor re-read;
- * pass normed = NULL as well).
  * Intermediate roundings replicate the reference's unfused bf16 path: hidden and normed are
  * rounded to `dtype` where the reference materialises them.
  */
@@ -191,11 +186,10 @@ typedef struct {
     const int32_t *rowmap;
     float *residual_out;
     void *normed, *modded;
-    const void *x_norm_w;
     int64_t mod_rs;
     int32_t batch, seqlen, dim;
     int32_t dtype, final_layer;
-    float eps, x_eps;
+    float eps;
 } zg_block_tail_params;
 
 int zg_block_tail_fwd(const zg_block_tail_params *p, void *stream);

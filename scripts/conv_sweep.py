@@ -25,7 +25,4 @@ x = torch.randn(bs, L, D, device=dev).bfloat16(); mix = torch.randn(bs, L, D, de
 mods = torch.randn(bs, 3 * D, device=dev).bfloat16(); res = torch.randn(bs, L, D, device=dev); nw = torch.ones(D, device=dev).bfloat16()
 rev = torch.from_numpy(reverse_permut_np(zigzag_path(32)[1])).to(dev).to(torch.int32)
 t2 = timeit(lambda: block_tail(x, mix, mods[:, :D], mods[:, D:2*D], mods[:, 2*D:], nw, res, rev, 1e-5))
-res0, _, _ = block_tail(x, None, None, mods[:, :D], mods[:, D:2*D], nw, None, None, 1e-5, want_normed=False)
-t3 = timeit(lambda: block_tail(None, mix, mods[:, :D], mods[:, D:2*D], mods[:, 2*D:], nw, res0, rev, 1e-5, x_norm_w=nw, x_eps=1e-5, want_normed=False))
-print(f"block_tail with recomputed x (no normed in/out): {t3*1e3:.1f} us ({bs*L*D*(2+4+4+2)/t3/1e6:.0f} GB/s of 503 MB)")
 print(f"ZG_CONV_VEC={os.environ.get('ZG_CONV_VEC','default(4)')}: conv {t*1e3:.1f} us ({2*2*bs*L*E/t/1e6:.0f} GB/s of 335 MB)   block_tail {t2*1e3:.1f} us ({bs*L*D*(2+2+4+4+2+2)/t2/1e6:.0f} GB/s of 671 MB)")

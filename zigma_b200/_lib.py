@@ -61,10 +61,10 @@ class NormBwdParams(C.Structure):
 
 
 class BlockTailParams(C.Structure):
-    _fields_ = ([(n, vp) for n in ("x", "mix", "gate", "shift", "scale", "norm_w", "residual", "rowmap", "residual_out", "normed", "modded", "x_norm_w")]
+    _fields_ = ([(n, vp) for n in ("x", "mix", "gate", "shift", "scale", "norm_w", "residual", "rowmap", "residual_out", "normed", "modded")]
                 + [("mod_rs", i64)]
                 + [(n, i32) for n in ("batch", "seqlen", "dim", "dtype", "final_layer")]
-                + [("eps", f32), ("x_eps", f32)])
+                + [("eps", f32)])
 
 
 class GemmParams(C.Structure):

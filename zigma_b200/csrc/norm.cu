@@ -210,15 +210,13 @@ template <> __device__ __forceinline__ void cvt4<__half>(const Raw4<__half> &r, 
 
 template <typename T, int MAXQ>
 __global__ void __launch_bounds__(128, (MAXQ <= 6) ? 6 : 1) block_tail_kernel(const zg_block_tail_params p) {
-    // persistent warps: a warp walks rows with a grid stride (no CTA relaunch between rows)
+    const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     const int64_t nrows = (int64_t)p.batch * p.seqlen;
-    const int64_t wstride = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    if (row >= nrows) return;
     const int D = p.dim, nq = D >> 2;
-    for (int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < nrows; row += wstride) {
     const int b = (int)(row / p.seqlen), l = (int)(row % p.seqlen);
-    const T *x = p.x ? reinterpret_cast<const T *>(p.x) + row * D : nullptr;
-    const T *xw = reinterpret_cast<const T *>(p.x_norm_w);
+    const T *x = reinterpret_cast<const T *>(p.x) + row * D;
     const T *mix = nullptr;
     if (p.mix) {
         const int64_t src = (int64_t)b * p.seqlen + (p.rowmap ? p.rowmap[l] : l);
@@ -230,7 +228,7 @@ __global__ void __launch_bounds__(128, (MAXQ <= 6) ? 6 : 1) block_tail_kernel(co
     const T *nw = reinterpret_cast<const T *>(p.norm_w);
     const float *res = p.residual ? p.residual + row * D : nullptr;
     float *rout = p.residual_out ? p.residual_out + row * D : nullptr;
-    T *normed = p.normed ? reinterpret_cast<T *>(p.normed) + row * D : nullptr;
+    T *normed = reinterpret_cast<T *>(p.normed) + row * D;
     T *modded = p.modded ? reinterpret_cast<T *>(p.modded) + row * D : nullptr;
 
     // ---- phase 1: every streaming load of the row, back to back ---------------------------------------
@@ -240,22 +238,10 @@ __global__ void __launch_bounds__(128, (MAXQ <= 6) ? 6 : 1) block_tail_kernel(co
     for (int k = 0; k < MAXQ; ++k) {
         const int q = lane + 32 * k;
         if (q < nq) {
-            if (x) rx[k] = ldraw<T>(x, 4 * q);
+            rx[k] = ldraw<T>(x, 4 * q);
             if (mix) rm[k] = ldraw<T>(mix, 4 * q);
             if (res) rr[k] = *reinterpret_cast<const float4 *>(res + 4 * q);
         }
-    }
-    // x not given: recompute the previous block's norm output from the residual row (same arithmetic, same lane
-    // mapping and reduction order as the call that produced it -> bit identical)
-    float rstd_prev = 0.f;
-    if (!x) {
-        float ss = 0.f;
-#pragma unroll
-        for (int k = 0; k < MAXQ; ++k)
-            if (lane + 32 * k < nq) {     // same accumulation order as the `sumsq` loop below
-                ss += rr[k].x * rr[k].x; ss += rr[k].y * rr[k].y; ss += rr[k].z * rr[k].z; ss += rr[k].w * rr[k].w;
-            }
-        rstd_prev = 1.f / sqrtf(zg_warp_sum(ss) / D + p.x_eps);
     }
     // ---- phase 2: hidden = x + gate * mix; r = residual + hidden; statistics -------------------------
     float r[MAXQ][4];
@@ -264,16 +250,7 @@ __global__ void __launch_bounds__(128, (MAXQ <= 6) ? 6 : 1) block_tail_kernel(co
     for (int k = 0; k < MAXQ; ++k) {
         const int q = lane + 32 * k;
         if (q < nq) {
-            if (x) {
-                cvt4<T>(rx[k], r[k]);
-            } else {
-                float w[4];
-                ld4<T>(xw, 4 * q, w);
-                r[k][0] = round_to<T>(rr[k].x * rstd_prev * w[0]);
-                r[k][1] = round_to<T>(rr[k].y * rstd_prev * w[1]);
-                r[k][2] = round_to<T>(rr[k].z * rstd_prev * w[2]);
-                r[k][3] = round_to<T>(rr[k].w * rstd_prev * w[3]);
-            }
+            cvt4<T>(rx[k], r[k]);
             if (mix) {
                 float m[4], g[4];
                 cvt4<T>(rm[k], m);
@@ -325,13 +302,13 @@ __global__ void __launch_bounds__(128, (MAXQ <= 6) ? 6 : 1) block_tail_kernel(co
                 st4<T>(normed, 4 * q, o);
             }
         }
-        continue;
+        return;
     }
 #pragma unroll
     for (int k = 0; k < MAXQ; ++k) {
         const int q = lane + 32 * k;
         if (q < nq) {
-            if (normed) st4<T>(normed, 4 * q, r[k]);
+            st4<T>(normed, 4 * q, r[k]);
             if (modded) {
                 float sc[4], sh[4], o[4];
                 ld4<T>(scale, 4 * q, sc);
@@ -342,7 +319,6 @@ __global__ void __launch_bounds__(128, (MAXQ <= 6) ? 6 : 1) block_tail_kernel(co
                 st4<T>(modded, 4 * q, o);
             }
         }
-    }
     }
 }
 
@@ -426,9 +402,7 @@ extern "C" int zg_add_norm_bwd(const zg_norm_bwd_params *pp, void *stream) {
 extern "C" int zg_block_tail_fwd(const zg_block_tail_params *pp, void *stream) {
     ZG_REQUIRE(pp != nullptr, "block_tail_fwd: null params");
     const zg_block_tail_params &p = *pp;
-    ZG_REQUIRE(p.norm_w && (p.normed || p.modded), "block_tail_fwd: null tensor pointer");
-    ZG_REQUIRE(p.x || (p.x_norm_w && p.residual), "block_tail_fwd: x == NULL needs x_norm_w and residual to recompute it");
-    ZG_REQUIRE(!p.final_layer || p.normed, "block_tail_fwd: the final layer writes `normed`");
+    ZG_REQUIRE(p.x && p.norm_w && p.normed, "block_tail_fwd: null tensor pointer");
     ZG_REQUIRE(!p.mix || p.gate, "block_tail_fwd: mix needs gate");
     ZG_REQUIRE(!p.modded || (p.shift && p.scale), "block_tail_fwd: modded needs shift and scale");
     ZG_REQUIRE(p.dim > 0 && p.dim % 4 == 0 && p.dim <= 4 * 32 * zg::NORM_MAXQ, "block_tail_fwd: dim must be a multiple of 4 and <= %d, got %d",

@@ -41,13 +41,10 @@ def _linear(x2d, weight, bias=None):
     return F.linear(x2d, weight, bias)
 
 
-def block_tail(x, mix, gate, shift, scale, norm_w, residual, rowmap, eps, final=False, mod_div=1, want_modded=True,
-               x_norm_w=None, x_eps=1e-5, want_normed=True):
-    """zg_block_tail_fwd wrapper.  x: (Bt, L, D) contiguous or None (then recomputed from `residual` with
-    x_norm_w / x_eps, see include/zigma_b200.h); gate/shift/scale: (Bt // mod_div, D) views with a common
-    row stride.  Returns residual_out (fp32), normed (or None), modded."""
-    ref = x if x is not None else mix
-    Bt, L, D = ref.shape
+def block_tail(x, mix, gate, shift, scale, norm_w, residual, rowmap, eps, final=False, mod_div=1, want_modded=True):
+    """zg_block_tail_fwd wrapper.  x: (Bt, L, D) contiguous; gate/shift/scale: (Bt // mod_div, D)
+    views with a common row stride.  Returns residual_out (fp32), normed, modded."""
+    Bt, L, D = x.shape
     if mod_div != 1:
         # modulation vectors are per ORIGINAL batch element; expand to the folded batch (tiny)
         gate = None if gate is None else gate.repeat_interleave(mod_div, dim=0)
@@ -58,23 +55,20 @@ def block_tail(x, mix, gate, shift, scale, norm_w, residual, rowmap, eps, final=
     for m in mods:
         if m.stride(0) != rs or m.stride(1) != 1:
             raise RuntimeError("block_tail: modulation views must share one row stride")
-    if norm_w.dtype != ref.dtype:
-        norm_w = norm_w.to(ref.dtype)
-    if x_norm_w is not None and x_norm_w.dtype != ref.dtype:
-        x_norm_w = x_norm_w.to(ref.dtype)
+    if norm_w.dtype != x.dtype:
+        norm_w = norm_w.to(x.dtype)
     if residual is not None and residual.dtype != torch.float32:
         raise RuntimeError("block_tail: the residual stream must be fp32 (residual_in_fp32=True)")
-    res_out = torch.empty((Bt, L, D), dtype=torch.float32, device=ref.device) if not final else None
-    normed = torch.empty_like(ref) if (want_normed or final) else None
-    modded = torch.empty_like(ref) if (want_modded and not final) else None
+    res_out = torch.empty((Bt, L, D), dtype=torch.float32, device=x.device) if not final else None
+    normed = torch.empty_like(x)
+    modded = torch.empty_like(x) if (want_modded and not final) else None
     p = _lib.BlockTailParams()
     p.x, p.mix, p.gate, p.shift, p.scale = _lib.ptr(x), _lib.ptr(mix), _lib.ptr(gate), _lib.ptr(shift), _lib.ptr(scale)
     p.norm_w, p.residual, p.rowmap = _lib.ptr(norm_w), _lib.ptr(residual), _lib.ptr(rowmap)
     p.residual_out, p.normed, p.modded = _lib.ptr(res_out), _lib.ptr(normed), _lib.ptr(modded)
-    p.x_norm_w, p.x_eps = _lib.ptr(x_norm_w), float(x_eps)
     p.mod_rs = rs
     p.batch, p.seqlen, p.dim = Bt, L, D
-    p.dtype, p.final_layer, p.eps = _lib.dt(ref), int(final), float(eps)
+    p.dtype, p.final_layer, p.eps = _lib.dt(x), int(final), float(eps)
     _lib.call("zg_block_tail_fwd", p)
     return res_out, normed, modded
 
@@ -195,10 +189,7 @@ class ZigMaEngine:
         mods = F.linear(F.silu(c), self.ada_w, self.ada_b).view(B, depth, 3, D)     # shift, scale, gate per block
         eps = m.blocks[0].norm.eps
         lay0 = self.layers[0]
-        # block 0 head: residual = tokens (fp32), modded = modulate(RMSNorm(tokens)).  The norm output itself is
-        # never materialised between blocks: the next tail recomputes it from the residual row it reads anyway.
-        residual, _, modded = block_tail(hs, None, None, mods[:, 0, 0], mods[:, 0, 1], lay0["norm_w"], None, None, eps, want_normed=False)
-        normed = None
+        residual, normed, modded = block_tail(hs, None, None, mods[:, 0, 0], mods[:, 0, 1], lay0["norm_w"], None, None, eps)
         for i, lay in enumerate(self.layers):
             mix, rowmap, fold = self._mixer(modded, lay)
             last = i == depth - 1
@@ -207,17 +198,15 @@ class ZigMaEngine:
             gate = mods[:, i, 2]
             shift = None if last else mods[:, i + 1, 0]
             scale = None if last else mods[:, i + 1, 1]
-            kw = dict(final=last, x_norm_w=lay["norm_w"], x_eps=m.blocks[i].norm.eps, want_normed=False)
             if fold != 1:     # spatial video layer: rows are (b t, k); same memory as (b, t k)
                 Bf = B * fold
-                residual, normed, modded = block_tail(None, mix, gate, shift, scale, nw, residual.view(Bf, L // fold, D), rowmap, neps,
-                                                      mod_div=fold, **kw)
-                if last:
-                    normed = normed.view(B, L, D)
-                else:
+                residual, normed, modded = block_tail(normed.view(Bf, L // fold, D), mix, gate, shift, scale, nw,
+                                                      residual.view(Bf, L // fold, D), rowmap, neps, final=last, mod_div=fold)
+                normed = normed.view(B, L, D)
+                if not last:
                     residual, modded = residual.view(B, L, D), modded.view(B, L, D)
             else:
-                residual, normed, modded = block_tail(None, mix.view(B, L, D), gate, shift, scale, nw, residual, rowmap, neps, **kw)
+                residual, normed, modded = block_tail(normed, mix, gate, shift, scale, nw, residual, rowmap, neps, final=last)
         out = F.linear(normed, m.final_layer.linear.weight, m.final_layer.linear.bias)
         if m.video_frames > 0:
             return m.unpatchify_video(out, m.video_frames)
