@@ -27,6 +27,16 @@ out, _, ckpt, saved = _scan_fwd(u, delta, A, B, C, D, z, bias, True, want_last_s
 t_fwd_ck = timeit(lambda: _scan_fwd(u, delta, A, B, C, D, z, bias, True, want_last_state=False, want_ckpt=True))
 t_bwd = timeit(lambda: _scan_bwd(saved, ckpt, dout, True))
 print(f"bs={bs}: ours scan fwd(+ckpt) {t_fwd_ck:.3f} ms, scan bwd {t_bwd:.3f} ms")
+# token-major storage of the same problem (the engine's layout)
+tm = lambda a: a.transpose(-1, -2).contiguous().transpose(-1, -2)
+ut, deltat, zt, Bt_, Ct_, doutt = tm(u), tm(delta), tm(z), tm(B), tm(C), tm(dout)
+out_t, _, ckpt_t, saved_t = _scan_fwd(ut, deltat, A, Bt_, Ct_, D, zt, bias, True, want_last_state=False, want_ckpt=True)
+t_fwd_t = timeit(lambda: _scan_fwd(ut, deltat, A, Bt_, Ct_, D, zt, bias, True, want_last_state=False, want_ckpt=True))
+t_bwd_t = timeit(lambda: _scan_bwd(saved_t, ckpt_t, doutt, True))
+print(f"bs={bs}: ours token-major scan fwd(+ckpt) {t_fwd_t:.3f} ms, scan bwd {t_bwd_t:.3f} ms")
+m1, m2 = _scan_bwd(saved, ckpt, dout, True), _scan_bwd(saved_t, ckpt_t, doutt, True)
+print("   channel-first vs token-major grads: " + ", ".join(f"{n} {(a_.float() - b_.float()).abs().max().item():.2e}" for n, a_, b_ in
+      (("du", m1[0], m2[0]), ("ddelta", m1[1], m2[1]), ("dA", m1[2], m2[2]), ("dB", m1[3], m2[3]), ("dC", m1[4], m2[4]), ("dz", m1[7], m2[7]))))
 w = torch.randn(E, 4, device=dev, generator=g).to(dt); cb = torch.randn(E, device=dev, generator=g).to(dt)
 t_cb = timeit(lambda: _conv_bwd(u, w, cb, dout, True))
 print(f"ours conv bwd {t_cb:.3f} ms")
@@ -40,6 +50,6 @@ if ref_cuda.available():
     print(f"reference scan fwd {t_rf:.3f} ms, scan bwd {t_rb:.3f} ms, conv bwd {t_rcb:.3f} ms")
     r = ss.bwd(u, delta, A, B, C, D, z, bias, dout, x, outr, None, True, False)
     mine = _scan_bwd(saved, ckpt, dout, True)
-    for name, a_, b_ in (("du", mine[0], r[0]), ("ddelta", mine[1], r[1]), ("dA", mine[2], r[2]), ("dz", mine[7], r[7])):
+    for name, a_, b_ in (("du", mine[0], r[0]), ("ddelta", mine[1], r[1]), ("dA", mine[2], r[2]), ("dB", mine[3], r[3]), ("dC", mine[4], r[4]), ("dz", mine[7], r[7])):
         d = (a_.float() - b_.float()).abs().max().item(); m = b_.float().abs().max().item()
         print(f"   ours vs reference CUDA {name}: max|diff| {d:.3e} (max|ref| {m:.3e})")

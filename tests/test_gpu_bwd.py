@@ -31,6 +31,28 @@ def test_selective_scan_bwd_golden(name):
         check_close(req[k].grad, g["d" + k], f"{name} d{k}", atol=1e-4, max_strict_viol=1e-2)
 
 
+@pytest.mark.parametrize("name", ["t128_g1", "t131_g2", "noz"])
+def test_selective_scan_bwd_token_major(name):
+    """Same golden gradients with every activation handed over TOKEN-MAJOR ((b, l, d) storage viewed as
+    (b, d, l), the engine's layout): the dstate == 16 backward takes the strides as they come."""
+    from zigma_b200 import selective_scan_fn
+    g = gold("scan_" + name)
+    Bt, E, L, N, G, hasD, hasz, hasb, sp = [int(v) for v in g["flags"]]
+    tm = lambda a: t(a, DEV).transpose(-1, -2).contiguous().transpose(-1, -2).requires_grad_()
+    req = {k: (tm(g[k]) if k in ("u", "delta", "z", "B", "C") else t(g[k], DEV).requires_grad_())
+           for k in ("u", "delta", "A", "B", "C", "D", "z", "delta_bias")}
+    assert req["u"].stride(1) == 1 and req["B"].stride(2) == 1
+    Bm = req["B"] if G > 1 else req["B"][:, 0]
+    Cm = req["C"] if G > 1 else req["C"][:, 0]
+    out = selective_scan_fn(req["u"], req["delta"], req["A"], Bm, Cm, req["D"] if hasD else None, z=req["z"] if hasz else None,
+                            delta_bias=req["delta_bias"] if hasb else None, delta_softplus=bool(sp))
+    check_close(out, g["out"], f"{name} out (token-major, grad mode)")
+    out.backward(t(g["g"], DEV).transpose(1, 2).contiguous().transpose(1, 2))
+    names = ["u", "delta", "A", "B", "C"] + (["D"] if hasD else []) + (["z"] if hasz else []) + (["delta_bias"] if hasb else [])
+    for k in names:
+        check_close(req[k].grad, g["d" + k], f"{name} token-major d{k}", atol=1e-4, max_strict_viol=1e-2)
+
+
 def test_selective_scan_bwd_bf16():
     from zigma_b200 import selective_scan_fn
     Bt, E, L, N = 2, 96, 150, 16

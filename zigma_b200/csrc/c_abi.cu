@@ -52,7 +52,7 @@ int zg_selective_scan_fwd(const zg_scan_params *pp, void *stream) {
         ZG_REQUIRE(!varB || p.B_sn == 1 || p.dstate == 1, "selective_scan_fwd: B must have dstate stride 1 for dim-contiguous activations");
         ZG_REQUIRE(!varC || p.C_sn == 1 || p.dstate == 1, "selective_scan_fwd: C must have dstate stride 1 for dim-contiguous activations");
     }
-    ZG_REQUIRE(!p.ckpt || (p.ckpt_every > 0 && p.ckpt_every % zg::SCAN_TL == 0), "selective_scan_fwd: ckpt_every must be a positive multiple of %d", zg::SCAN_TL);
+    ZG_REQUIRE(!p.ckpt || (p.ckpt_every > 0 && p.ckpt_every % 8 == 0), "selective_scan_fwd: ckpt_every must be a positive multiple of 8");
     if (p.batch == 0 || p.seqlen == 0) return 0;
     const bool constbc = !(varB && varC);
     cudaStream_t s = (cudaStream_t)stream;

@@ -1,10 +1,10 @@
 // Selective-scan (S6) backward for sm_100a -- same mapping as the forward (scan_fwd.cuh): a thread
-// owns one channel, keeps dh / dA partial sums in registers and walks L in reverse, one 16-step chunk
-// at a time.  Replaces selective_scan_bwd_kernel (dis_mamba/csrc/selective_scan/
+// owns one channel, keeps dh / dA partial sums in registers and walks L in reverse, one 8-step chunk
+// at a time (generic fallback: dstate < 16; the dstate == 16 case runs scan_bwd_q4.cuh).  Replaces selective_scan_bwd_kernel (dis_mamba/csrc/selective_scan/
 // selective_scan_bwd_kernel.cuh:75-489): no block-wide reverse scan, no BlockExchange.
 //
 // Per chunk: (1) the forward recurrence is recomputed from the checkpoint the forward kernel wrote at
-// the chunk boundary (ckpt_every == 16), parking h_{l-1} of every step in shared memory
+// the chunk boundary (ckpt_every == 8), parking h_{l-1} of every step in shared memory
 // ([step][state][thread]: conflict free); (2) the chunk is walked backwards:
 //     dh_l = dy_l C_l + a_{l+1} dh_{l+1}            dC_l += dy_l h_l          dB_l += dh_l d_l u_l
 //     du_l = dy_l D + d_l sum_n dh_l B_l             dA   += dh_l h_{l-1} a_l d_l
@@ -15,11 +15,12 @@
 // (warp, state, step); dA/dD/ddelta_bias are accumulated over the whole row in registers and added
 // once at the end (the reference uses fp32 atomics for all of these too, :297-316,467-488).
 #include "zg_common.cuh"
+#include "scan_bwd_q4.cuh"
 
 namespace zg {
 
 constexpr int BWD_CH = 64;
-constexpr int BWD_TS = 16;
+constexpr int BWD_TS = Q4_TS;   // == ckpt_every of the forward (8)
 
 template <typename T, int NS>
 __global__ void __launch_bounds__(BWD_CH) scan_bwd_kernel(const zg_scan_bwd_params q) {
@@ -207,6 +208,14 @@ template <typename T, int NS> static int launch_scan_bwd(const zg_scan_bwd_param
 }
 
 template <typename T> static int scan_bwd_t(const zg_scan_bwd_params &q, cudaStream_t s) {
+    const int rc = try_launch_scan_bwd_q4<T>(q, s);
+    if (rc >= 0) return rc;
+    {   // generic kernel: one thread per channel walking its own row
+        const zg_scan_params &p = q.fwd;
+    ZG_REQUIRE(p.u_sl == 1 && p.delta_sl == 1 && q.dout_sl == 1 && q.du_sl == 1 && q.ddelta_sl == 1 && (!p.z || (p.z_sl == 1 && q.dz && q.dz_sl == 1)) &&
+                   (p.B_sl == 1 || p.seqlen == 1) && (p.C_sl == 1 || p.seqlen == 1),
+               "selective_scan_bwd: the generic kernel (dstate != 16) needs seq-contiguous tensors");
+    }
     if (q.fwd.dstate <= 8) return launch_scan_bwd<T, 8>(q, s);
     if (q.fwd.dstate <= 16) return launch_scan_bwd<T, 16>(q, s);
     return zg_set_error("selective_scan_bwd: dstate <= 16 supported, got %d", q.fwd.dstate);
@@ -220,9 +229,7 @@ extern "C" int zg_selective_scan_bwd(const zg_scan_bwd_params *qq, void *stream)
     const zg_scan_params &p = q.fwd;
     ZG_REQUIRE(p.u && p.delta && p.A && p.B && p.C && q.dout && q.du && q.ddelta && q.dA && q.dB && q.dC, "selective_scan_bwd: null tensor pointer");
     ZG_REQUIRE((p.flags & ZG_SCAN_VARIABLE_B) && (p.flags & ZG_SCAN_VARIABLE_C), "selective_scan_bwd: only input-dependent B and C are supported");
-    ZG_REQUIRE(p.u_sl == 1 && p.delta_sl == 1 && q.dout_sl == 1 && q.du_sl == 1 && q.ddelta_sl == 1 && (!p.z || (p.z_sl == 1 && q.dz && q.dz_sl == 1)) &&
-                   (p.B_sl == 1 || p.seqlen == 1) && (p.C_sl == 1 || p.seqlen == 1),
-               "selective_scan_bwd: seq-contiguous tensors required");
+    ZG_REQUIRE(!p.z || q.dz, "selective_scan_bwd: dz output required when z is given");
     ZG_REQUIRE(p.ckpt != nullptr && p.ckpt_every == zg::BWD_TS, "selective_scan_bwd: needs the forward checkpoints with ckpt_every == %d", zg::BWD_TS);
     ZG_REQUIRE(p.ngroups >= 1 && p.dim % p.ngroups == 0, "selective_scan_bwd: bad groups");
     if (p.batch == 0 || p.seqlen == 0) return 0;

@@ -265,6 +265,12 @@ __global__ void __launch_bounds__(SCAN_CH, (NS <= 16 && !CONSTBC) ? SCAN_MIN_CTA
             if (2 * q + 1 < N) dst[2 * q + 1] = h2[q].y;
         }
     };
+    // recompute seeds for the backward pass: the state after every ckpt_every steps (and after the last one)
+    const int nck = p.ckpt ? (L + p.ckpt_every - 1) / p.ckpt_every : 0;
+    auto ckpt_after = [&](int lend) {      // lend = number of steps done, a multiple of SB or == L
+        if (p.ckpt && (lend % p.ckpt_every == 0 || lend == L))
+            store_state(p.ckpt + (((int64_t)b * E + e) * nck + (lend - 1) / p.ckpt_every) * N);
+    };
     // a step beyond the end of the sequence inside a partial block is the identity (delta' = 0 -> a = 1,
     // b = 0), selective_scan_fwd_kernel.cuh:218-222
     const float pad_delta = (softplus ? -1e30f : 0.f) - bias;
@@ -347,6 +353,7 @@ __global__ void __launch_bounds__(SCAN_CH, (NS <= 16 && !CONSTBC) ? SCAN_MIN_CTA
                             }
                         }
                         block(t0, uu, dd, zz, y);
+                        ckpt_after(min(l0 + t0 + SB, L));
 #pragma unroll
                         for (int i = 0; i < SB; ++i) O.e[sb * SB + i] = zg_from_float<T>(y[i]);
                     }
@@ -375,6 +382,7 @@ __global__ void __launch_bounds__(SCAN_CH, (NS <= 16 && !CONSTBC) ? SCAN_MIN_CTA
                             zz[i] = has_z ? zg_to_float<T>(sz[(t0 + i) * CH]) : 0.f;
                         }
                         block(t0, uu, dd, zz, y);
+                        ckpt_after(min(l0 + t0 + SB, L));
 #pragma unroll
                         for (int i = 0; i < SB; ++i) ocol[(int64_t)(t0 + i) * p.out_sl] = zg_from_float<T>(y[i]);
                     }
@@ -390,19 +398,11 @@ __global__ void __launch_bounds__(SCAN_CH, (NS <= 16 && !CONSTBC) ? SCAN_MIN_CTA
                             zz[i] = (ok && has_z) ? zg_to_float<T>(sz[(t0 + i) * CH]) : 0.f;
                         }
                         block(t0, uu, dd, zz, y);
+                        ckpt_after(min(l0 + t0 + SB, L));
 #pragma unroll
                         for (int i = 0; i < SB; ++i)
                             if (t0 + i < nsteps) ocol[(int64_t)(t0 + i) * p.out_sl] = zg_from_float<T>(y[i]);
                     }
-                }
-            }
-            // recompute seeds for the backward pass
-            if (p.ckpt) {
-                const int lend = l0 + nsteps;
-                if (lend % p.ckpt_every == 0 || lend == L) {
-                    const int k = (lend - 1) / p.ckpt_every;
-                    const int nck = (L + p.ckpt_every - 1) / p.ckpt_every;
-                    store_state(p.ckpt + (((int64_t)b * E + e) * nck + k) * N);
                 }
             }
         }

@@ -140,15 +140,14 @@ __global__ void __launch_bounds__(TPC2_THREADS, 9) scan_fwd_tpc2_kernel(const zg
             float y = (hf ? yp1 : yp0) + recv + Dv * (hf ? u1 : u0);
             if (has_z) y *= zg_silu(zg_to_float<T>(sz[tm * CH]));
             ocol[tm * (int)p.out_sl] = zg_from_float<T>(y);
-        }
-        if (p.ckpt) {
-            const int lend = (s + 1) * TL;
-            if (lend % p.ckpt_every == 0 || lend == L) {
-                const int k = (lend - 1) / p.ckpt_every;
-                const int nck = (L + p.ckpt_every - 1) / p.ckpt_every;
-                float *dst = p.ckpt + (((int64_t)b * E + e) * nck + k) * NS + 8 * hf;
+            if (p.ckpt) {                   // recompute seeds for the backward pass (uniform branch)
+                const int lend = s * TL + t0 + 2;
+                if (lend % p.ckpt_every == 0 || lend == L) {
+                    const int nck = (L + p.ckpt_every - 1) / p.ckpt_every;
+                    float *dst = p.ckpt + (((int64_t)b * E + e) * nck + (lend - 1) / p.ckpt_every) * NS + 8 * hf;
 #pragma unroll
-                for (int q = 0; q < 4; ++q) { dst[2 * q] = h2[q].x; dst[2 * q + 1] = h2[q].y; }
+                    for (int q = 0; q < 4; ++q) { dst[2 * q] = h2[q].x; dst[2 * q + 1] = h2[q].y; }
+                }
             }
         }
         __syncthreads();

@@ -15,7 +15,7 @@ import torch.nn.functional as F
 from . import _lib
 from .causal_conv1d_interface import _conv_fwd, _conv_bwd
 
-CKPT_EVERY = 16  # recompute-seed spacing: the backward kernel re-runs 16-step chunks from these states
+CKPT_EVERY = 8  # recompute-seed spacing: the backward kernel re-runs 8-step chunks from these states
 
 
 def _strides3(t):
@@ -135,16 +135,22 @@ def _scan_bwd(saved, ckpt, dout, delta_softplus, dz_out=None):
         raise NotImplementedError("zigma_b200: backward with constant (non input-dependent) B/C is not implemented")
     ngroups = B.shape[1]
 
-    def seqc(t):
-        return t if (t is None or t.stride(2) == 1) else t.contiguous()
-    u, delta, z, dout = seqc(u), seqc(delta), seqc(z), seqc(dout)
-    B = B if B.stride(3) == 1 else B.contiguous()
-    C = C if C.stride(3) == 1 else C.contiguous()
+    def dense(t):      # the dstate == 16 kernel takes any strides; keep channel-first or token-major as given
+        return t is None or t.stride(2) == 1 or t.stride(1) == 1
+    if dstate == 16 and all(dense(t) for t in (u, delta, z, dout)):
+        fmt = torch.preserve_format
+    else:              # generic kernel: a thread walks its own row, rows must be seq-contiguous
+        def seqc(t):
+            return t if (t is None or t.stride(2) == 1) else t.contiguous()
+        u, delta, z, dout = seqc(u), seqc(delta), seqc(z), seqc(dout)
+        B = B if B.stride(3) == 1 else B.contiguous()
+        C = C if C.stride(3) == 1 else C.contiguous()
+        fmt = torch.contiguous_format
     dev = u.device
-    du, ddelta = torch.empty_like(u, memory_format=torch.contiguous_format), torch.empty_like(delta, memory_format=torch.contiguous_format)
+    du, ddelta = torch.empty_like(u, memory_format=fmt), torch.empty_like(delta, memory_format=fmt)
     dz = None
     if z is not None:
-        dz = dz_out if dz_out is not None else torch.empty_like(z, memory_format=torch.contiguous_format)
+        dz = dz_out if dz_out is not None else torch.empty_like(z, memory_format=fmt)
     dA = torch.zeros((dim, dstate), dtype=torch.float32, device=dev)
     dD = torch.zeros((dim,), dtype=torch.float32, device=dev)
     dbias = torch.zeros((dim,), dtype=torch.float32, device=dev)
