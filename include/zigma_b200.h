@@ -62,7 +62,7 @@ uint64_t zg_launch_count(void);
  * z_rowmap (int32[seqlen], NULL = identity): step l reads z at sequence position z_rowmap[l]
  *   (fuses forward_permutation of the z half, mamba_simple.py:55-56,365-370; dim-contiguous only).
  * last_state (batch, dim, dstate) fp32 or NULL.
- * ckpt (batch, dim, n_ckpt, dstate) fp32 or NULL: state after every ckpt_every steps
+ * ckpt (batch, n_ckpt, dim, dstate) fp32 or NULL: state after every ckpt_every steps
  *   (n_ckpt = ceil(seqlen / ckpt_every); ckpt_every must be a multiple of 8; the backward needs 8) -- the recompute
  *   seeds of the backward pass; plays the role of the reference's `x` (selective_scan.cpp:313).
  * dstate <= 64.

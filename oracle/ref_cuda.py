@@ -56,3 +56,71 @@ def backend(norm_fn=None):
     if norm_fn is not None:
         be["norm"] = norm_fn
     return be
+
+
+# ---- training: the reference kernels' forward AND backward behind autograd -----------------------------
+class _RefScanFn(torch.autograd.Function):
+    """selective_scan_cuda.fwd / .bwd the way SelectiveScanFn drives them (selective_scan_interface.py:21-83)."""
+
+    @staticmethod
+    def forward(ctx, u, delta, A, B, C, D, z, delta_bias):
+        ss, _ = load()
+        if B.dim() == 3:
+            B, C = B.unsqueeze(1), C.unsqueeze(1)
+            ctx.squeeze = True
+        else:
+            ctx.squeeze = False
+        B, C = B.contiguous(), C.contiguous()
+        if u.stride(-1) != 1:
+            u = u.contiguous()
+        if delta.stride(-1) != 1:
+            delta = delta.contiguous()
+        if z is not None and z.stride(-1) != 1:
+            z = z.contiguous()
+        res = ss.fwd(u, delta, A, B, C, D, z, delta_bias, True)
+        out, x = res[0], res[1]
+        ctx.save_for_backward(u, delta, A, B, C, D, z, delta_bias, x, out)
+        return res[-1] if z is not None else out
+
+    @staticmethod
+    def backward(ctx, dout):
+        ss, _ = load()
+        u, delta, A, B, C, D, z, delta_bias, x, out = ctx.saved_tensors
+        if dout.stride(-1) != 1:
+            dout = dout.contiguous()
+        r = ss.bwd(u, delta, A, B, C, D, z, delta_bias, dout, x, out, None, True, False)
+        du, ddelta, dA, dB, dC, dD, dbias = r[:7]
+        dz = r[7] if z is not None else None
+        if ctx.squeeze:
+            dB, dC = dB.squeeze(1), dC.squeeze(1)
+        return du, ddelta, dA, dB.to(B.dtype), dC.to(C.dtype), dD, dz, dbias
+
+
+class _RefConvFn(torch.autograd.Function):
+    """causal_conv1d_fwd / _bwd (causal_conv1d_interface.py:11-47)."""
+
+    @staticmethod
+    def forward(ctx, x, w, b):
+        _, cc = load()
+        if x.stride(2) != 1 and x.stride(1) != 1:
+            x = x.contiguous()
+        ctx.save_for_backward(x, w, b)
+        return cc.causal_conv1d_fwd(x, w, b, True)
+
+    @staticmethod
+    def backward(ctx, dout):
+        _, cc = load()
+        x, w, b = ctx.saved_tensors
+        if dout.stride(2) != 1 and dout.stride(1) != 1:
+            dout = dout.contiguous()
+        dx, dw, db = cc.causal_conv1d_bwd(x, w, b, dout, None, True)
+        return dx, dw, db
+
+
+def train_backend(norm_fn=None):
+    """BACKEND for zigma_oracle under autograd: reference CUDA forward + backward kernels."""
+    be = {"conv": lambda x, w, b: _RefConvFn.apply(x, w.contiguous(), b),
+          "scan": lambda u, d, A, B, C, D, z, bias: _RefScanFn.apply(u, d, A, B, C, D, z, bias)}
+    if norm_fn is not None:
+        be["norm"] = norm_fn
+    return be

@@ -256,6 +256,43 @@ def test_causal_conv1d_backward_golden():
             check_close(b.grad, g["db_" + tag], "conv dbias " + tag, rtol=1e-3, atol=1e-4)
 
 
+def test_causal_conv1d_backward_token_major_and_rowmap():
+    """Token-major backward kernel: (a) same golden gradients as the channel-first kernel when the tensors are
+    handed over channel-last; (b) with x_rowmap it equals gather -> conv backward -> scatter, odd sizes
+    (dim not a multiple of 4, seqlen not a multiple of the 64-position chunk) included."""
+    from zigma_b200 import causal_conv1d_fn
+    from zigma_b200.causal_conv1d_interface import _conv_bwd
+    g = gold("conv")
+    tm = lambda a: a.transpose(1, 2).contiguous().transpose(1, 2)
+    for tag in ("W4_s1_b1", "W3_s0_b0", "W2_s1_b0"):
+        W, silu, hb = int(tag[1]), int(tag[4]), int(tag[7])
+        x = tm(t(g["x"], DEV)).requires_grad_()
+        w = t(g[f"w{W}"], DEV).requires_grad_()
+        b = t(g[f"b{W}"], DEV).requires_grad_() if hb else None
+        out = causal_conv1d_fn(x, w, b, "silu" if silu else None)
+        out.backward(tm(t(g["g"], DEV)))
+        check_close(x.grad, g["dx_" + tag], "conv dx (token-major) " + tag)
+        check_close(w.grad, g["dw_" + tag], "conv dweight (token-major) " + tag, rtol=1e-3, atol=1e-4)
+        if hb:
+            check_close(b.grad, g["db_" + tag], "conv dbias (token-major) " + tag, rtol=1e-3, atol=1e-4)
+    gen = torch.Generator(device=DEV).manual_seed(4)
+    for (bs, E, L, dt) in ((2, 64, 200, torch.float32), (3, 30, 77, torch.float32), (2, 128, 256, torch.bfloat16)):
+        x = tm(torch.randn(bs, E, L, device=DEV, generator=gen).to(dt))
+        do = tm(torch.randn(bs, E, L, device=DEV, generator=gen).to(dt))
+        w = torch.randn(E, 4, device=DEV, generator=gen).to(dt)
+        b = torch.randn(E, device=DEV, generator=gen).to(dt)
+        perm = torch.randperm(L, device=DEV, generator=gen)
+        dx, dw, db = _conv_bwd(x, w, b, do, True, x_rowmap=perm.to(torch.int32))
+        xg = x.float()[:, :, perm].contiguous()
+        dxr, dwr, dbr = _conv_bwd(xg, w.float(), b.float(), do.float().contiguous(), True)
+        want_dx = torch.empty_like(dxr)
+        want_dx[:, :, perm] = dxr
+        lo = dt == torch.bfloat16
+        check_close(dx, want_dx, f"conv dx rowmap {bs}x{E}x{L}", **(dict(rtol=2e-2, atol=2e-2, max_strict_viol=1.0) if lo else {}))
+        check_close(dw, dwr, f"conv dweight rowmap {bs}x{E}x{L}", rtol=1e-3, atol=1e-4, max_strict_viol=1.0 if lo else 1e-4)
+        check_close(db, dbr, f"conv dbias rowmap {bs}x{E}x{L}", rtol=1e-3, atol=1e-4, max_strict_viol=1.0 if lo else 1e-4)
+
+
 # ------------------------------------------------------------------------------------------------
 def test_add_norm_golden():
     from zigma_b200 import rms_norm_fn, layer_norm_fn

@@ -92,3 +92,27 @@ def test_shard_sampling_world2_gloo():
                        env=env, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "DIST_OK" in r.stdout
+
+
+def test_permute_along_matches_advanced_indexing_fwd_and_bwd():
+    """The permutation gather with its inverse-gather backward (mamba_simple._PermuteFn) vs the
+    reference's ``x[:, :, perm]`` under autograd; a non-bijective index falls back to plain indexing."""
+    from zigma_b200.mamba_simple import permute_along, _inverse_of
+    g = torch.Generator().manual_seed(0)
+    perm = torch.randperm(37, generator=g)
+    for dim, shape in ((2, (3, 5, 37)), (1, (2, 37, 4))):
+        x = torch.randn(*shape, generator=g, requires_grad=True)
+        xr = x.detach().clone().requires_grad_()
+        w = torch.randn(*shape, generator=g)
+        y = permute_along(x, perm, dim)
+        yr = xr[:, :, perm] if dim == 2 else xr[:, perm, :]
+        assert torch.equal(y, yr) and y.is_contiguous()
+        (y * w).sum().backward(); (yr * w).sum().backward()
+        assert torch.equal(x.grad, xr.grad)
+    assert torch.equal(_inverse_of(perm)[perm], torch.arange(37))
+    dup = torch.tensor([0, 0, 2, 1])
+    assert _inverse_of(dup) is None
+    x = torch.randn(2, 3, 4, requires_grad=True)
+    xr = x.detach().clone().requires_grad_()
+    permute_along(x, dup, 2).sum().backward(); xr[:, :, dup].sum().backward()
+    assert torch.equal(x.grad, xr.grad)

@@ -44,35 +44,48 @@ def _conv_fwd(x, weight, bias, silu, x_rowmap=None, out=None):
     return out
 
 
-def _conv_bwd(x, weight, bias, dout, silu, dx_out=None):
+def _conv_bwd(x, weight, bias, dout, silu, dx_out=None, x_rowmap=None):
     """causal_conv1d_cuda.causal_conv1d_bwd (causal_conv1d.cpp:191-268): returns dx, dweight (fp32),
-    dbias (fp32 or None).  Channel-first tensors; a provided dx_out is written in place (the
-    reference uses that to fill one half of dxz, selective_scan_interface.py:425-427)."""
+    dbias (fp32 or None).  Channel-first tensors (stride(2) == 1; a provided dx_out is written in
+    place -- the reference uses that to fill one half of dxz, selective_scan_interface.py:425-427) or
+    token-major ones (stride(1) == 1, all three of x / dout / dx), where ``x_rowmap`` (int32, seqlen)
+    says the conv ran over the gathered sequence x[:, :, x_rowmap]: x is read and dx written through it."""
     batch, dim, seqlen = x.shape
-    if x.stride(2) != 1:
-        x = x.contiguous()
-    if dout.stride(2) != 1:
-        dout = dout.contiguous()
+    tok = x.stride(1) == 1 and not (x.stride(2) == 1 and dim > 1) and seqlen > 1
+    if tok:
+        if dout.stride(1) != 1:
+            dout = dout.transpose(1, 2).contiguous().transpose(1, 2)
+        dx = dx_out if dx_out is not None else torch.empty((batch, seqlen, dim), dtype=x.dtype, device=x.device).transpose(1, 2)
+        if dx.stride(1) != 1:
+            raise RuntimeError("causal_conv1d_bwd: dx must be token-major like x")
+    else:
+        if x_rowmap is not None:
+            raise RuntimeError("causal_conv1d_bwd: x_rowmap needs token-major (dim-contiguous) tensors")
+        if x.stride(2) != 1:
+            x = x.contiguous()
+        if dout.stride(2) != 1:
+            dout = dout.contiguous()
+        dx = dx_out if dx_out is not None else torch.empty_like(x, memory_format=torch.contiguous_format)
+        if dx.stride(2) != 1:
+            raise RuntimeError("causal_conv1d_bwd: dx must have seq stride 1")
     weight = weight.contiguous()
-    dx = dx_out if dx_out is not None else torch.empty_like(x, memory_format=torch.contiguous_format)
-    if dx.stride(2) != 1:
-        raise RuntimeError("causal_conv1d_bwd: dx must have seq stride 1")
     dweight = torch.zeros(weight.shape, dtype=torch.float32, device=x.device)
     dbias = torch.zeros((dim,), dtype=torch.float32, device=x.device) if bias is not None else None
     q = _lib.ConvBwdParams()
     p = q.fwd
     p.x, p.weight, p.bias = _lib.ptr(x), _lib.ptr(weight), _lib.ptr(bias)
+    p.x_rowmap = _lib.ptr(x_rowmap)
     p.x_sb, p.x_sd, p.x_sl = x.stride()
-    p.out_sl = 1
     p.batch, p.dim, p.seqlen, p.width = batch, dim, seqlen, weight.shape[1]
     p.dtype, p.wdtype, p.silu = _lib.dt(x), _lib.dt(weight), int(bool(silu))
-    if seqlen == 1:
-        p.x_sl = 1
     q.dout, q.dx, q.dweight, q.dbias = _lib.ptr(dout), _lib.ptr(dx), _lib.ptr(dweight), _lib.ptr(dbias)
-    q.dout_sb, q.dout_sd, q.dout_sl = dout.stride(0), dout.stride(1), 1
-    q.dx_sb, q.dx_sd, q.dx_sl = dx.stride(0), dx.stride(1), 1
-    # the kernel needs a non-null `out` only for validation symmetry
+    q.dout_sb, q.dout_sd, q.dout_sl = dout.stride()
+    q.dx_sb, q.dx_sd, q.dx_sl = dx.stride()
+    if not tok:
+        p.x_sl = q.dout_sl = q.dx_sl = 1           # (seqlen == 1: any stride is "contiguous")
+    # `out` only takes part in the shared validation (layout class of the call)
     p.out = _lib.ptr(dx)
+    p.out_sb, p.out_sd, p.out_sl = q.dx_sb, q.dx_sd, q.dx_sl
     _lib.call("zg_causal_conv1d_bwd", q)
     return dx, dweight, dbias
 

@@ -300,6 +300,120 @@ __global__ void __launch_bounds__(128) conv_bwd_seqc_kernel(const zg_conv_bwd_pa
     }
 }
 
+
+// backward, dim-contiguous (token-major): a thread owns DV adjacent channels and CONV_BLCH consecutive
+// positions and streams upwards in l with two sliding windows (x[l-3..l] for the pre-activation,
+// g[l-3..l] for dx[l-3] = sum_k w[k] g[l-3+k]); the three positions after the chunk are walked as a
+// halo (their g feeds the chunk's last dx, their dw/db belong to the next chunk).  x_rowmap[l]
+// redirects both the x reads and the dx writes (the conv ran over the permuted sequence; dx goes
+// back to token order).  dweight/dbias: summed over the 4 warps of the CTA (4 chunks of the same
+// channels) in shared memory, then one atomic per (CTA, channel, tap).
+constexpr int CONV_BLCH = 64;
+
+template <typename T, int DV>
+__global__ void __launch_bounds__(128) conv_bwd_tok_kernel(const zg_conv_bwd_params q) {
+    const zg_conv_params &p = q.fwd;
+    const int E = p.dim, L = p.seqlen, W = p.width;
+    const int nvec = E / DV;
+    const int nvb = (nvec + 31) >> 5;
+    const int nchunk = (L + CONV_BLCH - 1) / CONV_BLCH;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int v = (int)(blockIdx.x % nvb) * 32 + lane;
+    const int64_t row = (int64_t)(blockIdx.x / nvb) * 4 + warp;          // enumerates (batch, chunk)
+    const bool live = v < nvec && row < (int64_t)p.batch * nchunk;
+    __shared__ float red[4][5 * DV][32];
+
+    float dw[4][DV], db[DV];
+#pragma unroll
+    for (int i = 0; i < DV; ++i) {
+        db[i] = 0.f;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) dw[k][i] = 0.f;
+    }
+    const int e0 = v * DV;
+    if (live) {
+        const int b = (int)(row / nchunk), l0 = (int)(row % nchunk) * CONV_BLCH;
+        const T *x = reinterpret_cast<const T *>(p.x) + (int64_t)b * p.x_sb + e0;
+        const T *dout = reinterpret_cast<const T *>(q.dout) + (int64_t)b * q.dout_sb + e0;
+        T *dx = reinterpret_cast<T *>(q.dx) + (int64_t)b * q.dx_sb + e0;
+        float w[4][DV], bias[DV];
+#pragma unroll
+        for (int i = 0; i < DV; ++i) {
+            bias[i] = p.bias ? load_w_dt(p.bias, e0 + i, p.wdtype) : 0.f;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) w[k][i] = (k < W) ? load_w_dt(p.weight, (int64_t)(e0 + i) * W + (W - 1 - k), p.wdtype) : 0.f;
+        }
+        auto rowof = [&](int l) -> int64_t { return p.x_rowmap ? p.x_rowmap[l] : l; };
+        float x1[DV], x2[DV], x3[DV], g1[DV], g2[DV], g3[DV];
+#pragma unroll
+        for (int i = 0; i < DV; ++i) { x1[i] = x2[i] = x3[i] = 0.f; g1[i] = g2[i] = g3[i] = 0.f; }
+        // x window before the chunk; g window: positions l0-1.. are only needed for dx of the PREVIOUS chunk
+        if (l0 >= 1) load_vec<T, DV>(x1, x + rowof(l0 - 1) * p.x_sl);
+        if (l0 >= 2) load_vec<T, DV>(x2, x + rowof(l0 - 2) * p.x_sl);
+        if (l0 >= 3) load_vec<T, DV>(x3, x + rowof(l0 - 3) * p.x_sl);
+        const int lend = min(l0 + CONV_BLCH, L);
+        const int lhalo = min(lend + 3, L);
+#pragma unroll 2
+        for (int l = l0; l < lend + 3; ++l) {
+            float g0[DV], x0[DV];
+            if (l < lhalo) {
+                float go[DV];
+                load_vec<T, DV>(x0, x + rowof(l) * p.x_sl);
+                load_vec<T, DV>(go, dout + (int64_t)l * q.dout_sl);
+#pragma unroll
+                for (int i = 0; i < DV; ++i) {
+                    float gg = go[i];
+                    if (p.silu) {
+                        const float pre = fmaf(w[0][i], x0[i], fmaf(w[1][i], x1[i], fmaf(w[2][i], x2[i], fmaf(w[3][i], x3[i], bias[i]))));
+                        const float sg = zg_sigmoid(pre);
+                        gg *= sg * fmaf(pre, 1.f - sg, 1.f);
+                    }
+                    g0[i] = gg;
+                }
+                if (l < lend) {
+#pragma unroll
+                    for (int i = 0; i < DV; ++i) {
+                        db[i] += g0[i];
+                        dw[0][i] = fmaf(g0[i], x0[i], dw[0][i]);
+                        dw[1][i] = fmaf(g0[i], x1[i], dw[1][i]);
+                        dw[2][i] = fmaf(g0[i], x2[i], dw[2][i]);
+                        dw[3][i] = fmaf(g0[i], x3[i], dw[3][i]);
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < DV; ++i) { g0[i] = 0.f; x0[i] = 0.f; }
+            }
+            const int m = l - 3;                          // dx[m] = w0 g[m] + w1 g[m+1] + w2 g[m+2] + w3 g[m+3]
+            if (m >= l0) {                                //   (m < lend always holds inside the loop)
+                float o[DV];
+#pragma unroll
+                for (int i = 0; i < DV; ++i) o[i] = fmaf(w[0][i], g3[i], fmaf(w[1][i], g2[i], fmaf(w[2][i], g1[i], w[3][i] * g0[i])));
+                store_vec<T, DV>(dx + rowof(m) * q.dx_sl, o);
+            }
+#pragma unroll
+            for (int i = 0; i < DV; ++i) { x3[i] = x2[i]; x2[i] = x1[i]; x1[i] = x0[i]; g3[i] = g2[i]; g2[i] = g1[i]; g1[i] = g0[i]; }
+        }
+    }
+    // CTA reduction of the weight / bias gradients over the 4 warps
+#pragma unroll
+    for (int i = 0; i < DV; ++i) {
+        red[warp][4 * DV + i][lane] = db[i];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) red[warp][k * DV + i][lane] = dw[k][i];
+    }
+    __syncthreads();
+    for (int it = threadIdx.x; it < 5 * DV * 32; it += 128) {
+        const int j = it >> 5, ln = it & 31;
+        const int vv = (int)(blockIdx.x % nvb) * 32 + ln;
+        if (vv >= nvec) continue;
+        const float sum = red[0][j][ln] + red[1][j][ln] + red[2][j][ln] + red[3][j][ln];
+        const int k = j / DV, i = j % DV, e = vv * DV + i;
+        if (k == 4) { if (q.dbias) atomicAdd(q.dbias + e, sum); }
+        else if (k < W) atomicAdd(q.dweight + (int64_t)e * W + (W - 1 - k), sum);
+    }
+}
+
 template <typename T> static int conv_fwd_t(const zg_conv_params &p, bool seq, cudaStream_t s) {
     constexpr int VEC = 16 / sizeof(T);
     const uintptr_t align_bits = reinterpret_cast<uintptr_t>(p.x) | reinterpret_cast<uintptr_t>(p.out);
@@ -392,11 +506,37 @@ extern "C" int zg_causal_conv1d_bwd(const zg_conv_bwd_params *qq, void *stream) 
     ZG_REQUIRE(qq != nullptr, "causal_conv1d_bwd: null params");
     const zg_conv_bwd_params &q = *qq;
     if (int rc = conv_validate(q.fwd, "causal_conv1d_bwd")) return rc;
-    ZG_REQUIRE(q.fwd.x_sl == 1 && q.dout_sl == 1 && q.dx_sl == 1, "causal_conv1d_bwd: seq-contiguous tensors required");
     ZG_REQUIRE(q.dout && q.dx && q.dweight, "causal_conv1d_bwd: null tensor pointer");
-    ZG_REQUIRE(q.fwd.x_rowmap == nullptr, "causal_conv1d_bwd: x_rowmap not supported");
     if (q.fwd.batch == 0 || q.fwd.seqlen == 0) return 0;
     cudaStream_t s = (cudaStream_t)stream;
+    const zg_conv_params &p = q.fwd;
+    if (p.x_sd == 1 && q.dout_sd == 1 && q.dx_sd == 1 && !(p.x_sl == 1 && p.dim > 1)) {
+        // token-major: DV channels per thread when everything is DV-aligned
+        const int esz = zg_dtype_size(p.dtype);
+        const uintptr_t al = reinterpret_cast<uintptr_t>(p.x) | reinterpret_cast<uintptr_t>(q.dout) | reinterpret_cast<uintptr_t>(q.dx);
+        const int64_t so = p.x_sb | p.x_sl | q.dout_sb | q.dout_sl | q.dx_sb | q.dx_sl;
+        const bool vec = (p.dim % 4 == 0) && (al % (4 * esz) == 0) && (so % 4 == 0);
+        const int dv = vec ? 4 : 1;
+        const int nvb = (p.dim / dv + 31) / 32;
+        const int nchunk = (p.seqlen + zg::CONV_BLCH - 1) / zg::CONV_BLCH;
+        const int64_t grid = (int64_t)nvb * (((int64_t)p.batch * nchunk + 3) / 4);
+        ZG_REQUIRE(grid <= 0x7fffffffLL, "causal_conv1d_bwd: grid too large");
+#define ZG_CONV_BWD_TOK(TT)                                                                   \
+        do {                                                                                  \
+            if (vec) zg::conv_bwd_tok_kernel<TT, 4><<<(unsigned)grid, 128, 0, s>>>(q);       \
+            else zg::conv_bwd_tok_kernel<TT, 1><<<(unsigned)grid, 128, 0, s>>>(q);           \
+        } while (0)
+        switch (p.dtype) {
+            case ZG_F32: ZG_CONV_BWD_TOK(float); break;
+            case ZG_F16: ZG_CONV_BWD_TOK(__half); break;
+            default: ZG_CONV_BWD_TOK(__nv_bfloat16); break;
+        }
+#undef ZG_CONV_BWD_TOK
+        zg_count_launch();
+        return zg_check_launch("causal_conv1d_bwd(token-major)");
+    }
+    ZG_REQUIRE(q.fwd.x_sl == 1 && q.dout_sl == 1 && q.dx_sl == 1, "causal_conv1d_bwd: tensors must be all seq-contiguous or all dim-contiguous");
+    ZG_REQUIRE(q.fwd.x_rowmap == nullptr, "causal_conv1d_bwd: x_rowmap needs the dim-contiguous layout");
     const int64_t nthreads = (int64_t)q.fwd.batch * q.fwd.dim * 32;
     const unsigned grid = (unsigned)((nthreads + 127) / 128);
     switch (q.fwd.dtype) {

@@ -57,7 +57,7 @@ __global__ void __launch_bounds__(BWD_CH) scan_bwd_kernel(const zg_scan_bwd_para
     float *gdB = q.dB + ((int64_t)b * p.ngroups + g) * (int64_t)N * L;     // (batch, groups, dstate, seqlen) contiguous
     float *gdC = q.dC + ((int64_t)b * p.ngroups + g) * (int64_t)N * L;
     const int nck = (L + TS - 1) / TS;
-    const float *ck = p.ckpt + ((int64_t)b * E + e) * (int64_t)nck * N;
+    const float *ck = p.ckpt + ((int64_t)b * nck * E + e) * (int64_t)N;     // (batch, n_ckpt, dim, dstate)
 
     float A[NS], dA[NS], dh[NS], a_next[NS];
 #pragma unroll
@@ -86,7 +86,7 @@ __global__ void __launch_bounds__(BWD_CH) scan_bwd_kernel(const zg_scan_bwd_para
         float dl[TS], uu[TS];
         float h[NS];
 #pragma unroll
-        for (int n = 0; n < NS; ++n) h[n] = (k > 0 && n < N) ? ck[(int64_t)(k - 1) * N + n] : 0.f;
+        for (int n = 0; n < NS; ++n) h[n] = (k > 0 && n < N) ? ck[(int64_t)(k - 1) * E * N + n] : 0.f;
 #pragma unroll
         for (int t = 0; t < TS; ++t) {
             if (t < nsteps) {
@@ -212,6 +212,7 @@ template <typename T> static int scan_bwd_t(const zg_scan_bwd_params &q, cudaStr
     if (rc >= 0) return rc;
     {   // generic kernel: one thread per channel walking its own row
         const zg_scan_params &p = q.fwd;
+        ZG_REQUIRE(p.z_rowmap == nullptr, "selective_scan_bwd: z_rowmap needs the dstate == 16 kernel");
     ZG_REQUIRE(p.u_sl == 1 && p.delta_sl == 1 && q.dout_sl == 1 && q.du_sl == 1 && q.ddelta_sl == 1 && (!p.z || (p.z_sl == 1 && q.dz && q.dz_sl == 1)) &&
                    (p.B_sl == 1 || p.seqlen == 1) && (p.C_sl == 1 || p.seqlen == 1),
                "selective_scan_bwd: the generic kernel (dstate != 16) needs seq-contiguous tensors");

@@ -14,7 +14,8 @@
 //   * dB / dC (sums over the channels that share a group): 7-shuffle transpose-reduce over the 8
 //     channels of a warp, cross-warp sum through shared memory, then one fp32 atomic per
 //     (CTA, state, step) with 8 consecutive steps per 32-byte sector;
-//   * packed FFMA2 math on state pairs, as in the forward.
+//   * packed FFMA2 math on state pairs, as in the forward;
+//   * z_rowmap (the forward's fused permutation of the gate) redirects the z reads and the dz writes.
 #pragma once
 #include "zg_common.cuh"
 
@@ -90,7 +91,7 @@ __global__ void __launch_bounds__(Q4_THREADS, 4) scan_bwd_q4_kernel(const zg_sca
     float *gdB = q.dB + ((int64_t)b * p.ngroups + g) * (int64_t)16 * L;      // (batch, groups, dstate, seqlen)
     float *gdC = q.dC + ((int64_t)b * p.ngroups + g) * (int64_t)16 * L;
     const int nck = (L + TS - 1) / TS;
-    const float4 *ck = reinterpret_cast<const float4 *>(p.ckpt + ((int64_t)b * E + e) * (int64_t)nck * 16) + qd;
+    const float4 *ck = reinterpret_cast<const float4 *>(p.ckpt + ((int64_t)b * nck * E + e) * (int64_t)16) + qd;   // (batch, n_ckpt, dim, 16)
     // B / C staging: 2 x 8 steps x 16 states = 256 items, one per thread
     const int bw = tid >> 7, brem = tid & 127;
     const bool bc_tok = (bw ? p.C_sn : p.B_sn) == 1;
@@ -124,7 +125,8 @@ __global__ void __launch_bounds__(Q4_THREADS, 4) scan_bwd_q4_kernel(const zg_sca
                 s.y = zg_to_float<T>(gu[(int64_t)ic[j] * p.u_sd + (int64_t)l * p.u_sl]);
                 s.z = dout;
                 if (has_z) {
-                    const float zz = zg_to_float<T>(gz[(int64_t)ic[j] * p.z_sd + (int64_t)l * p.z_sl]);
+                    const int64_t lz = p.z_rowmap ? p.z_rowmap[l] : l;       // z is read (and dz written) in token order
+                    const float zz = zg_to_float<T>(gz[(int64_t)ic[j] * p.z_sd + lz * p.z_sl]);
                     const float sg = zg_sigmoid(zz);
                     s.z = dout * zz * sg;
                     s.w = dout * sg * (1.f + zz * (1.f - sg));
@@ -141,7 +143,7 @@ __global__ void __launch_bounds__(Q4_THREADS, 4) scan_bwd_q4_kernel(const zg_sca
         // ---- forward recompute from the checkpoint before the chunk, parking h_{l-1} -----------------------
         zg_f2 h[2];
         if (k > 0) {
-            const float4 h4 = ck[(int64_t)(k - 1) * 4];
+            const float4 h4 = ck[(int64_t)(k - 1) * E * 4];
             h[0] = make_float2(h4.x, h4.y); h[1] = make_float2(h4.z, h4.w);
         } else {
             h[0] = h[1] = zg_splat2(0.f);
@@ -226,7 +228,10 @@ __global__ void __launch_bounds__(Q4_THREADS, 4) scan_bwd_q4_kernel(const zg_sca
                 const int o = it[j] * CH + ic[j];
                 gdu[(int64_t)ic[j] * q.du_sd + (int64_t)l * q.du_sl] = zg_from_float<T>(outt[o]);
                 gdd[(int64_t)ic[j] * q.ddelta_sd + (int64_t)l * q.ddelta_sl] = zg_from_float<T>(outt[TS * CH + o]);
-                if (has_z) gdz[(int64_t)ic[j] * q.dz_sd + (int64_t)l * q.dz_sl] = zg_from_float<T>(outt[2 * TS * CH + o]);
+                if (has_z) {
+                    const int64_t lz = p.z_rowmap ? p.z_rowmap[l] : l;
+                    gdz[(int64_t)ic[j] * q.dz_sd + lz * q.dz_sl] = zg_from_float<T>(outt[2 * TS * CH + o]);
+                }
             }
         }
         {

@@ -269,7 +269,7 @@ __global__ void __launch_bounds__(SCAN_CH, (NS <= 16 && !CONSTBC) ? SCAN_MIN_CTA
     const int nck = p.ckpt ? (L + p.ckpt_every - 1) / p.ckpt_every : 0;
     auto ckpt_after = [&](int lend) {      // lend = number of steps done, a multiple of SB or == L
         if (p.ckpt && (lend % p.ckpt_every == 0 || lend == L))
-            store_state(p.ckpt + (((int64_t)b * E + e) * nck + (lend - 1) / p.ckpt_every) * N);
+            store_state(p.ckpt + (((int64_t)b * nck + (lend - 1) / p.ckpt_every) * E + e) * N);   // (batch, n_ckpt, dim, dstate)
     };
     // a step beyond the end of the sequence inside a partial block is the identity (delta' = 0 -> a = 1,
     // b = 0), selective_scan_fwd_kernel.cuh:218-222

@@ -144,9 +144,10 @@ __global__ void __launch_bounds__(TPC2_THREADS, 9) scan_fwd_tpc2_kernel(const zg
                 const int lend = s * TL + t0 + 2;
                 if (lend % p.ckpt_every == 0 || lend == L) {
                     const int nck = (L + p.ckpt_every - 1) / p.ckpt_every;
-                    float *dst = p.ckpt + (((int64_t)b * E + e) * nck + (lend - 1) / p.ckpt_every) * NS + 8 * hf;
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) { dst[2 * q] = h2[q].x; dst[2 * q + 1] = h2[q].y; }
+                    // (batch, n_ckpt, dim, dstate): the 16 channels x 2 halves of a warp write 1 KB contiguous
+                    float4 *dst = reinterpret_cast<float4 *>(p.ckpt + (((int64_t)b * nck + (lend - 1) / p.ckpt_every) * E + e) * NS + 8 * hf);
+                    dst[0] = make_float4(h2[0].x, h2[0].y, h2[1].x, h2[1].y);
+                    dst[1] = make_float4(h2[2].x, h2[2].y, h2[3].x, h2[3].y);
                 }
             }
         }
@@ -171,7 +172,7 @@ template <typename T> int try_launch_scan_fwd_tpc2(const zg_scan_params &p, cuda
     const uintptr_t al = reinterpret_cast<uintptr_t>(p.u) | reinterpret_cast<uintptr_t>(p.delta) | reinterpret_cast<uintptr_t>(p.z) |
                          reinterpret_cast<uintptr_t>(p.B) | reinterpret_cast<uintptr_t>(p.C);
     const int64_t so = p.u_sb | p.delta_sb | (p.z ? p.z_sb : 0) | p.B_sb | p.B_sg | p.C_sb | p.C_sg | p.u_sl | p.delta_sl | (p.z ? p.z_sl : 0) | p.B_sl | p.C_sl;
-    if (al % 16 != 0 || so % 8 != 0) return -1;
+    if (al % 16 != 0 || so % 8 != 0 || reinterpret_cast<uintptr_t>(p.ckpt) % 16 != 0) return -1;
     // 32-bit in-batch offsets inside the kernel
     const int64_t lim = 0x7fffffffLL;
     if ((int64_t)p.seqlen * p.u_sl > lim || (int64_t)p.seqlen * p.delta_sl > lim || (p.z && (int64_t)p.seqlen * p.z_sl > lim) ||

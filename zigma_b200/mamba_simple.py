@@ -16,15 +16,62 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from .selective_scan_interface import mamba_inner_fn, mamba_inner_fn_no_out_proj, selective_scan_fn
+import os
+
+from .selective_scan_interface import mamba_inner_fn, mamba_inner_fn_no_out_proj, mamba_inner_tok_fn, selective_scan_fn
+
+
+_INV_CACHE = {}
+
+
+def _inverse_of(perm):
+    """Inverse permutation, or None when ``perm`` is not a bijection of range(len) (cached per tensor)."""
+    key = (perm.data_ptr(), perm.numel(), str(perm.device))
+    hit = _INV_CACHE.get(key)
+    if hit is None or hit[0] is not perm:
+        n = perm.numel()
+        ok = bool(n) and bool(((perm >= 0) & (perm < n)).all()) and int(torch.unique(perm).numel()) == n
+        inv = None
+        if ok:
+            inv = torch.empty_like(perm)
+            inv[perm] = torch.arange(n, device=perm.device, dtype=perm.dtype)
+        if len(_INV_CACHE) > 256:
+            _INV_CACHE.clear()
+        hit = _INV_CACHE[key] = (perm, inv)
+    return hit[1]
+
+
+class _PermuteFn(torch.autograd.Function):
+    """y = x.index_select(dim, perm) for a PERMUTATION perm: the backward is the gather by the inverse
+    permutation.  The reference writes ``x[:, :, perm]`` (mamba_simple.py:56,61), whose autograd
+    backward is a sort-based index_put with accumulation -- 8 ms per layer at the config-2 shape,
+    46 % of a training step on B200 -- although no index repeats."""
+
+    @staticmethod
+    def forward(ctx, x, perm, inv, dim):
+        ctx.inv, ctx.dim = inv, dim
+        return x.index_select(dim, perm)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g.index_select(ctx.dim, ctx.inv), None, None, None
+
+
+def permute_along(x, perm, dim):
+    """x gathered along ``dim`` by ``perm`` (contiguous result), with the cheap permutation backward when
+    perm is a bijection and plain advanced indexing otherwise."""
+    inv = _inverse_of(perm) if (x.requires_grad and torch.is_grad_enabled()) else None
+    if inv is not None:
+        return _PermuteFn.apply(x, perm, inv, dim)
+    return x.index_select(dim, perm)
 
 
 def forward_permutation(xz_main, _perm):
-    return xz_main[:, :, _perm].contiguous()  # [B, C, T]
+    return permute_along(xz_main, _perm, 2)  # [B, C, T]
 
 
 def backward_permutation(o_main, _perm_rev):
-    return o_main[:, _perm_rev, :].contiguous()  # [B, T, C]
+    return permute_along(o_main, _perm_rev, 1)  # [B, T, C]
 
 
 def _is_video(scan_type):
@@ -116,9 +163,44 @@ class Mamba(nn.Module):
                     delta_proj_weight=dp.weight, A=-torch.exp(A_log.float()), D=D.float(),
                     delta_bias=dp.bias.float())
 
+    # ---- token-major path (training and eager inference): no transposes, permutation fused into the kernels ----
+    def _tok_eligible(self, hidden_states):
+        st = self.scan_type
+        return (self.use_fast_path and hidden_states.is_cuda and self.d_state == 16 and not (self.extras or 0)
+                and (st == "v1" or (not _is_video(st) and st != "v2"))
+                and os.environ.get("ZIGMA_TOKEN_MAJOR_TRAIN", "1") != "0")
+
+    def _rowmap32(self, perm):
+        cache = self.__dict__.setdefault("_rowmap_cache", {})
+        key = (perm.data_ptr(), str(perm.device))
+        hit = cache.get(key)
+        if hit is None or hit[0] is not perm:
+            hit = cache[key] = (perm, perm.to(torch.int32).contiguous())
+        return hit[1]
+
+    def _tok_forward(self, hidden_states):
+        """Same function as the channel-first branch below for v1 / zigzagN / hilbertN / randomN:
+        in_proj -> [gather by perm] -> conv -> x_proj / dt_proj -> scan * silu(z) -> out_proj -> [gather by
+        perm_rev], with the two gathers folded into the conv / scan kernels (forward and backward)."""
+        batch, seqlen, dm = hidden_states.shape
+        a = self._inner_args()
+        xz = F.linear(hidden_states.reshape(batch * seqlen, dm), self.in_proj.weight, self.in_proj.bias)
+        perm = perm_rev = None
+        if self.scan_type != "v1":
+            perm = self.zigzag_paths[self.layer_idx]
+            perm_rev = self.zigzag_paths_reverse[self.layer_idx]
+            if perm.device != xz.device:
+                perm, perm_rev = perm.to(xz.device), perm_rev.to(xz.device)
+        y = mamba_inner_tok_fn(xz, a["conv1d_weight"], a["conv1d_bias"], a["x_proj_weight"], a["delta_proj_weight"],
+                               a["A"], a["D"], a["delta_bias"], None if perm is None else self._rowmap32(perm), batch, seqlen)
+        out = F.linear(y, self.out_proj.weight, self.out_proj.bias).view(batch, seqlen, -1)
+        return out if perm_rev is None else permute_along(out, perm_rev, 1)
+
     def _mamba_inner_forward(self, hidden_states):
         """hidden_states (B, L, D) -> (B, L, D).  mamba_simple.py:274-444."""
         batch, seqlen, _ = hidden_states.shape
+        if self._tok_eligible(hidden_states):
+            return self._tok_forward(hidden_states)
         # matmul and BLD -> B(2E)L transpose in one go (:290-296)
         xz = (self.in_proj.weight @ hidden_states.reshape(batch * seqlen, -1).t()).reshape(-1, batch, seqlen).transpose(0, 1)
         if self.in_proj.bias is not None:
@@ -162,7 +244,7 @@ class Mamba(nn.Module):
             xr = x4.permute(0, 3, 1, 2).reshape(batch * K, -1, T)
         else:
             raise NotImplementedError
-        out = inner(xr[:, :, perm].contiguous())[:, perm_rev, :]
+        out = permute_along(inner(permute_along(xr, perm, 2)), perm_rev, 1)
         if s_or_t == "s":
             return out.reshape(batch, seqlen, -1)
         return out.reshape(batch, K, T, -1).permute(0, 2, 1, 3).reshape(batch, seqlen, -1)

@@ -101,7 +101,7 @@ def _scan_fwd(u, delta, A, B, C, D=None, z=None, delta_bias=None, delta_softplus
     ckpt = None
     if want_ckpt:
         nck = max(1, (seqlen + CKPT_EVERY - 1) // CKPT_EVERY)
-        ckpt = torch.empty((batch, dim, nck, dstate), dtype=torch.float32, device=u.device)
+        ckpt = torch.empty((batch, nck, dim, dstate), dtype=torch.float32, device=u.device)
 
     p = _lib.ScanParams()
     p.u, p.delta, p.z, p.B, p.C = _lib.ptr(u), _lib.ptr(delta), _lib.ptr(z), _lib.ptr(B), _lib.ptr(C)
@@ -124,7 +124,7 @@ def _scan_fwd(u, delta, A, B, C, D=None, z=None, delta_bias=None, delta_softplus
     return out, last, ckpt, (u, delta, z, B, C, D, delta_bias, A)
 
 
-def _scan_bwd(saved, ckpt, dout, delta_softplus, dz_out=None):
+def _scan_bwd(saved, ckpt, dout, delta_softplus, dz_out=None, z_rowmap=None):
     """Raw backward (selective_scan_cuda.bwd, selective_scan.cpp:338-492).  Returns
     du, ddelta, dA, dB, dC, dD, ddelta_bias, dz."""
     u, delta, z, B, C, D, delta_bias, A = saved
@@ -162,6 +162,7 @@ def _scan_bwd(saved, ckpt, dout, delta_softplus, dz_out=None):
     p.u, p.delta, p.z, p.B, p.C = _lib.ptr(u), _lib.ptr(delta), _lib.ptr(z), _lib.ptr(B), _lib.ptr(C)
     p.A, p.D, p.delta_bias = _lib.ptr(A), _lib.ptr(D), _lib.ptr(delta_bias)
     p.ckpt = _lib.ptr(ckpt)
+    p.z_rowmap = _lib.ptr(z_rowmap)     # z read / dz written in token order (dstate == 16 kernel only)
     p.u_sb, p.u_sd, p.u_sl = _strides3(u)
     p.delta_sb, p.delta_sd, p.delta_sl = _strides3(delta)
     if z is not None:
@@ -379,6 +380,104 @@ class MambaInnerFn(torch.autograd.Function):
         dbias = dout2.sum(0) if ctx.has_out_bias else None
         (dxz, dcw, dcb, dxw, ddw, dA, dB, dC, dD, dbias_dt, dBb, dCb) = _inner_bwd(ctx, dout_y)
         return (dxz, dcw, dcb, dxw, ddw, dW, dbias, dA, dB, dC, dD, dbias_dt, dBb, dCb, None, None)
+
+
+# ------------------------------------------------------------------------------------------------
+# Token-major training core: what MambaInnerFn computes between in_proj and out_proj, but laid out the
+# way the sampling engine runs it -- activations (batch * seqlen, channels) row-major, the zigzag
+# permutation never materialised (the conv gathers x rows, the scan gathers z rows through the path
+# table; the backward scatters dx / dz rows back through the same table).  No transposed copies, no
+# index_select in either direction.
+def _tok_linear(x, w):
+    """x (M, K) @ w(N, K)^T on the tcgen05 kernel for bf16, cuBLAS otherwise."""
+    if x.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and x.is_cuda:
+        from .engine import _linear
+        return _linear(x, w)
+    return F.linear(x, w)
+
+
+def _tok_core_fwd(xz, conv_w, conv_b, x_proj_w, dt_proj_w, A, D, delta_bias, rowmap, bt, L, want_ckpt):
+    from .causal_conv1d_interface import _conv_fwd
+    E = xz.shape[1] // 2
+    R, N = dt_proj_w.shape[1], A.shape[1]
+    xz3 = xz.view(bt, L, 2 * E)
+    x_log = xz3[:, :, :E].transpose(1, 2)             # logical (bt, E, L), channel stride 1
+    z_log = xz3[:, :, E:].transpose(1, 2)
+    xc = _conv_fwd(x_log, conv_w, conv_b, True, x_rowmap=rowmap)                # token-major memory, scan order
+    xc_flat = xc.transpose(1, 2).reshape(bt * L, E)
+    x_dbl = _tok_linear(xc_flat, x_proj_w)                                       # (bt L, R + 2N)
+    delta = _tok_linear(x_dbl[:, :R], dt_proj_w)                                 # (bt L, E)
+    d_log = delta.view(bt, L, E).transpose(1, 2)
+    xd3 = x_dbl.view(bt, L, R + 2 * N)
+    B_log = xd3[:, :, R:R + N].permute(0, 2, 1).unsqueeze(1)                     # (bt, 1, N, L) views
+    C_log = xd3[:, :, R + N:].permute(0, 2, 1).unsqueeze(1)
+    y, _, ckpt, _ = _scan_fwd(xc, d_log, A, B_log, C_log, D, z_log, delta_bias, True, z_rowmap=rowmap,
+                              want_last_state=False, want_ckpt=want_ckpt)
+    return y, ckpt, x_dbl, (x_log, z_log, xc, xc_flat, d_log, B_log, C_log)
+
+
+class MambaInnerTokFn(torch.autograd.Function):
+    """xz (batch * seqlen, 2 * d_inner) token-major, TOKEN order -> y (batch * seqlen, d_inner) in SCAN
+    order (scan position l holds token rowmap[l]; rowmap None = identity).  Same math as
+    MambaInnerFnNoOutProj (selective_scan_interface.py:155-289 of the reference) applied to
+    xz[:, :, rowmap]; checkpoint_lvl-1 style: the conv output and delta are recomputed in the backward."""
+
+    @staticmethod
+    def forward(ctx, xz, conv1d_weight, conv1d_bias, x_proj_weight, delta_proj_weight, A, D, delta_bias, rowmap, bt, L):
+        if torch.is_autocast_enabled():
+            x_proj_weight = x_proj_weight.to(dtype=torch.get_autocast_gpu_dtype())
+            delta_proj_weight = delta_proj_weight.to(dtype=torch.get_autocast_gpu_dtype())
+        if not xz.is_contiguous():
+            xz = xz.contiguous()
+        conv_w = conv1d_weight.reshape(conv1d_weight.shape[0], conv1d_weight.shape[-1]).contiguous()
+        conv_b = conv1d_bias.contiguous() if conv1d_bias is not None else None
+        need_grad = any(t is not None and t.requires_grad for t in
+                        (xz, conv1d_weight, conv1d_bias, x_proj_weight, delta_proj_weight, A, D, delta_bias))
+        y, ckpt, x_dbl, _ = _tok_core_fwd(xz, conv_w, conv_b, x_proj_weight, delta_proj_weight, A, D, delta_bias,
+                                          rowmap, bt, L, need_grad)
+        if need_grad:
+            ctx.saved = (xz, conv_w, conv_b, x_dbl, x_proj_weight, delta_proj_weight, A, D, delta_bias, ckpt, rowmap)
+            ctx.dims = (bt, L)
+            ctx.wshape = conv1d_weight.shape
+        return y.transpose(1, 2).reshape(bt * L, -1)
+
+    @staticmethod
+    def backward(ctx, dy):
+        from .causal_conv1d_interface import _conv_fwd, _conv_bwd
+        (xz, conv_w, conv_b, x_dbl, x_proj_w, dt_proj_w, A, D, delta_bias, ckpt, rowmap) = ctx.saved
+        bt, L = ctx.dims
+        E = xz.shape[1] // 2
+        R, N = dt_proj_w.shape[1], A.shape[1]
+        xz3 = xz.view(bt, L, 2 * E)
+        x_log, z_log = xz3[:, :, :E].transpose(1, 2), xz3[:, :, E:].transpose(1, 2)
+        xc = _conv_fwd(x_log, conv_w, conv_b, True, x_rowmap=rowmap)             # recompute (cheap, saves 2 E bytes / token)
+        xc_flat = xc.transpose(1, 2).reshape(bt * L, E)
+        delta = _tok_linear(x_dbl[:, :R], dt_proj_w)
+        d_log = delta.view(bt, L, E).transpose(1, 2)
+        xd3 = x_dbl.view(bt, L, R + 2 * N)
+        B_log = xd3[:, :, R:R + N].permute(0, 2, 1).unsqueeze(1)
+        C_log = xd3[:, :, R + N:].permute(0, 2, 1).unsqueeze(1)
+        dxz = torch.empty_like(xz)
+        dxz3 = dxz.view(bt, L, 2 * E)
+        dx_log, dz_log = dxz3[:, :, :E].transpose(1, 2), dxz3[:, :, E:].transpose(1, 2)
+        dy_log = dy.contiguous().view(bt, L, E).transpose(1, 2)
+        du, ddelta, dA, dB, dC, dD, dbias, _ = _scan_bwd((xc, d_log, z_log, B_log, C_log, D, delta_bias, A), ckpt, dy_log,
+                                                         True, dz_out=dz_log, z_rowmap=rowmap)
+        ddelta_flat = ddelta.transpose(1, 2).reshape(bt * L, E)
+        dx_dbl = torch.empty_like(x_dbl)
+        dx_dbl[:, :R] = ddelta_flat @ dt_proj_w
+        dx_dbl[:, R:R + N] = dB.squeeze(1).transpose(1, 2).reshape(bt * L, N)
+        dx_dbl[:, R + N:] = dC.squeeze(1).transpose(1, 2).reshape(bt * L, N)
+        d_dt_w = ddelta_flat.t() @ x_dbl[:, :R]
+        d_x_w = dx_dbl.t() @ xc_flat
+        dxc = torch.addmm(du.transpose(1, 2).reshape(bt * L, E), dx_dbl, x_proj_w)
+        _, dcw, dcb = _conv_bwd(x_log, conv_w, conv_b, dxc.view(bt, L, E).transpose(1, 2), True, dx_out=dx_log, x_rowmap=rowmap)
+        return (dxz, dcw.reshape(ctx.wshape).to(conv_w.dtype), dcb.to(conv_b.dtype) if conv_b is not None else None,
+                d_x_w, d_dt_w, dA, dD if D is not None else None, dbias if delta_bias is not None else None, None, None, None)
+
+
+def mamba_inner_tok_fn(xz, conv1d_weight, conv1d_bias, x_proj_weight, delta_proj_weight, A, D, delta_bias, rowmap, bt, L):
+    return MambaInnerTokFn.apply(xz, conv1d_weight, conv1d_bias, x_proj_weight, delta_proj_weight, A, D, delta_bias, rowmap, bt, L)
 
 
 def mamba_inner_fn(xz, conv1d_weight, conv1d_bias, x_proj_weight, delta_proj_weight,
