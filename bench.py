@@ -198,6 +198,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ref-cuda", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch kernels eagerly (for ncu launch lists)")
+    ap.add_argument("--no-train", action="store_true", help="skip the forward+backward (training step) side measurement")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -336,7 +337,7 @@ def main():
             tp = os.path.join(ROOT, "profiles", "scan_fwd_traffic.json")
             if os.path.exists(tp):
                 traffic = json.load(open(tp)).get("dram_bytes_per_launch")
-            roof = {"bound": "hbm", "kernel": "zg::scan_fwd_kernel<bf16,16,token-major>", "achieved": ach, "peak": peak, "unit": "GB/s",
+            roof = {"bound": "hbm", "kernel": "zg::scan_fwd_tpc2_kernel<bf16> (dstate 16, token-major, z gathered through the zigzag table)", "achieved": ach, "peak": peak, "unit": "GB/s",
                     "frac": ach / peak, "traffic": traffic, "peak_source": how, "ms_per_launch": kms, "algorithmic_bytes": abytes,
                     "launches_per_step": CFG["depth"], "share_of_step": CFG["depth"] * kms / (ms / K)}
 
@@ -371,6 +372,16 @@ def main():
         line["reference_cuda"] = rc
         if rc and "denoiser_eval_ms" in rc:
             line["speedup_vs_reference_cuda"] = rc["denoiser_eval_ms"] / (ms / K)
+    if not args.no_train and world == 1:
+        # side measurement (not the headline): one flow-matching training step, forward + backward, of the same
+        # denoiser at bs 16 -- ours vs the reference's forward/backward CUDA kernels in the reference's glue
+        try:
+            r = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "train_bench.py")], capture_output=True, text=True, timeout=600,
+                               env=dict(os.environ, BS="16", DTYPE="bf16", CUDA_VISIBLE_DEVICES=os.environ.get("CUDA_VISIBLE_DEVICES", str(local))))
+            js = [l for l in r.stdout.splitlines() if l.startswith("{")]
+            line["train_step"] = json.loads(js[-1]) if js else {"error": (r.stderr or r.stdout)[-300:]}
+        except Exception as ex:
+            line["train_step"] = {"error": repr(ex)[:300]}
     if not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
         dt = cpu_reference_eval(cores, 2)

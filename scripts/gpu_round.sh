@@ -11,12 +11,12 @@ echo "== pytest -m gpu"; timeout 2400 python -m pytest tests -m gpu -q -rA -p no
 grep -E "^(PASSED|FAILED|ERROR)|passed|failed" gpurun_out/pytest_gpu.log | tail -100
 if [ -z "$SKIP_BENCH" ]; then
 echo "== bench"; timeout 900 python bench.py --steps ${BENCH_STEPS:-20} --warmup 5 > gpurun_out/bench.log 2> gpurun_out/bench.err; echo "bench rc=$?"; tail -3 gpurun_out/bench.log | cut -c1-400; tail -5 gpurun_out/bench.err
-if [ -n "$BENCH_TCGEN05" ]; then ZIGMA_TCGEN05=1 timeout 900 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-ref-cuda > gpurun_out/bench_tcgen05.log 2> gpurun_out/bench_tcgen05.err; tail -1 gpurun_out/bench_tcgen05.log | cut -c1-300; fi
+if [ -n "$BENCH_TCGEN05" ]; then ZIGMA_TCGEN05=1 timeout 900 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-ref-cuda --no-train > gpurun_out/bench_tcgen05.log 2> gpurun_out/bench_tcgen05.err; tail -1 gpurun_out/bench_tcgen05.log | cut -c1-300; fi
 fi
 if [ -n "$DO_NCU_LIST" ]; then
-echo "== ncu launch list"; timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off -c 400 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-ref-cuda --no-graph > gpurun_out/ncu_list.log 2>&1; echo "ncu rc=$?"
+echo "== ncu launch list"; timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off -c 400 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-ref-cuda --no-train --no-graph > gpurun_out/ncu_list.log 2>&1; echo "ncu rc=$?"
 fi
 if [ -n "$DO_NCU_FULL" ]; then
-echo "== ncu full (scan kernel)"; timeout 900 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:${NCU_KERNEL:-scan_fwd_kernel} -c ${NCU_COUNT:-2} -o gpurun_out/${NCU_OUT:-scan_fwd} python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-ref-cuda --no-graph > gpurun_out/ncu_full.log 2>&1; echo "ncu full rc=$?"
+echo "== ncu full (scan kernel)"; timeout 900 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:${NCU_KERNEL:-scan_fwd_kernel} -c ${NCU_COUNT:-2} -o gpurun_out/${NCU_OUT:-scan_fwd} python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-ref-cuda --no-train --no-graph > gpurun_out/ncu_full.log 2>&1; echo "ncu full rc=$?"
 fi
 echo done

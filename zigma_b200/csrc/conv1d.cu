@@ -301,6 +301,91 @@ __global__ void __launch_bounds__(128) conv_bwd_seqc_kernel(const zg_conv_bwd_pa
 }
 
 
+// backward, seq-contiguous (channel-first), vector path: one warp per (batch, channel) row; a lane owns VEC
+// consecutive positions of a 32 * VEC tile (one 16-byte load of x and of dout, one 16-byte store of dx), the
+// x halo comes from the lane below and the g halo from the lane above by shuffles; tiles are walked from the
+// END of the row so that the three g values the last lane needs from the next tile are already known.  Each
+// silu' is evaluated once (the scalar kernel above evaluates it four times per position).
+template <typename T>
+__global__ void __launch_bounds__(128) conv_bwd_seqc_vec_kernel(const zg_conv_bwd_params q) {
+    constexpr int VEC = 16 / (int)sizeof(T);
+    const zg_conv_params &p = q.fwd;
+    const int E = p.dim, L = p.seqlen, W = p.width;
+    const int warp = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    const int lane = threadIdx.x & 31;
+    if (warp >= p.batch * E) return;
+    const int b = warp / E, e = warp % E;
+    const T *x = reinterpret_cast<const T *>(p.x) + (int64_t)b * p.x_sb + (int64_t)e * p.x_sd;
+    const T *dout = reinterpret_cast<const T *>(q.dout) + (int64_t)b * q.dout_sb + (int64_t)e * q.dout_sd;
+    T *dx = reinterpret_cast<T *>(q.dx) + (int64_t)b * q.dx_sb + (int64_t)e * q.dx_sd;
+    float w[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) w[k] = k < W ? load_w_dt(p.weight, (int64_t)e * W + (W - 1 - k), p.wdtype) : 0.f;
+    const float bias = p.bias ? load_w_dt(p.bias, e, p.wdtype) : 0.f;
+    float dw[4] = {0.f, 0.f, 0.f, 0.f}, db = 0.f;
+    float gn[3] = {0.f, 0.f, 0.f};                 // g at the first three positions of the tile above (0 past the end)
+    const int ntiles = (L + 32 * VEC - 1) / (32 * VEC);
+    for (int tile = ntiles - 1; tile >= 0; --tile) {
+        const int l = tile * 32 * VEC + lane * VEC;          // first position of this lane (L % VEC == 0: all-or-nothing)
+        const bool in = l < L;
+        float xv[VEC + 3], g[VEC + 3];                        // xv[j] = x[l - 3 + j];  g[j] = g[l + j]
+        float go[VEC];
+        if (in) {
+            load_vec<T, VEC>(*reinterpret_cast<float(*)[VEC]>(&xv[3]), x + l);
+            load_vec<T, VEC>(go, dout + l);
+        } else {
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) { xv[3 + j] = 0.f; go[j] = 0.f; }
+        }
+        // x halo: the last three positions of the lane below; lane 0 reads them from memory
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            const float up = __shfl_up_sync(0xffffffffu, xv[VEC + j], 1);
+            xv[j] = up;
+        }
+        if (lane == 0) {
+#pragma unroll
+            for (int j = 0; j < 3; ++j) xv[j] = (l - 3 + j >= 0 && in) ? zg_to_float<T>(x[l - 3 + j]) : 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) {
+            float gg = go[j];
+            if (p.silu) {
+                const float pre = fmaf(w[0], xv[j + 3], fmaf(w[1], xv[j + 2], fmaf(w[2], xv[j + 1], fmaf(w[3], xv[j], bias))));
+                const float sg = zg_sigmoid(pre);
+                gg *= sg * fmaf(pre, 1.f - sg, 1.f);
+            }
+            g[j] = in ? gg : 0.f;
+            db += g[j];
+            dw[0] = fmaf(g[j], xv[j + 3], dw[0]);
+            dw[1] = fmaf(g[j], xv[j + 2], dw[1]);
+            dw[2] = fmaf(g[j], xv[j + 1], dw[2]);
+            dw[3] = fmaf(g[j], xv[j], dw[3]);
+        }
+        // g halo: the first three positions of the lane above; the last lane takes the tile above's
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            const float dn = __shfl_down_sync(0xffffffffu, g[j], 1);
+            g[VEC + j] = (lane == 31) ? gn[j] : dn;
+        }
+        if (in) {
+            float o[VEC];
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) o[j] = fmaf(w[0], g[j], fmaf(w[1], g[j + 1], fmaf(w[2], g[j + 2], w[3] * g[j + 3])));
+            store_vec<T, VEC>(dx + l, o);
+        }
+#pragma unroll
+        for (int j = 0; j < 3; ++j) gn[j] = __shfl_sync(0xffffffffu, g[j], 0);
+    }
+    db = zg_warp_sum(db);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) dw[k] = zg_warp_sum(dw[k]);
+    if (lane == 0) {
+        if (q.dbias) atomicAdd(q.dbias + e, db);
+        for (int k = 0; k < W; ++k) atomicAdd(q.dweight + (int64_t)e * W + (W - 1 - k), dw[k]);
+    }
+}
+
 // backward, dim-contiguous (token-major): a thread owns DV adjacent channels and CONV_BLCH consecutive
 // positions and streams upwards in l with two sliding windows (x[l-3..l] for the pre-activation,
 // g[l-3..l] for dx[l-3] = sum_k w[k] g[l-3+k]); the three positions after the chunk are walked as a
@@ -309,9 +394,10 @@ __global__ void __launch_bounds__(128) conv_bwd_seqc_kernel(const zg_conv_bwd_pa
 // back to token order).  dweight/dbias: summed over the 4 warps of the CTA (4 chunks of the same
 // channels) in shared memory, then one atomic per (CTA, channel, tap).
 constexpr int CONV_BLCH = 64;
+constexpr int CONV_BRB = 4;     // rows per batch of independent loads in the backward (x and dout: 2 * CONV_BRB loads in flight)
 
 template <typename T, int DV>
-__global__ void __launch_bounds__(128) conv_bwd_tok_kernel(const zg_conv_bwd_params q) {
+__global__ void __launch_bounds__(128, 4) conv_bwd_tok_kernel(const zg_conv_bwd_params q) {
     const zg_conv_params &p = q.fwd;
     const int E = p.dim, L = p.seqlen, W = p.width;
     const int nvec = E / DV;
@@ -353,46 +439,59 @@ __global__ void __launch_bounds__(128) conv_bwd_tok_kernel(const zg_conv_bwd_par
         if (l0 >= 3) load_vec<T, DV>(x3, x + rowof(l0 - 3) * p.x_sl);
         const int lend = min(l0 + CONV_BLCH, L);
         const int lhalo = min(lend + 3, L);
-#pragma unroll 2
-        for (int l = l0; l < lend + 3; ++l) {
-            float g0[DV], x0[DV];
-            if (l < lhalo) {
-                float go[DV];
-                load_vec<T, DV>(x0, x + rowof(l) * p.x_sl);
-                load_vec<T, DV>(go, dout + (int64_t)l * q.dout_sl);
+        // positions are walked in batches of CONV_BRB: all 2 * CONV_BRB row loads of a batch are issued before the
+        // first use (ncu round 1, one row at a time: half of the stall samples sat on the first use of a load)
+#pragma unroll 1
+        for (int lb = l0; lb < lend + 3; lb += CONV_BRB) {
+            VecT<T, DV> xr[CONV_BRB], gr[CONV_BRB];
 #pragma unroll
-                for (int i = 0; i < DV; ++i) {
-                    float gg = go[i];
-                    if (p.silu) {
-                        const float pre = fmaf(w[0][i], x0[i], fmaf(w[1][i], x1[i], fmaf(w[2][i], x2[i], fmaf(w[3][i], x3[i], bias[i]))));
-                        const float sg = zg_sigmoid(pre);
-                        gg *= sg * fmaf(pre, 1.f - sg, 1.f);
-                    }
-                    g0[i] = gg;
+            for (int j = 0; j < CONV_BRB; ++j) {
+                const int l = lb + j;
+                if (l < lhalo) {
+                    xr[j] = *reinterpret_cast<const VecT<T, DV> *>(x + rowof(l) * p.x_sl);
+                    gr[j] = *reinterpret_cast<const VecT<T, DV> *>(dout + (int64_t)l * q.dout_sl);
                 }
-                if (l < lend) {
+            }
+#pragma unroll
+            for (int j = 0; j < CONV_BRB; ++j) {
+                const int l = lb + j;
+                float g0[DV], x0[DV];
+                if (l < lhalo) {
 #pragma unroll
                     for (int i = 0; i < DV; ++i) {
-                        db[i] += g0[i];
-                        dw[0][i] = fmaf(g0[i], x0[i], dw[0][i]);
-                        dw[1][i] = fmaf(g0[i], x1[i], dw[1][i]);
-                        dw[2][i] = fmaf(g0[i], x2[i], dw[2][i]);
-                        dw[3][i] = fmaf(g0[i], x3[i], dw[3][i]);
+                        x0[i] = zg_to_float<T>(xr[j].e[i]);
+                        float gg = zg_to_float<T>(gr[j].e[i]);
+                        if (p.silu) {
+                            const float pre = fmaf(w[0][i], x0[i], fmaf(w[1][i], x1[i], fmaf(w[2][i], x2[i], fmaf(w[3][i], x3[i], bias[i]))));
+                            const float sg = zg_sigmoid(pre);
+                            gg *= sg * fmaf(pre, 1.f - sg, 1.f);
+                        }
+                        g0[i] = gg;
                     }
+                    if (l < lend) {
+#pragma unroll
+                        for (int i = 0; i < DV; ++i) {
+                            db[i] += g0[i];
+                            dw[0][i] = fmaf(g0[i], x0[i], dw[0][i]);
+                            dw[1][i] = fmaf(g0[i], x1[i], dw[1][i]);
+                            dw[2][i] = fmaf(g0[i], x2[i], dw[2][i]);
+                            dw[3][i] = fmaf(g0[i], x3[i], dw[3][i]);
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < DV; ++i) { g0[i] = 0.f; x0[i] = 0.f; }
                 }
-            } else {
+                const int m = l - 3;                      // dx[m] = w0 g[m] + w1 g[m+1] + w2 g[m+2] + w3 g[m+3]
+                if (m >= l0 && m < lend) {
+                    float o[DV];
 #pragma unroll
-                for (int i = 0; i < DV; ++i) { g0[i] = 0.f; x0[i] = 0.f; }
+                    for (int i = 0; i < DV; ++i) o[i] = fmaf(w[0][i], g3[i], fmaf(w[1][i], g2[i], fmaf(w[2][i], g1[i], w[3][i] * g0[i])));
+                    store_vec<T, DV>(dx + rowof(m) * q.dx_sl, o);
+                }
+#pragma unroll
+                for (int i = 0; i < DV; ++i) { x3[i] = x2[i]; x2[i] = x1[i]; x1[i] = x0[i]; g3[i] = g2[i]; g2[i] = g1[i]; g1[i] = g0[i]; }
             }
-            const int m = l - 3;                          // dx[m] = w0 g[m] + w1 g[m+1] + w2 g[m+2] + w3 g[m+3]
-            if (m >= l0) {                                //   (m < lend always holds inside the loop)
-                float o[DV];
-#pragma unroll
-                for (int i = 0; i < DV; ++i) o[i] = fmaf(w[0][i], g3[i], fmaf(w[1][i], g2[i], fmaf(w[2][i], g1[i], w[3][i] * g0[i])));
-                store_vec<T, DV>(dx + rowof(m) * q.dx_sl, o);
-            }
-#pragma unroll
-            for (int i = 0; i < DV; ++i) { x3[i] = x2[i]; x2[i] = x1[i]; x1[i] = x0[i]; g3[i] = g2[i]; g2[i] = g1[i]; g1[i] = g0[i]; }
         }
     }
     // CTA reduction of the weight / bias gradients over the 4 warps
@@ -539,10 +638,14 @@ extern "C" int zg_causal_conv1d_bwd(const zg_conv_bwd_params *qq, void *stream) 
     ZG_REQUIRE(q.fwd.x_rowmap == nullptr, "causal_conv1d_bwd: x_rowmap needs the dim-contiguous layout");
     const int64_t nthreads = (int64_t)q.fwd.batch * q.fwd.dim * 32;
     const unsigned grid = (unsigned)((nthreads + 127) / 128);
+    const int vec = 16 / zg_dtype_size(p.dtype);
+    const uintptr_t al2 = reinterpret_cast<uintptr_t>(p.x) | reinterpret_cast<uintptr_t>(q.dout) | reinterpret_cast<uintptr_t>(q.dx);
+    const int64_t so2 = p.x_sb | p.x_sd | q.dout_sb | q.dout_sd | q.dx_sb | q.dx_sd;
+    const bool fast = (p.seqlen % vec == 0) && (al2 % 16 == 0) && (so2 % vec == 0);
     switch (q.fwd.dtype) {
-        case ZG_F32: zg::conv_bwd_seqc_kernel<float><<<grid, 128, 0, s>>>(q); break;
-        case ZG_F16: zg::conv_bwd_seqc_kernel<__half><<<grid, 128, 0, s>>>(q); break;
-        default: zg::conv_bwd_seqc_kernel<__nv_bfloat16><<<grid, 128, 0, s>>>(q); break;
+        case ZG_F32: if (fast) zg::conv_bwd_seqc_vec_kernel<float><<<grid, 128, 0, s>>>(q); else zg::conv_bwd_seqc_kernel<float><<<grid, 128, 0, s>>>(q); break;
+        case ZG_F16: if (fast) zg::conv_bwd_seqc_vec_kernel<__half><<<grid, 128, 0, s>>>(q); else zg::conv_bwd_seqc_kernel<__half><<<grid, 128, 0, s>>>(q); break;
+        default: if (fast) zg::conv_bwd_seqc_vec_kernel<__nv_bfloat16><<<grid, 128, 0, s>>>(q); else zg::conv_bwd_seqc_kernel<__nv_bfloat16><<<grid, 128, 0, s>>>(q); break;
     }
     zg_count_launch();
     return zg_check_launch("causal_conv1d_bwd");
