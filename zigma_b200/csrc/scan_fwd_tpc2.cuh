@@ -62,6 +62,7 @@ __global__ void __launch_bounds__(TPC2_THREADS, 9) scan_fwd_tpc2_kernel(const zg
     const float Dv = p.D ? p.D[e] : 0.f;
     const float bias = p.delta_bias ? p.delta_bias[e] : 0.f;
     const int nstages = L / TL;
+    const bool do_ckpt = p.ckpt != nullptr;      // host side: only with ckpt_every == 8
 
     auto issue_stage = [&](int s) {
         if (s < nstages) {
@@ -140,15 +141,11 @@ __global__ void __launch_bounds__(TPC2_THREADS, 9) scan_fwd_tpc2_kernel(const zg
             float y = (hf ? yp1 : yp0) + recv + Dv * (hf ? u1 : u0);
             if (has_z) y *= zg_silu(zg_to_float<T>(sz[tm * CH]));
             ocol[tm * (int)p.out_sl] = zg_from_float<T>(y);
-            if (p.ckpt) {                   // recompute seeds for the backward pass (uniform branch)
-                const int lend = s * TL + t0 + 2;
-                if (lend % p.ckpt_every == 0 || lend == L) {
-                    const int nck = (L + p.ckpt_every - 1) / p.ckpt_every;
-                    // (batch, n_ckpt, dim, dstate): the 16 channels x 2 halves of a warp write 1 KB contiguous
-                    float4 *dst = reinterpret_cast<float4 *>(p.ckpt + (((int64_t)b * nck + (lend - 1) / p.ckpt_every) * E + e) * NS + 8 * hf);
-                    dst[0] = make_float4(h2[0].x, h2[0].y, h2[1].x, h2[1].y);
-                    dst[1] = make_float4(h2[2].x, h2[2].y, h2[3].x, h2[3].y);
-                }
+            if (do_ckpt && ((t0 + 2) & 7) == 0) {       // recompute seeds for the backward pass: every 8 steps (uniform branch)
+                // (batch, n_ckpt, dim, dstate): the 16 channels x 2 halves of a warp write 1 KB contiguous
+                float4 *dst = reinterpret_cast<float4 *>(p.ckpt + (((int64_t)b * (L >> 3) + ((s * TL + t0 + 2) >> 3) - 1) * E + e) * NS + 8 * hf);
+                dst[0] = make_float4(h2[0].x, h2[0].y, h2[1].x, h2[1].y);
+                dst[1] = make_float4(h2[2].x, h2[2].y, h2[3].x, h2[3].y);
             }
         }
         __syncthreads();
@@ -167,6 +164,7 @@ template <typename T> int try_launch_scan_fwd_tpc2(const zg_scan_params &p, cuda
     if (!enabled || sizeof(T) != 2) return -1;
     const bool varBC = (p.flags & ZG_SCAN_VARIABLE_B) && (p.flags & ZG_SCAN_VARIABLE_C);
     if (!varBC || p.dstate != 16 || p.seqlen % SCAN_TL != 0 || p.seqlen == 0) return -1;
+    if (p.ckpt && p.ckpt_every != 8) return -1;
     if ((p.dim / p.ngroups) % SCAN_CH != 0) return -1;
     if (!(p.u_sd == 1 && p.delta_sd == 1 && p.out_sd == 1 && (!p.z || p.z_sd == 1) && p.B_sn == 1 && p.C_sn == 1)) return -1;
     const uintptr_t al = reinterpret_cast<uintptr_t>(p.u) | reinterpret_cast<uintptr_t>(p.delta) | reinterpret_cast<uintptr_t>(p.z) |
