@@ -213,6 +213,25 @@ typedef struct {
 
 int zg_gemm_bf16_tn(const zg_gemm_params *p, void *stream);
 
+
+/* ---------------------------------------------------------------------------------------------
+ * Fused AdamW + EMA step over flat fp32 buffers of n elements (the optimiser / EMA part of the training
+ * step around the path: train_acc.py:213-215,442-448, utils/train_utils.py:104-115 of the reference):
+ *     g  = grad * grad_scale (* *grad_scale_ptr when given: a device scalar, e.g. a clip coefficient)
+ *     p *= 1 - lr * weight_decay;   m = beta1 m + (1-beta1) g;   v = beta2 v + (1-beta2) g^2
+ *     p -= lr / bias_correction1 * m / (sqrt(v) / sqrt(bias_correction2) + eps)
+ *     ema = ema_decay * ema + (1 - ema_decay) * p            (ema may be NULL)
+ * bias_correction{1,2} = 1 - beta{1,2}^step are computed by the caller.  grad is not modified.
+ */
+typedef struct {
+    float *param, *exp_avg, *exp_avg_sq, *ema;
+    const float *grad, *grad_scale_ptr;
+    int64_t n;
+    float lr, beta1, beta2, eps, weight_decay, bias_correction1, bias_correction2, ema_decay, grad_scale;
+} zg_adamw_params;
+
+int zg_adamw_ema_step(const zg_adamw_params *p, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

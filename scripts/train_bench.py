@@ -64,6 +64,26 @@ torch.cuda.reset_peak_memory_stats()
 ours_step(); torch.cuda.synchronize()
 res["ours_peak_mem_gb"] = torch.cuda.max_memory_allocated() / 2 ** 30
 
+# ---- optimiser + EMA part of the iteration (fp32 master weights only): fused kernel vs torch AdamW + the reference's EMA loop
+if MODE != "bf16":
+    from zigma_b200.train import FlatParams, FusedAdamWEMA, reference_update_ema_
+    import copy
+    twin = copy.deepcopy(m)
+    flat = FlatParams(m)
+    fopt = FusedAdamWEMA(flat, lr=1e-4, weight_decay=0.0)
+    ours_step()
+    res["ours_adamw_ema_ms"] = timeit(lambda: fopt.step(), n=10)
+    tp = [p_ for p_ in twin.parameters() if p_.requires_grad]
+    for p_ in tp:
+        p_.grad = torch.randn_like(p_)
+    topt = torch.optim.AdamW(tp, lr=1e-4, weight_decay=0.0)
+    ema_ref = [p_.detach().clone() for p_ in tp]
+    def torch_opt():
+        topt.step(); reference_update_ema_(ema_ref, tp)
+    res["torch_adamw_plus_ema_loop_ms"] = timeit(torch_opt, n=10)
+    res["n_params"] = flat.numel
+    del twin, topt, ema_ref
+
 if ref_cuda.available():
     sdr = {k: v.to(dev).clone().requires_grad_(v.is_floating_point()) for k, v in sd.items()}
     norm = lambda x_, w, b, residual=None, prenorm=False, residual_in_fp32=False, eps=1e-6: rms_norm_fn(

@@ -73,9 +73,16 @@ class GemmParams(C.Structure):
                 + [(n, i32) for n in ("M", "N", "K", "rows_per_batch")])
 
 
+class AdamWParams(C.Structure):
+    _fields_ = ([(n, vp) for n in ("param", "exp_avg", "exp_avg_sq", "ema", "grad", "grad_scale_ptr")]
+                + [("n", i64)]
+                + [(n, f32) for n in ("lr", "beta1", "beta2", "eps", "weight_decay", "bias_correction1", "bias_correction2",
+                                      "ema_decay", "grad_scale")])
+
+
 EXPORTS = ["zg_abi_version", "zg_last_error", "zg_launch_count", "zg_selective_scan_fwd", "zg_selective_scan_bwd",
            "zg_causal_conv1d_fwd", "zg_causal_conv1d_bwd", "zg_add_norm_fwd", "zg_add_norm_bwd",
-           "zg_block_tail_fwd", "zg_gemm_bf16_tn"]
+           "zg_block_tail_fwd", "zg_gemm_bf16_tn", "zg_adamw_ema_step"]
 
 _lib = None
 
