@@ -1,4 +1,4 @@
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_train.py tests/test_gpu_ops.py -m gpu -q -x -p no:cacheprovider --timeout=600 > gpurun_out/pytest_train.log 2>&1; echo "pytest rc=$?"; tail -8 gpurun_out/pytest_train.log
-for bs in 16 64; do BS=$bs DTYPE=bf16 timeout 600 python scripts/train_bench.py 2>&1 | grep "^{" | cut -c1-420; done | tee gpurun_out/train_bench_bs.log
-BS=16 DTYPE=amp timeout 600 python scripts/train_bench.py 2>&1 | grep "^{" | cut -c1-700 | tee -a gpurun_out/train_bench_bs.log
+timeout 300 python scripts/train_ddp_bench.py 2>&1 | grep "^{" | tee gpurun_out/train_ddp.log
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29611 scripts/train_ddp_bench.py 2>&1 | grep -E "^\{|Error|error" | tee -a gpurun_out/train_ddp.log
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29612 bench.py --gpus 2 --steps 20 --warmup 5 2> gpurun_out/bench_n2.err | tail -1 > gpurun_out/bench_n2.log; cut -c1-300 gpurun_out/bench_n2.log
