@@ -11,7 +11,7 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda"
 
 
-@pytest.mark.parametrize("name", ["t128_g1", "t131_g2", "e64_n16", "noz", "l1", "l16_many", "n4"])
+@pytest.mark.parametrize("name", ["t128_g1", "t131_g2", "e64_n16", "plain", "noz", "l1", "l16_many", "n4"])
 def test_selective_scan_bwd_golden(name):
     """Gradients of selective_scan_fn vs autograd through the reference's selective_scan_ref
     (test_selective_scan.py:121-149 protocol; tolerances: the north-star rtol 1e-3 with a range-scaled
@@ -154,3 +154,66 @@ def test_mamba_token_major_path_matches_channel_first(scan_type, dtype, monkeypa
     assert set(res["1"][2]) == set(res["0"][2]) and len(res["1"][2]) >= 9
     for k in res["0"][2]:
         check_close(res["1"][2][k], res["0"][2][k], f"{scan_type} token-major d{k}", **tol)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_scan_bwd_staged_kernel_groups_rowmap_vs_oracle_autograd(dtype):
+    """The cp.async-staged dstate-16 backward (whole 64-channel tiles, L % 8 == 0): two groups, both layouts, and the
+    fused z permutation (z_rowmap) -- against autograd through the CPU oracle on gathered inputs."""
+    from zigma_b200.selective_scan_interface import _scan_fwd, _scan_bwd
+    Bt, E, L, N, G = 2, 128, 72, 16, 2
+    inp = synth.synth_scan_inputs(Bt, E, L, N, G, seed=31)
+    lo = {k: (v.to(dtype) if k in ("u", "delta", "z", "B", "C") else v.clone()) for k, v in inp.items()}
+    perm = torch.randperm(L, generator=torch.Generator().manual_seed(5))
+    gout = torch.randn(Bt, E, L, generator=torch.Generator().manual_seed(6)).to(dtype)
+    ref = {k: v.float().clone().requires_grad_() for k, v in lo.items()}
+    out_ref = zo.selective_scan(ref["u"], ref["delta"], ref["A"], ref["B"], ref["C"], ref["D"], ref["z"][:, :, perm], ref["delta_bias"], True)
+    out_ref.backward(gout.float())
+    tm = lambda a: a.transpose(-1, -2).contiguous().transpose(-1, -2)
+    d = {k: v.to(DEV) for k, v in lo.items()}
+    tol = dict(rtol=3e-2, atol=3e-2, max_strict_viol=1.0) if dtype == torch.bfloat16 else dict(atol=1e-4, max_strict_viol=1e-2)
+    for layout in ("tok", "seq"):
+        if layout == "tok":
+            u, dl, z, B, C, go = tm(d["u"]), tm(d["delta"]), tm(d["z"]), tm(d["B"]), tm(d["C"]), tm(gout.to(DEV))
+            rowmap = perm.to(DEV).to(torch.int32)
+        else:   # channel-first has no rowmap: hand over the gathered z and scatter dz afterwards
+            u, dl, z, B, C, go = d["u"], d["delta"], d["z"][:, :, perm.to(DEV)].contiguous(), d["B"], d["C"], gout.to(DEV)
+            rowmap = None
+        out, _, ckpt, saved = _scan_fwd(u, dl, d["A"], B, C, d["D"], z, d["delta_bias"], True, z_rowmap=rowmap, want_last_state=False, want_ckpt=True)
+        check_close(out, out_ref, f"staged {layout} fwd(+ckpt)", **tol)
+        du, ddl, dA, dB, dC, dD, dbias, dz = _scan_bwd(saved, ckpt, go, True, z_rowmap=rowmap)
+        if layout == "seq":
+            full = torch.empty_like(dz); full[:, :, perm.to(DEV)] = dz; dz = full
+        for name, got, want in (("du", du, ref["u"].grad), ("ddelta", ddl, ref["delta"].grad), ("dz", dz, ref["z"].grad), ("dA", dA, ref["A"].grad),
+                                ("dB", dB, ref["B"].grad), ("dC", dC, ref["C"].grad), ("dD", dD, ref["D"].grad), ("dbias", dbias, ref["delta_bias"].grad)):
+            check_close(got, want, f"staged {layout} {name}", **tol)
+
+
+def test_scan_bwd_full_size_properties():
+    """BASELINE config-2 layer shape (bs 16 x 1280 x 1024, bf16, token-major): (a) every gradient is linear in dout --
+    bwd(2 dout) == 2 bwd(dout) exactly for the per-element outputs (power-of-two scaling commutes with every rounding),
+    (b) the first half of the batch gives bit-identical du / ddelta / dz when the second half of every input changes."""
+    from zigma_b200.selective_scan_interface import _scan_fwd, _scan_bwd
+    bs, E, L, N = 16, 1280, 1024, 16
+    g = torch.Generator(device=DEV).manual_seed(0)
+    dt = torch.bfloat16
+    mk = lambda *s: torch.randn(*s, device=DEV, generator=g).to(dt)
+    u, z, dout = mk(bs, L, E).transpose(1, 2), mk(bs, L, E).transpose(1, 2), mk(bs, L, E).transpose(1, 2)
+    delta = (0.5 * torch.rand(bs, L, E, device=DEV, generator=g)).to(dt).transpose(1, 2)
+    B, C = mk(bs, 1, L, N).transpose(2, 3), mk(bs, 1, L, N).transpose(2, 3)
+    A = -0.5 * torch.rand(E, N, device=DEV, generator=g); D = torch.randn(E, device=DEV, generator=g); bias = 0.5 * torch.rand(E, device=DEV, generator=g)
+    _, _, ckpt, saved = _scan_fwd(u, delta, A, B, C, D, z, bias, True, want_last_state=False, want_ckpt=True)
+    r1 = _scan_bwd(saved, ckpt, dout, True)
+    r2 = _scan_bwd(saved, ckpt, dout * 2, True)
+    for i, name in ((0, "du"), (1, "ddelta"), (7, "dz")):
+        assert torch.equal(r2[i].float(), 2 * r1[i].float()), name
+    check_close(r2[3], 2 * r1[3], "dB linear", rtol=1e-4, atol=1e-3, max_strict_viol=1.0)      # (atomics: order-dependent last bits)
+    u2, z2, dl2, do2 = u.clone(), z.clone(), delta.clone(), dout.clone()
+    for t_ in (u2, z2, dl2, do2):
+        t_[bs // 2:] = t_[bs // 2:].flip(0)
+    B2, C2 = B.clone(), C.clone(); B2[bs // 2:] = B2[bs // 2:].flip(0); C2[bs // 2:] = C2[bs // 2:].flip(0)
+    _, _, ck2, sv2 = _scan_fwd(u2, dl2, A, B2, C2, D, z2, bias, True, want_last_state=False, want_ckpt=True)
+    r3 = _scan_bwd(sv2, ck2, do2, True)
+    for i, name in ((0, "du"), (1, "ddelta"), (7, "dz")):
+        assert torch.equal(r3[i][:bs // 2], r1[i][:bs // 2]), name + " batch slice"
+        assert torch.equal(r3[i][bs // 2:], r1[i][bs // 2:].flip(0)), name + " flipped half"

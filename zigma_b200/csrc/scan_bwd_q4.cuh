@@ -290,7 +290,7 @@ __global__ void __launch_bounds__(Q4_THREADS, 4) scan_bwd_q4_kernel(const zg_sca
                     s1q += __shfl_xor_sync(0xffffffffu, s1q, o);
                     s2q += __shfl_xor_sync(0xffffffffu, s2q, o);
                 }
-                // (the quad's reads of *scp above precede this write in the warp's program order)
+                __syncwarp();        // the quad has read *scp (compute-sanitizer racecheck: WAR hazard without it)
                 if (qd == 0) {
                     const float du_ = fmaf(s.x, s1q, s.z * Dv);
                     float dd = fmaf(s2q, ZG_LN2, s.y * s1q);
