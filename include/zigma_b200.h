@@ -190,9 +190,37 @@ typedef struct {
     int32_t batch, seqlen, dim;
     int32_t dtype, final_layer;
     float eps;
+    float *rstd;                  /* (batch * seqlen) fp32 or NULL: 1 / sqrt(mean(r^2) + eps), saved for the backward */
 } zg_block_tail_params;
 
 int zg_block_tail_fwd(const zg_block_tail_params *p, void *stream);
+
+/* Backward of the block tail (training).  With the forward's
+ *     hidden = x + gate * mix[rowmap];  r = residual + hidden;  normed = r * rstd * norm_w;  modded = normed * (1 + scale) + shift
+ * and incoming gradients d_residual_out (fp32), d_normed, d_modded (dtype; any of them may be NULL = zero):
+ *     dy      = d_normed + d_modded * (1 + scale)          dshift[b] += sum_l d_modded      dscale[b] += sum_l d_modded * normed
+ *     dr      = rmsnorm_bwd(dy; r, rstd, norm_w) + d_residual_out                           d_norm_w  += sum dy * r * rstd
+ *     d_residual_in = dr (fp32);   dh = round_to_dtype(dr);   d_x = dh
+ *     d_mix[rowmap[l]] = gate * dh[l]                       dgate[b] += sum_l dh[l] * mix[rowmap[l]]
+ * r = the forward's residual_out, rstd its rstd.  dgate / dshift / dscale are (batch, dim) fp32 accumulated with atomics
+ * (caller zero-fills).  d_norm_w is a PARTIALS buffer (nparts, dim) fp32: the kernel runs nparts persistent CTAs and CTA i
+ * stores its column sums in row i (no atomics; the caller adds the rows up; nparts ~ 3 per SM is a good choice).  mix / gate / d_mix / dgate NULL together for the first block;
+ * d_residual_in NULL when the forward had no residual input.  Replaces, in the reference's training graph, the backward
+ * of _layer_norm_fwd/_bwd (layernorm.py:195-290) plus the autograd nodes of modulate and the gated residual add
+ * (model_zigma.py:416-445). */
+typedef struct {
+    const float *d_residual_out;
+    const void *d_normed, *d_modded;
+    const float *r, *rstd;
+    const void *mix, *gate, *scale, *norm_w;
+    const int32_t *rowmap;
+    void *d_x, *d_mix;
+    float *d_residual_in, *dgate, *dshift, *dscale, *d_norm_w;
+    int64_t mod_rs;
+    int32_t batch, seqlen, dim, dtype, nparts;
+} zg_block_tail_bwd_params;
+
+int zg_block_tail_bwd(const zg_block_tail_bwd_params *p, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
  * bf16 GEMM on tcgen05 tensor cores:  C[M,N] = A[M,K] * B[N,K]^T (+ bias[N]), fp32 accumulate in

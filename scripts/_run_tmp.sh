@@ -1,4 +1,2 @@
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_bwd.py -m gpu -q -x -p no:cacheprovider --timeout=600 > gpurun_out/pytest_bwd.log 2>&1; echo "pytest rc=$?"; tail -6 gpurun_out/pytest_bwd.log
-echo "== memcheck"; timeout 1200 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_bwd.py tests/test_gpu_ops.py -m gpu -q -x -p no:cacheprovider --timeout=1000 -k "staged or token_major or rowmap or bwd_golden or backward_golden or add_norm" > gpurun_out/sanitizer_memcheck.log 2>&1; echo "memcheck rc=$?"; grep -E "ERROR SUMMARY|passed|failed|Invalid|out of bounds" gpurun_out/sanitizer_memcheck.log | tail -5
-echo "== racecheck"; timeout 1200 compute-sanitizer --tool racecheck --error-exitcode 9 python -m pytest tests/test_gpu_bwd.py -m gpu -q -x -p no:cacheprovider --timeout=1000 -k "staged or bwd_golden" > gpurun_out/sanitizer_racecheck.log 2>&1; echo "racecheck rc=$?"; grep -E "RACECHECK SUMMARY|passed|failed|hazard" gpurun_out/sanitizer_racecheck.log | tail -5
+timeout 900 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:"conv_bwd_tok|block_tail_bwd" -c 2 -o gpurun_out/conv_bwd python scripts/profile_bwd.py > gpurun_out/ncu_conv.log 2>&1; echo "ncu rc=$?"; tail -2 gpurun_out/ncu_conv.log

@@ -40,6 +40,10 @@ print("   channel-first vs token-major grads: " + ", ".join(f"{n} {(a_.float() -
 w = torch.randn(E, 4, device=dev, generator=g).to(dt); cb = torch.randn(E, device=dev, generator=g).to(dt)
 t_cb = timeit(lambda: _conv_bwd(u, w, cb, dout, True))
 print(f"ours conv bwd {t_cb:.3f} ms")
+from zigma_b200 import zigzag_path
+perm = torch.from_numpy(zigzag_path(32)[1]).to(dev).to(torch.int32)
+t_cbt = timeit(lambda: _conv_bwd(ut, w, cb, doutt, True, x_rowmap=perm))
+print(f"ours token-major conv bwd (+rowmap) {t_cbt:.3f} ms")
 if ref_cuda.available():
     ss, cc = ref_cuda.load()
     o = ss.fwd(u, delta, A, B, C, D, z, bias, True)

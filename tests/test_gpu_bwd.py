@@ -217,3 +217,71 @@ def test_scan_bwd_full_size_properties():
     for i, name in ((0, "du"), (1, "ddelta"), (7, "dz")):
         assert torch.equal(r3[i][:bs // 2], r1[i][:bs // 2]), name + " batch slice"
         assert torch.equal(r3[i][bs // 2:], r1[i][bs // 2:].flip(0)), name + " flipped half"
+
+
+def test_block_tail_fn_vs_unfused_autograd():
+    """BlockTailFn (zg_block_tail_fwd / zg_block_tail_bwd) against torch autograd through the unfused formula, fp32:
+    first block (no mix / residual), a middle block with the un-permutation folded in, odd row count (strips that cross
+    batch boundaries), one missing output gradient."""
+    from zigma_b200.block_ops import block_tail_fn
+    gen = torch.Generator(device=DEV).manual_seed(3)
+    rn = lambda *s: torch.randn(*s, device=DEV, generator=gen)
+    for (B, L, D, first) in ((3, 37, 64, False), (2, 24, 640, False), (2, 16, 128, True)):
+        perm = torch.randperm(L, device=DEV, generator=gen)
+        leaf = lambda *s: rn(*s).requires_grad_()
+        x, mix, mods, nw, res = leaf(B, L, D), leaf(B, L, D), leaf(B, 3 * D), leaf(D), leaf(B, L, D)
+        gro, gn, gm = rn(B, L, D), rn(B, L, D), rn(B, L, D)
+
+        def unfused(x, mix, mods, nw, res):
+            shift, scale, gate = mods.chunk(3, dim=1)
+            hidden = x if first else x + gate.unsqueeze(1) * mix[:, perm]
+            r = hidden if first else res + hidden
+            normed = r * torch.rsqrt(r.pow(2).mean(-1, keepdim=True) + 1e-5) * nw
+            return r, normed, normed * (1 + scale.unsqueeze(1)) + shift.unsqueeze(1)
+
+        def fused(x, mix, mods, nw, res):
+            shift, scale, gate = mods.chunk(3, dim=1)
+            if first:
+                return block_tail_fn(x, None, None, shift, scale, nw, None, None, 1e-5)
+            return block_tail_fn(x, mix, gate, shift, scale, nw, res, perm.to(torch.int32), 1e-5)
+        outs = {}
+        for name, fn in (("ref", unfused), ("ours", fused)):
+            for t_ in (x, mix, mods, nw, res):
+                t_.grad = None
+            r, n, m = fn(x, mix, mods, nw, res)
+            loss = (r * gro).sum() + (n * gn).sum() + ((m * gm).sum() if D != 128 else 0.0)       # D == 128 case: no d_modded
+            loss.backward()
+            outs[name] = [r.detach(), n.detach(), m.detach()] + [None if t_.grad is None else t_.grad.clone() for t_ in (x, mix, mods, nw, res)]
+        for i, what in enumerate(("residual_out", "normed", "modded", "dx", "dmix", "dmods", "dnorm_w", "dresidual")):
+            a, b = outs["ours"][i], outs["ref"][i]
+            if b is None or (first and what in ("dmix", "dresidual")):
+                assert a is None or float(a.abs().max()) == 0.0, what
+                continue
+            check_close(a, b, f"block tail {B}x{L}x{D} first={first} {what}", atol=2e-5, max_strict_viol=1e-2)
+
+
+@pytest.mark.parametrize("name", ["tiny_zigzag8", "tiny_sweep2", "tiny_video_sst"])
+def test_fused_training_tail_matches_unfused_block_loop(name, monkeypatch):
+    """ZigMa.forward_autograd with the fused block tails (ZIGMA_FUSED_TRAIN_TAIL=1, default) vs the per-op block loop:
+    output and every parameter gradient (fp32)."""
+    from zigma_b200 import ZigMa
+    from oracle.gen_golden import model_io
+    g, cfg, shapes = model_case(name)
+    sd = synth.synth_state_dict(shapes, seed=0)
+    m = ZigMa(device=DEV, **cfg).eval()
+    m.load_state_dict(sd)
+    x, tt, y = model_io(cfg, g["out"].shape[0])
+    target = synth.synth_latents(tuple(g["out"].shape), seed=77).to(DEV)
+    res = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("ZIGMA_FUSED_TRAIN_TAIL", mode)
+        for p_ in m.parameters():
+            p_.grad = None
+        out = m.forward_autograd(x.to(DEV), tt.to(DEV), None if y is None else y.to(DEV))
+        ((out - target) ** 2).mean().backward()
+        res[mode] = (out.detach(), {k: v.grad.clone() for k, v in m.named_parameters() if v.grad is not None})
+    check_close(res["1"][0], res["0"][0], f"{name} fused-tail forward", atol=2e-5)
+    check_close(res["1"][0], g["out"], f"{name} fused-tail forward vs reference golden", atol=2e-5)
+    assert set(res["1"][1]) == set(res["0"][1])
+    for k in res["0"][1]:
+        check_close(res["1"][1][k], res["0"][1][k], f"{name} fused-tail d{k}", atol=2e-5, max_strict_viol=2e-2)

@@ -64,7 +64,14 @@ class BlockTailParams(C.Structure):
     _fields_ = ([(n, vp) for n in ("x", "mix", "gate", "shift", "scale", "norm_w", "residual", "rowmap", "residual_out", "normed", "modded")]
                 + [("mod_rs", i64)]
                 + [(n, i32) for n in ("batch", "seqlen", "dim", "dtype", "final_layer")]
-                + [("eps", f32)])
+                + [("eps", f32), ("rstd", vp)])
+
+
+class BlockTailBwdParams(C.Structure):
+    _fields_ = ([(n, vp) for n in ("d_residual_out", "d_normed", "d_modded", "r", "rstd", "mix", "gate", "scale", "norm_w", "rowmap",
+                                   "d_x", "d_mix", "d_residual_in", "dgate", "dshift", "dscale", "d_norm_w")]
+                + [("mod_rs", i64)]
+                + [(n, i32) for n in ("batch", "seqlen", "dim", "dtype", "nparts")])
 
 
 class GemmParams(C.Structure):
@@ -82,7 +89,7 @@ class AdamWParams(C.Structure):
 
 EXPORTS = ["zg_abi_version", "zg_last_error", "zg_launch_count", "zg_selective_scan_fwd", "zg_selective_scan_bwd",
            "zg_causal_conv1d_fwd", "zg_causal_conv1d_bwd", "zg_add_norm_fwd", "zg_add_norm_bwd",
-           "zg_block_tail_fwd", "zg_gemm_bf16_tn", "zg_adamw_ema_step"]
+           "zg_block_tail_fwd", "zg_block_tail_bwd", "zg_gemm_bf16_tn", "zg_adamw_ema_step"]
 
 _lib = None
 

@@ -396,8 +396,8 @@ __global__ void __launch_bounds__(128) conv_bwd_seqc_vec_kernel(const zg_conv_bw
 constexpr int CONV_BLCH = 64;
 constexpr int CONV_BRB = 4;     // rows per batch of independent loads in the backward (x and dout: 2 * CONV_BRB loads in flight)
 
-template <typename T, int DV>
-__global__ void __launch_bounds__(128, 4) conv_bwd_tok_kernel(const zg_conv_bwd_params q) {
+template <typename T, int DV, int BRB>
+__global__ void __launch_bounds__(128, (DV <= 2) ? 6 : 4) conv_bwd_tok_kernel(const zg_conv_bwd_params q) {
     const zg_conv_params &p = q.fwd;
     const int E = p.dim, L = p.seqlen, W = p.width;
     const int nvec = E / DV;
@@ -439,21 +439,26 @@ __global__ void __launch_bounds__(128, 4) conv_bwd_tok_kernel(const zg_conv_bwd_
         if (l0 >= 3) load_vec<T, DV>(x3, x + rowof(l0 - 3) * p.x_sl);
         const int lend = min(l0 + CONV_BLCH, L);
         const int lhalo = min(lend + 3, L);
-        // positions are walked in batches of CONV_BRB: all 2 * CONV_BRB row loads of a batch are issued before the
-        // first use (ncu round 1, one row at a time: half of the stall samples sat on the first use of a load)
-#pragma unroll 1
-        for (int lb = l0; lb < lend + 3; lb += CONV_BRB) {
-            VecT<T, DV> xr[CONV_BRB], gr[CONV_BRB];
+        // positions are walked in batches of BRB rows, software pipelined: the 2 * BRB row loads of batch k + 1 are issued
+        // before batch k is consumed (a thread's batches are sequential; without the prefetch every batch paid a full
+        // HBM round trip: 60 us per 64-position chunk, ncu round 1)
+        VecT<T, DV> xr[BRB], gr[BRB], xn[BRB], gn[BRB];
+        auto fetch = [&](int lb, VecT<T, DV> (&xd)[BRB], VecT<T, DV> (&gd)[BRB]) {
 #pragma unroll
-            for (int j = 0; j < CONV_BRB; ++j) {
+            for (int j = 0; j < BRB; ++j) {
                 const int l = lb + j;
                 if (l < lhalo) {
-                    xr[j] = *reinterpret_cast<const VecT<T, DV> *>(x + rowof(l) * p.x_sl);
-                    gr[j] = *reinterpret_cast<const VecT<T, DV> *>(dout + (int64_t)l * q.dout_sl);
+                    xd[j] = *reinterpret_cast<const VecT<T, DV> *>(x + rowof(l) * p.x_sl);
+                    gd[j] = *reinterpret_cast<const VecT<T, DV> *>(dout + (int64_t)l * q.dout_sl);
                 }
             }
+        };
+        fetch(l0, xr, gr);
+#pragma unroll 1
+        for (int lb = l0; lb < lend + 3; lb += BRB) {
+            if (lb + BRB < lend + 3) fetch(lb + BRB, xn, gn);
 #pragma unroll
-            for (int j = 0; j < CONV_BRB; ++j) {
+            for (int j = 0; j < BRB; ++j) {
                 const int l = lb + j;
                 float g0[DV], x0[DV];
                 if (l < lhalo) {
@@ -492,6 +497,8 @@ __global__ void __launch_bounds__(128, 4) conv_bwd_tok_kernel(const zg_conv_bwd_
 #pragma unroll
                 for (int i = 0; i < DV; ++i) { x3[i] = x2[i]; x2[i] = x1[i]; x1[i] = x0[i]; g3[i] = g2[i]; g2[i] = g1[i]; g1[i] = g0[i]; }
             }
+#pragma unroll
+            for (int j = 0; j < BRB; ++j) { xr[j] = xn[j]; gr[j] = gn[j]; }
         }
     }
     // CTA reduction of the weight / bias gradients over the 4 warps
@@ -615,15 +622,21 @@ extern "C" int zg_causal_conv1d_bwd(const zg_conv_bwd_params *qq, void *stream) 
         const uintptr_t al = reinterpret_cast<uintptr_t>(p.x) | reinterpret_cast<uintptr_t>(q.dout) | reinterpret_cast<uintptr_t>(q.dx);
         const int64_t so = p.x_sb | p.x_sl | q.dout_sb | q.dout_sl | q.dx_sb | q.dx_sl;
         const bool vec = (p.dim % 4 == 0) && (al % (4 * esz) == 0) && (so % 4 == 0);
-        const int dv = vec ? 4 : 1;
+        static int brb = -1, dvs = -1;     // tuning knobs: rows per batch of loads (ZG_CONV_BWD_RB), channels per thread (ZG_CONV_BWD_DV = 2 | 4)
+        if (brb < 0) { const char *e = getenv("ZG_CONV_BWD_RB"); brb = e ? atoi(e) : 4; }
+        if (dvs < 0) { const char *e = getenv("ZG_CONV_BWD_DV"); dvs = e ? atoi(e) : 2; }
+        const int dv = vec ? (dvs == 2 ? 2 : 4) : 1;
         const int nvb = (p.dim / dv + 31) / 32;
         const int nchunk = (p.seqlen + zg::CONV_BLCH - 1) / zg::CONV_BLCH;
         const int64_t grid = (int64_t)nvb * (((int64_t)p.batch * nchunk + 3) / 4);
         ZG_REQUIRE(grid <= 0x7fffffffLL, "causal_conv1d_bwd: grid too large");
-#define ZG_CONV_BWD_TOK(TT)                                                                   \
-        do {                                                                                  \
-            if (vec) zg::conv_bwd_tok_kernel<TT, 4><<<(unsigned)grid, 128, 0, s>>>(q);       \
-            else zg::conv_bwd_tok_kernel<TT, 1><<<(unsigned)grid, 128, 0, s>>>(q);           \
+#define ZG_CONV_BWD_TOK(TT)                                                                                  \
+        do {                                                                                                 \
+            if (vec && dvs == 2 && brb == 4) zg::conv_bwd_tok_kernel<TT, 2, 4><<<(unsigned)grid, 128, 0, s>>>(q);      \
+            else if (vec && dvs == 2) zg::conv_bwd_tok_kernel<TT, 2, 8><<<(unsigned)grid, 128, 0, s>>>(q);             \
+            else if (vec && brb == 2) zg::conv_bwd_tok_kernel<TT, 4, 2><<<(unsigned)grid, 128, 0, s>>>(q);             \
+            else if (vec) zg::conv_bwd_tok_kernel<TT, 4, 4><<<(unsigned)grid, 128, 0, s>>>(q);                        \
+            else zg::conv_bwd_tok_kernel<TT, 1, 4><<<(unsigned)grid, 128, 0, s>>>(q);                                \
         } while (0)
         switch (p.dtype) {
             case ZG_F32: ZG_CONV_BWD_TOK(float); break;

@@ -358,6 +358,7 @@ __global__ void __launch_bounds__(128, (MAXQ <= 6) ? 6 : 1) block_tail_kernel(co
         }
     }
     const float rstd = 1.f / sqrtf(zg_warp_sum(sumsq) / D + p.eps);
+    if (p.rstd && lane == 0) p.rstd[row] = rstd;
     float sum2 = 0.f;
 #pragma unroll
     for (int k = 0; k < MAXQ; ++k) {
@@ -426,6 +427,179 @@ template <typename T> static int block_tail_t(const zg_block_tail_params &p, cud
     else block_tail_kernel<T, NORM_MAXQ><<<grid, 128, 0, s>>>(p);
     zg_count_launch();
     return zg_check_launch("block_tail_fwd");
+}
+
+// ------------------------------------------------------------------------------------------------
+// Block tail backward (see include/zigma_b200.h).  A warp walks ROWS_PER_WARP consecutive token rows; lanes own
+// 4-column quads, so the four kinds of column sums (d_norm_w over everything; dgate / dshift / dscale per batch element)
+// stay in registers and are flushed with atomics when the batch element changes and at the end.  Every row operand is
+// read once as raw 8/16-byte vectors; 22 B read + 10 B written per element (bf16), pure HBM streaming.
+constexpr int TAILB_ROWS = 16;
+
+template <typename T, int MAXQ>
+__global__ void __launch_bounds__(128, 3) block_tail_bwd_kernel(const zg_block_tail_bwd_params p) {
+    // per-batch column sums live in shared memory (lane-private slots, no conflicts): keeping all four accumulator sets
+    // in registers cost 212 registers = 8 warps per SM, too few for a streaming kernel
+    extern __shared__ __align__(16) float tailb_smem[];
+    float4 *acc_s = reinterpret_cast<float4 *>(tailb_smem) + (threadIdx.x >> 5) * (3 * MAXQ * 32) + (threadIdx.x & 31);   // [warp][3][MAXQ][32 lanes]
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    const int64_t nrows = (int64_t)p.batch * p.seqlen;
+    const int64_t nstrips = (nrows + TAILB_ROWS - 1) / TAILB_ROWS;
+    const int D = p.dim, nq = D >> 2;
+    const float invD = 1.f / D;
+    const T *nw = reinterpret_cast<const T *>(p.norm_w);
+    float w[MAXQ][4], acc_w[MAXQ][4];
+#pragma unroll
+    for (int k = 0; k < MAXQ; ++k) {
+        const int q = lane + 32 * k;
+        if (q < nq) ld4<T>(nw, 4 * q, w[k]);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc_w[k][i] = 0.f;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) acc_s[(j * MAXQ + k) * 32] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    auto flush_batch = [&](int b) {
+#pragma unroll
+        for (int k = 0; k < MAXQ; ++k) {
+            const int q = lane + 32 * k;
+            if (q < nq) {
+                float *dst[3] = {p.dgate, p.dshift, p.dscale};
+#pragma unroll
+                for (int j = 0; j < 3; ++j) {
+                    const float4 v = acc_s[(j * MAXQ + k) * 32];
+                    if (dst[j]) {
+                        float *o = dst[j] + (int64_t)b * D + 4 * q;
+                        atomicAdd(o, v.x); atomicAdd(o + 1, v.y); atomicAdd(o + 2, v.z); atomicAdd(o + 3, v.w);
+                    }
+                    acc_s[(j * MAXQ + k) * 32] = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            }
+        }
+    };
+    // persistent warps: strips of TAILB_ROWS rows with a grid stride (the d_norm_w partial sums of a warp cover all of them)
+    for (int64_t strip = warp; strip < nstrips; strip += nwarps) {
+    const int64_t row0 = strip * TAILB_ROWS, row1 = min(row0 + TAILB_ROWS, nrows);
+    int cur_b = (int)(row0 / p.seqlen);
+    for (int64_t row = row0; row < row1; ++row) {
+        const int b = (int)(row / p.seqlen), l = (int)(row % p.seqlen);
+        if (b != cur_b) { flush_batch(cur_b); cur_b = b; }
+        const int64_t mrow = (int64_t)b * p.seqlen + (p.rowmap ? p.rowmap[l] : l);
+        const float *r = p.r + row * D;
+        const T *dn = p.d_normed ? reinterpret_cast<const T *>(p.d_normed) + row * D : nullptr;
+        const T *dm = p.d_modded ? reinterpret_cast<const T *>(p.d_modded) + row * D : nullptr;
+        const float *dro = p.d_residual_out ? p.d_residual_out + row * D : nullptr;
+        const T *mix = p.mix ? reinterpret_cast<const T *>(p.mix) + mrow * D : nullptr;
+        const T *gate = p.gate ? reinterpret_cast<const T *>(p.gate) + (int64_t)b * p.mod_rs : nullptr;
+        const T *scale = p.scale ? reinterpret_cast<const T *>(p.scale) + (int64_t)b * p.mod_rs : nullptr;
+        const float rstd = p.rstd[row];
+        // ---- all streaming loads of the row first ----
+        float4 rr[MAXQ];
+        Raw4<T> rdn[MAXQ], rdm[MAXQ], rmx[MAXQ];
+#pragma unroll
+        for (int k = 0; k < MAXQ; ++k) {
+            const int q = lane + 32 * k;
+            if (q < nq) {
+                rr[k] = *reinterpret_cast<const float4 *>(r + 4 * q);
+                if (dn) rdn[k] = ldraw<T>(dn, 4 * q);
+                if (dm) rdm[k] = ldraw<T>(dm, 4 * q);
+                if (mix) rmx[k] = ldraw<T>(mix, 4 * q);
+            }
+        }
+        // ---- dy, per-column sums, c1 = mean(xhat * w * dy)  (xhat = r * rstd is recomputed where needed: registers) ----
+        float dy[MAXQ][4];
+        float c1 = 0.f;
+#pragma unroll
+        for (int k = 0; k < MAXQ; ++k) {
+            const int q = lane + 32 * k;
+            if (q < nq) {
+                const float xh[4] = {rr[k].x * rstd, rr[k].y * rstd, rr[k].z * rstd, rr[k].w * rstd};
+                float a[4] = {0.f, 0.f, 0.f, 0.f};
+                if (dn) cvt4<T>(rdn[k], a);
+                if (dm) {
+                    float sc[4], m[4];
+                    cvt4<T>(rdm[k], m);
+                    ld4<T>(scale, 4 * q, sc);
+                    float4 ash = acc_s[(1 * MAXQ + k) * 32], asc = acc_s[(2 * MAXQ + k) * 32];
+                    float *psh = &ash.x, *psc = &asc.x;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        a[i] = fmaf(m[i], 1.f + sc[i], a[i]);
+                        psh[i] += m[i];
+                        psc[i] = fmaf(m[i], xh[i] * w[k][i], psc[i]);       // d_modded * normed
+                    }
+                    acc_s[(1 * MAXQ + k) * 32] = ash; acc_s[(2 * MAXQ + k) * 32] = asc;
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    dy[k][i] = a[i];
+                    acc_w[k][i] = fmaf(a[i], xh[i], acc_w[k][i]);
+                    c1 = fmaf(xh[i], a[i] * w[k][i], c1);
+                }
+            }
+        }
+        c1 = zg_warp_sum(c1) * invD;
+        // ---- dr, outputs ----
+        float *drin = p.d_residual_in ? p.d_residual_in + row * D : nullptr;
+        T *dx = reinterpret_cast<T *>(p.d_x) + row * D;
+        T *dmix = p.d_mix ? reinterpret_cast<T *>(p.d_mix) + mrow * D : nullptr;
+#pragma unroll
+        for (int k = 0; k < MAXQ; ++k) {
+            const int q = lane + 32 * k;
+            if (q < nq) {
+                const float xh[4] = {rr[k].x * rstd, rr[k].y * rstd, rr[k].z * rstd, rr[k].w * rstd};
+                float dr[4], dh[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) dr[i] = (dy[k][i] * w[k][i] - xh[i] * c1) * rstd;
+                if (dro) {
+                    const float4 t = *reinterpret_cast<const float4 *>(dro + 4 * q);
+                    dr[0] += t.x; dr[1] += t.y; dr[2] += t.z; dr[3] += t.w;
+                }
+                if (drin) st4<float>(drin, 4 * q, dr);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) dh[i] = round_to<T>(dr[i]);
+                st4<T>(dx, 4 * q, dh);
+                if (mix) {
+                    float m[4], g[4], o[4];
+                    cvt4<T>(rmx[k], m);
+                    ld4<T>(gate, 4 * q, g);
+                    float4 ag = acc_s[(0 * MAXQ + k) * 32];
+                    float *pg = &ag.x;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) { o[i] = g[i] * dh[i]; pg[i] = fmaf(dh[i], m[i], pg[i]); }
+                    acc_s[(0 * MAXQ + k) * 32] = ag;
+                    st4<T>(dmix, 4 * q, o);
+                }
+            }
+        }
+    }
+    flush_batch(cur_b);
+    }
+    // d_norm_w: sum over the CTA's 4 warps in shared memory, then ONE plain store per column into this CTA's row of the
+    // (gridDim.x, dim) partials buffer -- atomics from every warp onto the same 640 addresses serialised for ~50 us
+    // (first version, 126 us per call); the caller adds the few hundred partial rows up.
+    if (p.d_norm_w) {
+        __syncthreads();
+        float *red = tailb_smem;                           // [4][4 * 32 * MAXQ]
+#pragma unroll
+        for (int k = 0; k < MAXQ; ++k)
+            *reinterpret_cast<float4 *>(red + (threadIdx.x >> 5) * (128 * MAXQ) + 4 * (lane + 32 * k)) = make_float4(acc_w[k][0], acc_w[k][1], acc_w[k][2], acc_w[k][3]);
+        __syncthreads();
+        for (int c = threadIdx.x; c < D; c += 128)
+            p.d_norm_w[(int64_t)blockIdx.x * D + c] = red[c] + red[128 * MAXQ + c] + red[2 * 128 * MAXQ + c] + red[3 * 128 * MAXQ + c];
+    }
+}
+
+template <typename T> static int block_tail_bwd_t(const zg_block_tail_bwd_params &p, cudaStream_t s) {
+    const unsigned grid = (unsigned)p.nparts;          // persistent: the caller sized the d_norm_w partials buffer
+    // dynamic shared memory: 4 warps x 3 accumulator sets x MAXQ quads x 32 lanes x 16 B  (<= 48 KB for MAXQ <= 8)
+    if (p.dim <= 512) block_tail_bwd_kernel<T, 4><<<grid, 128, 4 * 3 * 4 * 32 * 16, s>>>(p);
+    else if (p.dim <= 640) block_tail_bwd_kernel<T, 5><<<grid, 128, 4 * 3 * 5 * 32 * 16, s>>>(p);
+    else if (p.dim <= 768) block_tail_bwd_kernel<T, 6><<<grid, 128, 4 * 3 * 6 * 32 * 16, s>>>(p);
+    else block_tail_bwd_kernel<T, 8><<<grid, 128, 4 * 3 * 8 * 32 * 16, s>>>(p);
+    zg_count_launch();
+    return zg_check_launch("block_tail_bwd");
 }
 
 template <typename T, typename R> static int norm_fwd_tr(const zg_norm_params &p, cudaStream_t s) {
@@ -522,4 +696,26 @@ extern "C" int zg_block_tail_fwd(const zg_block_tail_params *pp, void *stream) {
         case ZG_BF16: return zg::block_tail_t<__nv_bfloat16>(p, s);
     }
     return zg_set_error("block_tail_fwd: bad dtype %d", p.dtype);
+}
+
+extern "C" int zg_block_tail_bwd(const zg_block_tail_bwd_params *pp, void *stream) {
+    ZG_REQUIRE(pp != nullptr, "block_tail_bwd: null params");
+    const zg_block_tail_bwd_params &p = *pp;
+    ZG_REQUIRE(p.r && p.rstd && p.norm_w && p.d_x, "block_tail_bwd: null tensor pointer");
+    ZG_REQUIRE((p.mix != nullptr) == (p.gate != nullptr) && (p.mix != nullptr) == (p.d_mix != nullptr), "block_tail_bwd: mix, gate and d_mix go together");
+    ZG_REQUIRE(!p.d_modded || p.scale, "block_tail_bwd: d_modded needs scale");
+    ZG_REQUIRE(p.dim > 0 && p.dim % 4 == 0 && p.dim <= 1024, "block_tail_bwd: dim must be a multiple of 4 and <= 1024, got %d", p.dim);
+    ZG_REQUIRE(p.mod_rs % 4 == 0, "block_tail_bwd: modulation row stride must be a multiple of 4");
+    ZG_REQUIRE(p.nparts >= 1 && p.nparts <= 65535, "block_tail_bwd: nparts (rows of the d_norm_w partials buffer = CTAs) must be in [1, 65535]");
+    ZG_REQUIRE(aligned16(p.r) && aligned16(p.d_residual_out) && aligned16(p.d_normed) && aligned16(p.d_modded) && aligned16(p.mix) && aligned16(p.d_x) &&
+                   aligned16(p.d_mix) && aligned16(p.d_residual_in) && aligned16(p.gate) && aligned16(p.scale) && aligned16(p.norm_w),
+               "block_tail_bwd: tensors must be 16-byte aligned");
+    if (p.batch == 0 || p.seqlen == 0) return 0;
+    cudaStream_t s = (cudaStream_t)stream;
+    switch (p.dtype) {
+        case ZG_F32: return zg::block_tail_bwd_t<float>(p, s);
+        case ZG_F16: return zg::block_tail_bwd_t<__half>(p, s);
+        case ZG_BF16: return zg::block_tail_bwd_t<__nv_bfloat16>(p, s);
+    }
+    return zg_set_error("block_tail_bwd: bad dtype %d", p.dtype);
 }

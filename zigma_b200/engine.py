@@ -41,7 +41,7 @@ def _linear(x2d, weight, bias=None):
     return F.linear(x2d, weight, bias)
 
 
-def block_tail(x, mix, gate, shift, scale, norm_w, residual, rowmap, eps, final=False, mod_div=1, want_modded=True):
+def block_tail(x, mix, gate, shift, scale, norm_w, residual, rowmap, eps, final=False, mod_div=1, want_modded=True, want_rstd=False):
     """zg_block_tail_fwd wrapper.  x: (Bt, L, D) contiguous; gate/shift/scale: (Bt // mod_div, D)
     views with a common row stride.  Returns residual_out (fp32), normed, modded."""
     Bt, L, D = x.shape
@@ -69,7 +69,11 @@ def block_tail(x, mix, gate, shift, scale, norm_w, residual, rowmap, eps, final=
     p.mod_rs = rs
     p.batch, p.seqlen, p.dim = Bt, L, D
     p.dtype, p.final_layer, p.eps = _lib.dt(x), int(final), float(eps)
+    rstd = torch.empty((Bt * L,), dtype=torch.float32, device=x.device) if want_rstd else None
+    p.rstd = _lib.ptr(rstd)
     _lib.call("zg_block_tail_fwd", p)
+    if want_rstd:
+        return res_out, normed, modded, rstd
     return res_out, normed, modded
 
 

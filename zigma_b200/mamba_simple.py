@@ -178,7 +178,7 @@ class Mamba(nn.Module):
             hit = cache[key] = (perm, perm.to(torch.int32).contiguous())
         return hit[1]
 
-    def _tok_forward(self, hidden_states):
+    def _tok_forward(self, hidden_states, scan_order=False):
         """Same function as the channel-first branch below for v1 / zigzagN / hilbertN / randomN:
         in_proj -> [gather by perm] -> conv -> x_proj / dt_proj -> scan * silu(z) -> out_proj -> [gather by
         perm_rev], with the two gathers folded into the conv / scan kernels (forward and backward)."""
@@ -194,7 +194,17 @@ class Mamba(nn.Module):
         y = mamba_inner_tok_fn(xz, a["conv1d_weight"], a["conv1d_bias"], a["x_proj_weight"], a["delta_proj_weight"],
                                a["A"], a["D"], a["delta_bias"], None if perm is None else self._rowmap32(perm), batch, seqlen)
         out = F.linear(y, self.out_proj.weight, self.out_proj.bias).view(batch, seqlen, -1)
+        if scan_order:      # the caller folds the un-permutation into its own kernel (block tail)
+            return out, (None if perm_rev is None else self._rowmap32(perm_rev))
         return out if perm_rev is None else permute_along(out, perm_rev, 1)
+
+    def forward_scan_order(self, hidden_states):
+        """(mix, rowmap): ``forward(hidden_states) == mix[:, rowmap]`` (rowmap None = identity).  For the token-major
+        mixers the out_proj result is returned in SCAN order together with the int32 inverse table, so that the gather
+        can be fused downstream; every other scan type returns the finished output."""
+        if self._tok_eligible(hidden_states):
+            return self._tok_forward(hidden_states, scan_order=True)
+        return self.forward(hidden_states), None
 
     def _mamba_inner_forward(self, hidden_states):
         """hidden_states (B, L, D) -> (B, L, D).  mamba_simple.py:274-444."""

@@ -403,9 +403,40 @@ class ZigMa(nn.Module):
             return self._engine.forward(hidden_states, t, y)
         return self.forward_autograd(hidden_states, t, y)
 
+    def _fused_tail_ok(self, hidden_states):
+        """The fused training loop (block_ops.BlockTailFn) covers the configuration every shipped config uses."""
+        import os
+        D = hidden_states.shape[-1]
+        return (hidden_states.is_cuda and self.fused_add_norm and self.residual_in_fp32 and not self.has_text and self.use_pe != 3
+                and not self.use_checkpoint and D % 4 == 0 and D <= 1024 and hidden_states.dtype in (torch.float32, torch.bfloat16, torch.float16)
+                and all(isinstance(b.norm, RMSNorm) and b.skip_linear is None and (isinstance(b.drop_path, nn.Identity) or not b.training)
+                        for b in self.blocks)
+                and isinstance(self.norm_f, RMSNorm) and (isinstance(self.drop_path, nn.Identity) or not self.training)
+                and os.environ.get("ZIGMA_FUSED_TRAIN_TAIL", "1") != "0")
+
+    def _forward_fused_tail(self, hidden_states, c):
+        """Same function as the block loop of forward_autograd: each block's add+norm+modulate and the PREVIOUS block's
+        gated residual add + un-permutation run as one kernel (forward and backward)."""
+        from .block_ops import block_tail_fn
+        from .mamba_simple import permute_along
+        residual, mix, gate, rowmap = None, None, None, None
+        x = hidden_states.contiguous()
+        for block in self.blocks:
+            mods = block.adaLN_modulation(c)
+            shift, scale, gate_next = mods.chunk(3, dim=1)
+            residual, x, modded = block_tail_fn(x, mix, gate, shift, scale, block.norm.weight, residual, rowmap, block.norm.eps)
+            mix, rowmap = block.mixer.forward_scan_order(modded)
+            gate = gate_next
+        if rowmap is not None:
+            mix = permute_along(mix, rowmap.long(), 1)
+        return x + gate.unsqueeze(1) * mix, residual
+
     def forward_autograd(self, hidden_states, t, y=None):
         hidden_states, c, y = self.embed(hidden_states, t, y)
         residual = None
+        if self._fused_tail_ok(hidden_states):
+            hidden_states, residual = self._forward_fused_tail(hidden_states, c)
+            return self._forward_head(hidden_states, residual, c)
         for layer_idx, block in enumerate(self.blocks):
             if self.use_pe == 3:
                 hidden_states = hidden_states + self.pos_embed_list[layer_idx]
@@ -414,6 +445,9 @@ class ZigMa(nn.Module):
                     lambda *a: block(*a), hidden_states, residual, c, y, use_reentrant=False)
             else:
                 hidden_states, residual = block(hidden_states, residual=residual, c=c, text=y)
+        return self._forward_head(hidden_states, residual, c)
+
+    def _forward_head(self, hidden_states, residual, c):
         if not self.fused_add_norm:
             residual = hidden_states if residual is None else residual + self.drop_path(hidden_states)
             hidden_states = self.norm_f(residual.to(dtype=self.norm_f.weight.dtype))
