@@ -276,18 +276,21 @@ def test_causal_conv1d_backward_token_major_and_rowmap():
         if hb:
             check_close(b.grad, g["db_" + tag], "conv dbias (token-major) " + tag, rtol=1e-3, atol=1e-4)
     gen = torch.Generator(device=DEV).manual_seed(4)
-    for (bs, E, L, dt) in ((2, 64, 200, torch.float32), (3, 30, 77, torch.float32), (2, 128, 256, torch.bfloat16)):
+    # (the last three shapes take the branch-free 16-bit fast path: whole 32-position chunks; one without a rowmap, one with
+    # a single chunk per row, i.e. no halo at all)
+    for (bs, E, L, dt, use_map) in ((2, 64, 200, torch.float32, True), (3, 30, 77, torch.float32, True), (2, 128, 256, torch.bfloat16, True),
+                                    (3, 96, 96, torch.float16, False), (5, 64, 32, torch.bfloat16, True)):
         x = tm(torch.randn(bs, E, L, device=DEV, generator=gen).to(dt))
         do = tm(torch.randn(bs, E, L, device=DEV, generator=gen).to(dt))
         w = torch.randn(E, 4, device=DEV, generator=gen).to(dt)
         b = torch.randn(E, device=DEV, generator=gen).to(dt)
-        perm = torch.randperm(L, device=DEV, generator=gen)
-        dx, dw, db = _conv_bwd(x, w, b, do, True, x_rowmap=perm.to(torch.int32))
+        perm = torch.randperm(L, device=DEV, generator=gen) if use_map else torch.arange(L, device=DEV)
+        dx, dw, db = _conv_bwd(x, w, b, do, True, x_rowmap=perm.to(torch.int32) if use_map else None)
         xg = x.float()[:, :, perm].contiguous()
         dxr, dwr, dbr = _conv_bwd(xg, w.float(), b.float(), do.float().contiguous(), True)
         want_dx = torch.empty_like(dxr)
         want_dx[:, :, perm] = dxr
-        lo = dt == torch.bfloat16
+        lo = dt != torch.float32
         check_close(dx, want_dx, f"conv dx rowmap {bs}x{E}x{L}", **(dict(rtol=2e-2, atol=2e-2, max_strict_viol=1.0) if lo else {}))
         check_close(dw, dwr, f"conv dweight rowmap {bs}x{E}x{L}", rtol=1e-3, atol=1e-4, max_strict_viol=1.0 if lo else 1e-4)
         check_close(db, dbr, f"conv dbias rowmap {bs}x{E}x{L}", rtol=1e-3, atol=1e-4, max_strict_viol=1.0 if lo else 1e-4)

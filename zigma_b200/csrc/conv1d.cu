@@ -520,6 +520,154 @@ __global__ void __launch_bounds__(128, (DV <= 2) ? 6 : 4) conv_bwd_tok_kernel(co
     }
 }
 
+// backward, token-major FAST path (16-bit I/O, dim % 4 == 0, seqlen % CONV_B4_LCH == 0, aligned): same streaming scheme
+// as conv_bwd_tok_kernel but branch-free -- chunks are whole, the three halo positions either all exist (another chunk
+// follows) or none does, so the per-position bounds tests, the divergent branches and most of the address arithmetic of
+// the generic kernel go away (ncu round 1: 66 issued instructions per channel-position there, ~25 needed), rows are
+// fetched CONV_B4_RB at a time one batch ahead, taps run as packed FFMA2 on channel pairs.
+constexpr int CONV_B4_LCH = 32;
+constexpr int CONV_B4_RB = 4;
+
+template <typename T, bool HAS_MAP>
+__global__ void __launch_bounds__(128, 4) conv_bwd_tok4_kernel(const zg_conv_bwd_params q) {
+    static_assert(sizeof(T) == 2, "16-bit I/O");
+    constexpr int LCH = CONV_B4_LCH, RB = CONV_B4_RB;
+    const zg_conv_params &p = q.fwd;
+    const int E = p.dim, L = p.seqlen, W = p.width;
+    const int nvec = E >> 2;
+    const int nvb = (nvec + 31) >> 5;
+    const int nchunk = L / LCH;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int v = (int)(blockIdx.x % nvb) * 32 + lane;
+    const int64_t row = (int64_t)(blockIdx.x / nvb) * 4 + warp;          // enumerates (batch, chunk)
+    const bool live = v < nvec && row < (int64_t)p.batch * nchunk;
+    __shared__ float red[4][20][32];
+    zg_f2 dw[4][2], db[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        db[h] = zg_splat2(0.f);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) dw[k][h] = zg_splat2(0.f);
+    }
+    const int e0 = v * 4;
+    if (live) {
+        const int b = (int)(row / nchunk), l0 = (int)(row % nchunk) * LCH;
+        const bool halo = l0 + LCH < L;
+        const T *x = reinterpret_cast<const T *>(p.x) + (int64_t)b * p.x_sb + e0;
+        const T *dout = reinterpret_cast<const T *>(q.dout) + (int64_t)b * q.dout_sb + e0;
+        T *dx = reinterpret_cast<T *>(q.dx) + (int64_t)b * q.dx_sb + e0;
+        const int xsl = (int)p.x_sl, gsl = (int)q.dout_sl, dsl = (int)q.dx_sl;
+        const int32_t *rm = p.x_rowmap;
+        zg_f2 w[4][2], bias[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            bias[h].x = p.bias ? load_w_dt(p.bias, e0 + 2 * h, p.wdtype) : 0.f;
+            bias[h].y = p.bias ? load_w_dt(p.bias, e0 + 2 * h + 1, p.wdtype) : 0.f;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {   // w[k] multiplies x[l - k]
+                w[k][h].x = (k < W) ? load_w_dt(p.weight, (int64_t)(e0 + 2 * h) * W + (W - 1 - k), p.wdtype) : 0.f;
+                w[k][h].y = (k < W) ? load_w_dt(p.weight, (int64_t)(e0 + 2 * h + 1) * W + (W - 1 - k), p.wdtype) : 0.f;
+            }
+        }
+        auto xrow = [&](int l) -> const uint2 * { return reinterpret_cast<const uint2 *>(x + (HAS_MAP ? rm[l] : l) * xsl); };
+        auto unpack = [](uint2 r, zg_f2 (&d)[2]) {
+            if (std::is_same<T, __nv_bfloat16>::value) {
+                d[0] = make_float2(__uint_as_float(r.x << 16), __uint_as_float(r.x & 0xffff0000u));
+                d[1] = make_float2(__uint_as_float(r.y << 16), __uint_as_float(r.y & 0xffff0000u));
+            } else {
+                d[0] = __half22float2(*reinterpret_cast<const __half2 *>(&r.x));
+                d[1] = __half22float2(*reinterpret_cast<const __half2 *>(&r.y));
+            }
+        };
+        auto pack = [](const zg_f2 (&o)[2]) -> uint2 {
+            uint2 r;
+            if (std::is_same<T, __nv_bfloat16>::value) {
+                __nv_bfloat162 a = __floats2bfloat162_rn(o[0].x, o[0].y), c = __floats2bfloat162_rn(o[1].x, o[1].y);
+                r.x = *reinterpret_cast<unsigned *>(&a); r.y = *reinterpret_cast<unsigned *>(&c);
+            } else {
+                __half2 a = __floats2half2_rn(o[0].x, o[0].y), c = __floats2half2_rn(o[1].x, o[1].y);
+                r.x = *reinterpret_cast<unsigned *>(&a); r.y = *reinterpret_cast<unsigned *>(&c);
+            }
+            return r;
+        };
+        zg_f2 x1[2], x2[2], x3[2], g1[2], g2[2], g3[2];
+        const uint2 zero = make_uint2(0u, 0u);
+        unpack(l0 >= 1 ? *xrow(l0 - 1) : zero, x1);
+        unpack(l0 >= 2 ? *xrow(l0 - 2) : zero, x2);
+        unpack(l0 >= 3 ? *xrow(l0 - 3) : zero, x3);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) g1[h] = g2[h] = g3[h] = zg_splat2(0.f);
+        // one position: pre-activation, g = dout * silu'(pre), weight-gradient taps, dx of the position three back
+        auto step = [&](uint2 rawx, uint2 rawg, bool acc, bool emit, int m) {
+            zg_f2 x0[2], g0[2], o[2];
+            unpack(rawx, x0);
+            unpack(rawg, g0);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                if (p.silu) {
+                    zg_f2 pre = zg_fma2(w[3][h], x3[h], bias[h]);
+                    pre = zg_fma2(w[2][h], x2[h], pre);
+                    pre = zg_fma2(w[1][h], x1[h], pre);
+                    pre = zg_fma2(w[0][h], x0[h], pre);
+                    const zg_f2 sg = make_float2(zg_sigmoid(pre.x), zg_sigmoid(pre.y));
+                    const zg_f2 one = zg_splat2(1.f);
+                    // silu'(pre) = sg * (1 + pre * (1 - sg))
+                    const zg_f2 t = zg_fma2(pre, zg_fma2(sg, zg_splat2(-1.f), one), one);
+                    g0[h] = zg_mul2(g0[h], zg_mul2(sg, t));
+                }
+                if (acc) {
+                    db[h] = zg_add2(db[h], g0[h]);
+                    dw[0][h] = zg_fma2(g0[h], x0[h], dw[0][h]);
+                    dw[1][h] = zg_fma2(g0[h], x1[h], dw[1][h]);
+                    dw[2][h] = zg_fma2(g0[h], x2[h], dw[2][h]);
+                    dw[3][h] = zg_fma2(g0[h], x3[h], dw[3][h]);
+                }
+                o[h] = zg_fma2(w[0][h], g3[h], zg_fma2(w[1][h], g2[h], zg_fma2(w[2][h], g1[h], zg_mul2(w[3][h], g0[h]))));
+                x3[h] = x2[h]; x2[h] = x1[h]; x1[h] = x0[h]; g3[h] = g2[h]; g2[h] = g1[h]; g1[h] = g0[h];
+            }
+            if (emit) *reinterpret_cast<uint2 *>(dx + (HAS_MAP ? rm[m] : m) * dsl) = pack(o);
+        };
+        uint2 cx[RB], cg[RB], nx[RB], ng[RB];
+#pragma unroll
+        for (int j = 0; j < RB; ++j) { cx[j] = *xrow(l0 + j); cg[j] = *reinterpret_cast<const uint2 *>(dout + (l0 + j) * gsl); }
+#pragma unroll 1
+        for (int lb = l0; lb < l0 + LCH; lb += RB) {
+            const bool more = lb + RB < l0 + LCH;
+            if (more) {
+#pragma unroll
+                for (int j = 0; j < RB; ++j) { nx[j] = *xrow(lb + RB + j); ng[j] = *reinterpret_cast<const uint2 *>(dout + (lb + RB + j) * gsl); }
+            } else if (halo) {
+#pragma unroll
+                for (int j = 0; j < 3; ++j) { nx[j] = *xrow(lb + RB + j); ng[j] = *reinterpret_cast<const uint2 *>(dout + (lb + RB + j) * gsl); }
+            }
+#pragma unroll
+            for (int j = 0; j < RB; ++j) step(cx[j], cg[j], true, lb + j - 3 >= l0, lb + j - 3);
+#pragma unroll
+            for (int j = 0; j < RB; ++j) { cx[j] = nx[j]; cg[j] = ng[j]; }
+        }
+        // the three positions after the chunk: they only feed the chunk's last three dx
+#pragma unroll
+        for (int j = 0; j < 3; ++j) step(halo ? cx[j] : zero, halo ? cg[j] : zero, false, true, l0 + LCH - 3 + j);
+    }
+    // CTA reduction of the weight / bias gradients over the 4 warps (4 chunks of the same channels)
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        red[warp][16 + 2 * h][lane] = db[h].x; red[warp][16 + 2 * h + 1][lane] = db[h].y;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { red[warp][k * 4 + 2 * h][lane] = dw[k][h].x; red[warp][k * 4 + 2 * h + 1][lane] = dw[k][h].y; }
+    }
+    __syncthreads();
+    for (int it = threadIdx.x; it < 20 * 32; it += 128) {
+        const int j = it >> 5, ln = it & 31;
+        const int vv = (int)(blockIdx.x % nvb) * 32 + ln;
+        if (vv >= nvec) continue;
+        const float sum = red[0][j][ln] + red[1][j][ln] + red[2][j][ln] + red[3][j][ln];
+        const int k = j >> 2, i = j & 3, e = vv * 4 + i;
+        if (k == 4) { if (q.dbias) atomicAdd(q.dbias + e, sum); }
+        else if (k < W) atomicAdd(q.dweight + (int64_t)e * W + (W - 1 - k), sum);
+    }
+}
+
 template <typename T> static int conv_fwd_t(const zg_conv_params &p, bool seq, cudaStream_t s) {
     constexpr int VEC = 16 / sizeof(T);
     const uintptr_t align_bits = reinterpret_cast<uintptr_t>(p.x) | reinterpret_cast<uintptr_t>(p.out);
@@ -622,6 +770,23 @@ extern "C" int zg_causal_conv1d_bwd(const zg_conv_bwd_params *qq, void *stream) 
         const uintptr_t al = reinterpret_cast<uintptr_t>(p.x) | reinterpret_cast<uintptr_t>(q.dout) | reinterpret_cast<uintptr_t>(q.dx);
         const int64_t so = p.x_sb | p.x_sl | q.dout_sb | q.dout_sl | q.dx_sb | q.dx_sl;
         const bool vec = (p.dim % 4 == 0) && (al % (4 * esz) == 0) && (so % 4 == 0);
+        static int fast4 = -1;             // ZG_CONV_BWD_FAST=0 disables the branch-free 16-bit kernel
+        if (fast4 < 0) { const char *e = getenv("ZG_CONV_BWD_FAST"); fast4 = e ? atoi(e) : 1; }
+        if (fast4 && esz == 2 && vec && p.seqlen % zg::CONV_B4_LCH == 0 && p.seqlen >= zg::CONV_B4_LCH &&
+            (int64_t)p.seqlen * p.x_sl < 0x7fffffffLL && (int64_t)p.seqlen * q.dout_sl < 0x7fffffffLL && (int64_t)p.seqlen * q.dx_sl < 0x7fffffffLL) {
+            const int nvb4 = (p.dim / 4 + 31) / 32;
+            const int64_t g4 = (int64_t)nvb4 * (((int64_t)p.batch * (p.seqlen / zg::CONV_B4_LCH) + 3) / 4);
+            ZG_REQUIRE(g4 <= 0x7fffffffLL, "causal_conv1d_bwd: grid too large");
+            if (p.dtype == ZG_BF16) {
+                if (p.x_rowmap) zg::conv_bwd_tok4_kernel<__nv_bfloat16, true><<<(unsigned)g4, 128, 0, s>>>(q);
+                else zg::conv_bwd_tok4_kernel<__nv_bfloat16, false><<<(unsigned)g4, 128, 0, s>>>(q);
+            } else {
+                if (p.x_rowmap) zg::conv_bwd_tok4_kernel<__half, true><<<(unsigned)g4, 128, 0, s>>>(q);
+                else zg::conv_bwd_tok4_kernel<__half, false><<<(unsigned)g4, 128, 0, s>>>(q);
+            }
+            zg_count_launch();
+            return zg_check_launch("causal_conv1d_bwd(token-major, fast)");
+        }
         static int brb = -1, dvs = -1;     // tuning knobs: rows per batch of loads (ZG_CONV_BWD_RB), channels per thread (ZG_CONV_BWD_DV = 2 | 4)
         if (brb < 0) { const char *e = getenv("ZG_CONV_BWD_RB"); brb = e ? atoi(e) : 4; }
         if (dvs < 0) { const char *e = getenv("ZG_CONV_BWD_DV"); dvs = e ? atoi(e) : 2; }
