@@ -430,7 +430,7 @@ template <typename T> static int block_tail_t(const zg_block_tail_params &p, cud
 }
 
 // ------------------------------------------------------------------------------------------------
-// Block tail backward (see include/zigma_b200.h).  A warp walks ROWS_PER_WARP consecutive token rows; lanes own
+// Block tail backward (see include/zigma_b200.h).  A warp walks a contiguous range of token rows; lanes own
 // 4-column quads, so the four kinds of column sums (d_norm_w over everything; dgate / dshift / dscale per batch element)
 // stay in registers and are flushed with atomics when the batch element changes and at the end.  Every row operand is
 // read once as raw 8/16-byte vectors; 22 B read + 10 B written per element (bf16), pure HBM streaming.
@@ -446,7 +446,9 @@ __global__ void __launch_bounds__(128, 3) block_tail_bwd_kernel(const zg_block_t
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     const int lane = threadIdx.x & 31;
     const int64_t nrows = (int64_t)p.batch * p.seqlen;
-    const int64_t nstrips = (nrows + TAILB_ROWS - 1) / TAILB_ROWS;
+    // persistent warps, contiguous partition: warp i owns rows [i * per, (i + 1) * per) -- equal work for every warp and at
+    // most one batch boundary inside a range, so the per-batch sums are flushed once or twice per warp
+    const int64_t per = (nrows + nwarps - 1) / nwarps;
     const int D = p.dim, nq = D >> 2;
     const float invD = 1.f / D;
     const T *nw = reinterpret_cast<const T *>(p.norm_w);
@@ -478,9 +480,8 @@ __global__ void __launch_bounds__(128, 3) block_tail_bwd_kernel(const zg_block_t
             }
         }
     };
-    // persistent warps: strips of TAILB_ROWS rows with a grid stride (the d_norm_w partial sums of a warp cover all of them)
-    for (int64_t strip = warp; strip < nstrips; strip += nwarps) {
-    const int64_t row0 = strip * TAILB_ROWS, row1 = min(row0 + TAILB_ROWS, nrows);
+    const int64_t row0 = min(warp * per, nrows), row1 = min(row0 + per, nrows);
+    if (row0 < row1) {
     int cur_b = (int)(row0 / p.seqlen);
     for (int64_t row = row0; row < row1; ++row) {
         const int b = (int)(row / p.seqlen), l = (int)(row % p.seqlen);

@@ -20,7 +20,7 @@ constexpr int TPC2_THREADS = 128;   // 64 channels x 2 threads
 #endif
 
 // NPOLY of each thread's 4 state pairs take exp2 from the FMA-pipe polynomial (zg_ex2_poly2) instead of MUFU
-template <typename T, int NPOLY>
+template <typename T, int NPOLY, bool CKPT = false>
 __global__ void __launch_bounds__(TPC2_THREADS, 9) scan_fwd_tpc2_kernel(const zg_scan_params p) {
     static_assert(sizeof(T) == 2, "16-bit I/O only");
     constexpr int NS = 16, CH = SCAN_CH, TL = SCAN_TL, NSTAGE = 3, VEC = 8;
@@ -62,7 +62,6 @@ __global__ void __launch_bounds__(TPC2_THREADS, 9) scan_fwd_tpc2_kernel(const zg
     const float Dv = p.D ? p.D[e] : 0.f;
     const float bias = p.delta_bias ? p.delta_bias[e] : 0.f;
     const int nstages = L / TL;
-    const bool do_ckpt = p.ckpt != nullptr;      // host side: only with ckpt_every == 8
 
     auto issue_stage = [&](int s) {
         if (s < nstages) {
@@ -141,7 +140,7 @@ __global__ void __launch_bounds__(TPC2_THREADS, 9) scan_fwd_tpc2_kernel(const zg
             float y = (hf ? yp1 : yp0) + recv + Dv * (hf ? u1 : u0);
             if (has_z) y *= zg_silu(zg_to_float<T>(sz[tm * CH]));
             ocol[tm * (int)p.out_sl] = zg_from_float<T>(y);
-            if (do_ckpt && ((t0 + 2) & 7) == 0) {       // recompute seeds for the backward pass: every 8 steps (uniform branch)
+            if (CKPT && ((t0 + 2) & 7) == 0) {   // (compile-time: the sampling instantiation carries no trace of it; host side: ckpt_every == 8)       // recompute seeds for the backward pass: every 8 steps (uniform branch)
                 // (batch, n_ckpt, dim, dstate): the 16 channels x 2 halves of a warp write 1 KB contiguous
                 float4 *dst = reinterpret_cast<float4 *>(p.ckpt + (((int64_t)b * (L >> 3) + ((s * TL + t0 + 2) >> 3) - 1) * E + e) * NS + 8 * hf);
                 dst[0] = make_float4(h2[0].x, h2[0].y, h2[1].x, h2[1].y);
@@ -190,7 +189,8 @@ template <typename T> int try_launch_scan_fwd_tpc2(const zg_scan_params &p, cuda
         }
         kern<<<(unsigned)nblk, TPC2_THREADS, smem, stream>>>(p);
     };
-    if (npoly == 1) launch(scan_fwd_tpc2_kernel<T, 1>);
+    if (p.ckpt) launch(scan_fwd_tpc2_kernel<T, 0, true>);          // training forward (writes the recompute seeds)
+    else if (npoly == 1) launch(scan_fwd_tpc2_kernel<T, 1>);
     else if (npoly == 2) launch(scan_fwd_tpc2_kernel<T, 2>);
     else launch(scan_fwd_tpc2_kernel<T, 0>);
     zg_count_launch();
