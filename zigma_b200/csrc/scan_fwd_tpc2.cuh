@@ -9,6 +9,10 @@
 // the scheduler with ~1.1 eligible warps per cycle and `wait` (fixed-latency dependency) as the top stall.
 // Splitting the states halves the live registers (<= 56) and doubles the resident warps (8.6 per SMSP) for the
 // same total instruction and MUFU count, so the MUFU pipe -- the real bound of this kernel -- stays fed.
+//
+// Tried and rejected (round 1, gpurun call 35): a warp-autonomous variant (every warp stages / converts / consumes its own
+// 8-step tiles, __syncwarp instead of the three block barriers per 16 steps) -- bit-identical results, 0.638 ms instead of
+// 0.557 ms: the extra per-warp staging work and the 4x B/C traffic cost more than the barriers do.
 #pragma once
 #include "scan_fwd.cuh"
 
