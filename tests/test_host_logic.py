@@ -116,3 +116,29 @@ def test_permute_along_matches_advanced_indexing_fwd_and_bwd():
     xr = x.detach().clone().requires_grad_()
     permute_along(x, dup, 2).sum().backward(); xr[:, :, dup].sum().backward()
     assert torch.equal(x.grad, xr.grad)
+
+
+def test_reference_checkpoint_roundtrip(tmp_path):
+    """train_acc.py:492-503 format ({"model", "ema", "opt"}, optionally "module."-prefixed) -> sample_acc.py:70-78 load."""
+    from zigma_b200 import ZigMa
+    from zigma_b200.checkpoint import load_reference_checkpoint, save_reference_checkpoint
+    cfg = dict(img_dim=8, patch_size=1, in_channels=4, embed_dim=32, depth=2, scan_type="zigzagN8", num_classes=-1, has_text=False,
+               use_pe=0, rms_norm=True, fused_add_norm=True, residual_in_fp32=True)
+    torch.manual_seed(0)
+    a, ema, b = ZigMa(device="cpu", **cfg), ZigMa(device="cpu", **cfg), ZigMa(device="cpu", **cfg)
+    with torch.no_grad():
+        for p in ema.parameters():
+            p.add_(0.5)
+    path = str(tmp_path / "0001000.pt")
+    save_reference_checkpoint(path, a, ema_model=ema, opt_state={"state": {}}, args={"note": "x"}, ddp_prefix=True)
+    ck = torch.load(path, map_location="cpu", weights_only=False)
+    assert set(ck) == {"model", "ema", "opt", "args"} and all(k.startswith("module.") for k in ck["ema"])
+    missing, unexpected = load_reference_checkpoint(b, path)                # "ema", like sample_acc.py
+    assert not missing and not unexpected
+    assert all(torch.equal(v, ema.state_dict()[k]) for k, v in b.state_dict().items())
+    load_reference_checkpoint(b, path, which="model")
+    assert all(torch.equal(v, a.state_dict()[k]) for k, v in b.state_dict().items())
+    load_reference_checkpoint(b, ema.state_dict())                           # bare state dict
+    assert torch.equal(b.state_dict()["blocks.0.mixer.A_log"], ema.state_dict()["blocks.0.mixer.A_log"])
+    with pytest.raises(RuntimeError):
+        load_reference_checkpoint(b, {"ema": {"module.nope": torch.zeros(1)}})

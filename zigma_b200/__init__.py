@@ -4,6 +4,8 @@ Public surface mirrors the reference (CompVis/zigma):
     ZigMa, Mamba, selective_scan_fn, mamba_inner_fn, mamba_inner_fn_no_out_proj, bimamba_inner_fn,
     causal_conv1d_fn, rms_norm_fn, layer_norm_fn, RMSNorm, zigzag_path, hilbert_path,
     reverse_permut_np, create_transport, Sampler
+plus what sits around the path on a B200 node: train_step / FlatParams / GradSync / FusedAdamWEMA (zigma_b200.train),
+load_reference_checkpoint / save_reference_checkpoint (zigma_b200.checkpoint).
 All arithmetic on the path runs in libzigma_b200.so (include/zigma_b200.h); there is no CPU fallback.
 """
 from .utils_zigzag import zigzag_path, hilbert_path, reverse_permut_np  # noqa: F401  (pure numpy, always importable)
@@ -18,6 +20,9 @@ def __getattr__(name):
         "mamba_inner_fn_no_out_proj": "selective_scan_interface", "bimamba_inner_fn": "selective_scan_interface",
         "causal_conv1d_fn": "causal_conv1d_interface", "rms_norm_fn": "layernorm", "layer_norm_fn": "layernorm",
         "RMSNorm": "layernorm", "ZigMaEngine": "engine", "create_transport": "transport", "Sampler": "transport",
+        "mamba_inner_tok_fn": "selective_scan_interface", "block_tail_fn": "block_ops",
+        "FlatParams": "train", "GradSync": "train", "FusedAdamWEMA": "train", "train_step": "train",
+        "load_reference_checkpoint": "checkpoint", "save_reference_checkpoint": "checkpoint",
     }
     if name in table:
         return getattr(importlib.import_module("." + table[name], __name__), name)
