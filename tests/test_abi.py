@@ -22,7 +22,8 @@ def _declared():
 def test_header_declares_entry_points():
     names = _declared()
     for n in ("zg_selective_scan_fwd", "zg_selective_scan_bwd", "zg_causal_conv1d_fwd", "zg_causal_conv1d_bwd",
-              "zg_add_norm_fwd", "zg_add_norm_bwd", "zg_block_tail_fwd", "zg_gemm_bf16_tn", "zg_last_error"):
+              "zg_add_norm_fwd", "zg_add_norm_bwd", "zg_block_tail_fwd", "zg_block_tail_bwd", "zg_gemm_bf16_tn",
+              "zg_adamw_ema_step", "zg_last_error"):
         assert n in names
 
 
@@ -44,7 +45,8 @@ def test_ctypes_struct_layout_matches_c():
     structs = {"zg_scan_params": _lib.ScanParams, "zg_scan_bwd_params": _lib.ScanBwdParams,
                "zg_conv_params": _lib.ConvParams, "zg_conv_bwd_params": _lib.ConvBwdParams,
                "zg_norm_params": _lib.NormParams, "zg_norm_bwd_params": _lib.NormBwdParams,
-               "zg_block_tail_params": _lib.BlockTailParams, "zg_gemm_params": _lib.GemmParams}
+               "zg_block_tail_params": _lib.BlockTailParams, "zg_block_tail_bwd_params": _lib.BlockTailBwdParams,
+               "zg_gemm_params": _lib.GemmParams, "zg_adamw_params": _lib.AdamWParams}
     lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{HEADER}"', "int main(void) {"]
     for cname, st in structs.items():
         lines.append(f'printf("{cname} %zu\\n", sizeof({cname}));')
@@ -76,3 +78,6 @@ def test_ops_fail_loudly_without_cuda():
         causal_conv1d_fn(u, torch.randn(4, 3))
     with pytest.raises(RuntimeError):
         rms_norm_fn(torch.randn(2, 8), torch.ones(8), None)
+    from zigma_b200.block_ops import block_tail_fn
+    with pytest.raises(RuntimeError):
+        block_tail_fn(torch.randn(1, 4, 8), None, None, torch.zeros(1, 8), torch.zeros(1, 8), torch.ones(8), None, None, 1e-5)

@@ -26,7 +26,7 @@ int zg_check_launch(const char *what) {
 
 extern "C" {
 
-int zg_abi_version(void) { return 1; }
+int zg_abi_version(void) { return 2; }   // 2: block-tail rstd + backward, AdamW+EMA step, (batch, n_ckpt, dim, dstate) checkpoints
 const char *zg_last_error(void) { return g_err; }
 uint64_t zg_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 

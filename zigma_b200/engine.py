@@ -44,6 +44,7 @@ def _linear(x2d, weight, bias=None):
 def block_tail(x, mix, gate, shift, scale, norm_w, residual, rowmap, eps, final=False, mod_div=1, want_modded=True, want_rstd=False):
     """zg_block_tail_fwd wrapper.  x: (Bt, L, D) contiguous; gate/shift/scale: (Bt // mod_div, D)
     views with a common row stride.  Returns residual_out (fp32), normed, modded."""
+    _lib.require_cuda(x, mix, gate, shift, scale, norm_w, residual, rowmap)
     Bt, L, D = x.shape
     if mod_div != 1:
         # modulation vectors are per ORIGINAL batch element; expand to the folded batch (tiny)
