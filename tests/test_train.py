@@ -91,6 +91,9 @@ def test_fused_adamw_ema_matches_torch():
         coef, norm = opt.clip_coefficient(0.01)
         want = torch.nn.utils.clip_grad_norm_(net.parameters(), 1e9)
         assert torch.allclose(norm, want) and torch.allclose(coef, torch.clamp(0.01 / (want + 1e-6), max=1.0))
+        v0, w0 = em[0].weight._version, net[0].weight._version
+        opt.step()                                           # the raw-pointer update must bump autograd's version counters
+        assert em[0].weight._version > v0 and net[0].weight._version > w0
 
 
 @pytest.mark.gpu

@@ -171,6 +171,13 @@ class FusedAdamWEMA:
         q.bias_correction2 = 1.0 - self.betas[1] ** self.steps
         q.ema_decay, q.grad_scale = self.ema_decay, grad_scale
         _lib.call("zg_adamw_ema_step", q)
+        # the kernel wrote through raw pointers: tell autograd's version counters (every parameter view shares its
+        # buffer's counter), so that saved-tensor checks and the sampling engine's cached packed weights notice
+        torch.autograd.graph.increment_version(self.flat.flat)
+        torch.autograd.graph.increment_version(self.exp_avg)
+        torch.autograd.graph.increment_version(self.exp_avg_sq)
+        if self.ema is not None:
+            torch.autograd.graph.increment_version(self.ema)
 
     def clip_coefficient(self, max_norm, grad_scale=1.0):
         """torch.nn.utils.clip_grad_norm_'s coefficient min(1, max_norm / (||g|| + 1e-6)) as a device scalar, and the norm."""
