@@ -1,3 +1,4 @@
 mkdir -p gpurun_out
-echo "== memcheck"; timeout 1500 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_bwd.py tests/test_gpu_ops.py tests/test_train.py -m gpu -q -x -p no:cacheprovider --timeout=1400 -k "staged or token_major or rowmap or backward or block_tail or fused_training or adamw or add_norm" > gpurun_out/sanitizer_memcheck.log 2>&1; echo "memcheck rc=$?"; grep -E "ERROR SUMMARY|passed|failed|Invalid|out of bounds" gpurun_out/sanitizer_memcheck.log | tail -4
-echo "== racecheck"; timeout 1500 compute-sanitizer --tool racecheck --error-exitcode 9 python -m pytest tests/test_gpu_bwd.py tests/test_gpu_ops.py -m gpu -q -x -p no:cacheprovider --timeout=1400 -k "staged or block_tail_fn or conv1d_backward_token or bwd_golden" > gpurun_out/sanitizer_racecheck.log 2>&1; echo "racecheck rc=$?"; grep -E "RACECHECK SUMMARY|passed|failed|hazard" gpurun_out/sanitizer_racecheck.log | tail -4
+DO_NCU_LIST=1 bash scripts/gpu_round.sh
+python scripts/ncu_list_summary.py gpurun_out/launches.csv > gpurun_out/launch_list.txt 2>&1; tail -15 gpurun_out/launch_list.txt
+timeout 300 python bench.py --impl reference --steps 2 --warmup 1 2> gpurun_out/bench_ref.err | tail -1 | cut -c1-400 | tee gpurun_out/bench_ref.log

@@ -154,6 +154,7 @@ class FusedAdamWEMA:
         self.exp_avg_sq = torch.zeros_like(flat.flat)
         self.ema = flat.flat.clone() if ema else None      # update_ema(ema_model, model, decay=0) (train_acc.py:217-219)
         self.steps = 0
+        self._versioned = [p for _, p in flat.named] + [flat.flat, self.exp_avg, self.exp_avg_sq] + ([self.ema] if ema else [])
 
     def zero_grad(self):
         self.flat.zero_grad()
@@ -171,13 +172,9 @@ class FusedAdamWEMA:
         q.bias_correction2 = 1.0 - self.betas[1] ** self.steps
         q.ema_decay, q.grad_scale = self.ema_decay, grad_scale
         _lib.call("zg_adamw_ema_step", q)
-        # the kernel wrote through raw pointers: tell autograd's version counters (every parameter view shares its
-        # buffer's counter), so that saved-tensor checks and the sampling engine's cached packed weights notice
-        torch.autograd.graph.increment_version(self.flat.flat)
-        torch.autograd.graph.increment_version(self.exp_avg)
-        torch.autograd.graph.increment_version(self.exp_avg_sq)
-        if self.ema is not None:
-            torch.autograd.graph.increment_version(self.ema)
+        # the kernel wrote through raw pointers: bump autograd's version counters (a parameter whose .data was pointed
+        # at a view keeps its OWN counter), so that saved-tensor checks and the sampling engine's cached packed weights notice
+        torch.autograd.graph.increment_version(self._versioned)
 
     def clip_coefficient(self, max_norm, grad_scale=1.0):
         """torch.nn.utils.clip_grad_norm_'s coefficient min(1, max_norm / (||g|| + 1e-6)) as a device scalar, and the norm."""
@@ -198,6 +195,7 @@ class FusedAdamWEMA:
             byname[n].grad = None
         for p in m.parameters():
             p.requires_grad_(False)
+        self._versioned += [byname[n] for n, _ in self.flat.named]      # their storage changes with every step
         return m.eval()
 
 
