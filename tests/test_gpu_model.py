@@ -166,3 +166,31 @@ def test_other_baseline_configs_bf16_batch(name):
     check_close(out[1:2], one, f"{name} bf16 bs=3 vs bs=1", rtol=2e-2, atol=2e-2, scale_atol=False, max_strict_viol=1.0)
     want = _oracle_forward(cfg, sd, x[1:2], tt[1:2], None if y is None else y[1:2])
     check_close(one, want, f"{name} bf16 vs fp32 oracle", rtol=8e-2, atol=8e-2, scale_atol=False, max_strict_viol=1.0)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_has_text_blocks_on_the_engine(dtype):
+    """has_text models (cross-attention branch, 6-way adaLN): the sampling engine -- mixer through
+    the fused kernels, attention branch handed to the fused tail as the "mix" operand -- against the per-op block loop."""
+    from zigma_b200 import ZigMa
+    cfg = dict(img_dim=8, patch_size=1, in_channels=4, embed_dim=64, depth=3, scan_type="zigzagN8", num_classes=-1, has_text=True, d_context=24,
+               use_pe=0, rms_norm=True, fused_add_norm=True, residual_in_fp32=True)
+    torch.manual_seed(0)
+    m = ZigMa(device=DEV, dtype=dtype, **cfg).eval()
+    with torch.no_grad():
+        for p in m.parameters():
+            if p.requires_grad and p.abs().sum() == 0:      # adaLN-zero init would silence both branches
+                p.normal_(0, 0.05)
+    g = torch.Generator(device=DEV).manual_seed(1)
+    x = torch.randn(3, 4, 8, 8, device=DEV, generator=g).to(dtype)
+    t = torch.rand(3, device=DEV, generator=g).to(dtype)
+    ctx_dim = m.y_embedder.in_features if hasattr(m.y_embedder, "in_features") else m.y_embedder[0].in_features
+    y = torch.randn(3, 7, ctx_dim, device=DEV, generator=g).to(dtype)
+    with torch.no_grad():
+        ref = m.forward_autograd(x, t, y)
+        out = m(x, t, y)
+    assert m._engine is not None, "ZigMa.forward did not take the engine"
+    if dtype == torch.float32:
+        check_close(out, ref, "has_text engine vs block loop (fp32)", atol=2e-5)
+    else:
+        check_close(out, ref, "has_text engine vs block loop (bf16)", rtol=5e-2, atol=5e-2, max_strict_viol=1.0)

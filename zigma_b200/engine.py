@@ -187,11 +187,12 @@ class ZigMaEngine:
     # ---- whole forward -----------------------------------------------------------------------------
     def _forward_impl(self, x, t, y):
         m = self.m
-        hs, c, _ = m.embed(x, t, y)
+        hs, c, text = m.embed(x, t, y)
         hs = hs.contiguous()
         B, L, D = hs.shape
         depth = len(self.layers)
-        mods = F.linear(F.silu(c), self.ada_w, self.ada_b).view(B, depth, 3, D)     # shift, scale, gate per block
+        nmod = 6 if m.has_text else 3          # (+ shift, scale, gate of the text cross-attention branch)
+        mods = F.linear(F.silu(c), self.ada_w, self.ada_b).view(B, depth, nmod, D)  # shift, scale, gate per block
         eps = m.blocks[0].norm.eps
         lay0 = self.layers[0]
         residual, normed, modded = block_tail(hs, None, None, mods[:, 0, 0], mods[:, 0, 1], lay0["norm_w"], None, None, eps)
@@ -203,6 +204,17 @@ class ZigMaEngine:
             gate = mods[:, i, 2]
             shift = None if last else mods[:, i + 1, 0]
             scale = None if last else mods[:, i + 1, 1]
+            if m.has_text:
+                # text blocks (model_zigma.py:446-458): the mixer's gated residual has to exist before the cross-attention
+                # reads it; the attention branch (library SDPA on 77 text tokens) then takes the place of the mixer output
+                # in the fused tail:  hidden2 = hidden + gate_msa * msa(modulate(norm_msa(hidden)))
+                blk = m.blocks[i]
+                if fold != 1:
+                    raise NotImplementedError("zigma_b200 engine: has_text together with factorised video scans")
+                mixed = mix if rowmap is None else mix.index_select(1, lay["perm_rev64"])
+                hidden = normed + gate.unsqueeze(1) * mixed
+                q_in = blk.norm_msa(hidden) * (1 + mods[:, i, 4].unsqueeze(1)) + mods[:, i, 3].unsqueeze(1)
+                mix, rowmap, gate, normed = blk.msa(q_in, text=text, mask=None).contiguous(), None, mods[:, i, 5], hidden
             if fold != 1:     # spatial video layer: rows are (b t, k); same memory as (b, t k)
                 Bf = B * fold
                 residual, normed, modded = block_tail(normed.view(Bf, L // fold, D), mix, gate, shift, scale, nw,

@@ -395,7 +395,7 @@ class ZigMa(nn.Module):
     def forward(self, hidden_states, t, y=None):
         """x: (N, C, H, W) latents (video: (N, T, C, H, W)); t: (N,) timesteps; y: (N,) labels."""
         use_engine = (not torch.is_grad_enabled()) and (not self.training) and hidden_states.is_cuda \
-            and self.fused_add_norm and self.residual_in_fp32 and not self.has_text and self.use_pe != 3
+            and self.fused_add_norm and self.residual_in_fp32 and self.use_pe != 3 and not (self.has_text and self.video_frames > 0)
         if use_engine:
             from .engine import ZigMaEngine
             if self._engine is None:
