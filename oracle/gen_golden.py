@@ -77,11 +77,15 @@ SCAN_CASES = [
     ("l1", 1, 8, 1, 16, 1, True, True, True, True),
     ("l16_many", 12, 16, 16, 16, 1, True, True, True, True),   # video temporal shape
     ("n4", 1, 8, 40, 4, 1, True, True, True, True),
+    ("e128_g2_n16", 2, 128, 72, 16, 2, True, True, True, True),   # whole 64-channel tiles, 2 groups: the staged dstate-16 backward
+    ("e96_l45_n16", 2, 96, 45, 16, 1, True, True, True, True),    # partial tile + ragged L: the unstaged dstate-16 backward
 ]
 
 
-def gen_scan(ref):
+def gen_scan(ref, only=None):
     for (name, Bt, E, L, N, G, hasD, hasz, hasb, sp) in SCAN_CASES:
+        if only is not None and name not in only:
+            continue
         print(f"  scan case {name}")
         inp = synth.synth_scan_inputs(Bt, E, L, N, G, seed=1)
         req = {k: v.clone().requires_grad_() for k, v in inp.items()}
@@ -107,6 +111,8 @@ def gen_scan(ref):
         save("scan_" + name, out=out, last_state=last, g=g,
              flags=np.array([Bt, E, L, N, G, hasD, hasz, hasb, sp], dtype=np.int32), **inp, **grads)
 
+    if only is not None:
+        return
     # config 1 of BASELINE.json: B=2 L=1024 D=640 N=16 -- digest only (full output is 5 MB)
     print("  scan case config1 (B=2 L=1024 D=640 N=16)")
     inp = synth.synth_scan_inputs(2, 640, 1024, 16, 1, seed=2)
@@ -272,6 +278,8 @@ def main():
         print(f"== {w}")
         if w.startswith("model:"):
             gen_models(ref, only=w.split(":", 1)[1].split(","))
+        elif w.startswith("scan:"):
+            gen_scan(ref, only=w.split(":", 1)[1].split(","))
         else:
             {"tables": gen_tables, "scan": gen_scan, "conv": gen_conv, "norm": gen_norm,
              "inner": gen_inner, "models": gen_models}[w](ref)

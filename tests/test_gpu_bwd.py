@@ -11,7 +11,7 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda"
 
 
-@pytest.mark.parametrize("name", ["t128_g1", "t131_g2", "e64_n16", "plain", "noz", "l1", "l16_many", "n4"])
+@pytest.mark.parametrize("name", ["t128_g1", "t131_g2", "e64_n16", "plain", "noz", "l1", "l16_many", "n4", "e128_g2_n16", "e96_l45_n16"])
 def test_selective_scan_bwd_golden(name):
     """Gradients of selective_scan_fn vs autograd through the reference's selective_scan_ref
     (test_selective_scan.py:121-149 protocol; tolerances: the north-star rtol 1e-3 with a range-scaled
@@ -31,7 +31,7 @@ def test_selective_scan_bwd_golden(name):
         check_close(req[k].grad, g["d" + k], f"{name} d{k}", atol=1e-4, max_strict_viol=1e-2)
 
 
-@pytest.mark.parametrize("name", ["t128_g1", "t131_g2", "noz"])
+@pytest.mark.parametrize("name", ["t128_g1", "t131_g2", "noz", "e128_g2_n16", "e96_l45_n16"])
 def test_selective_scan_bwd_token_major(name):
     """Same golden gradients with every activation handed over TOKEN-MAJOR ((b, l, d) storage viewed as
     (b, d, l), the engine's layout): the dstate == 16 backward takes the strides as they come."""

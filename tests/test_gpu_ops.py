@@ -10,7 +10,7 @@ from util import check_close, gold, t
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
 
-SCAN = ["t128_g1", "t131_g2", "e64_n16", "plain", "noz", "l1", "l16_many", "n4"]
+SCAN = ["t128_g1", "t131_g2", "e64_n16", "plain", "noz", "l1", "l16_many", "n4", "e128_g2_n16", "e96_l45_n16"]
 
 
 def _scan_args(g, dev=DEV, dtype=None):

@@ -7,7 +7,7 @@ import torch
 from oracle import c_oracle, synth, zigma_oracle as zo
 from util import check_close, gold, model_case, t
 
-SCAN = ["t128_g1", "t131_g2", "e64_n16", "plain", "noz", "l1", "l16_many", "n4"]
+SCAN = ["t128_g1", "t131_g2", "e64_n16", "plain", "noz", "l1", "l16_many", "n4", "e128_g2_n16", "e96_l45_n16"]
 
 
 @pytest.mark.parametrize("name", SCAN)
