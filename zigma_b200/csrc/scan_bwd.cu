@@ -1,7 +1,8 @@
 // Selective-scan (S6) backward for sm_100a -- same mapping as the forward (scan_fwd.cuh): a thread
 // owns one channel, keeps dh / dA partial sums in registers and walks L in reverse, one 8-step chunk
-// at a time (generic fallback: dstate < 16; the dstate == 16 case runs scan_bwd_q4.cuh).  Replaces selective_scan_bwd_kernel (dis_mamba/csrc/selective_scan/
-// selective_scan_bwd_kernel.cuh:75-489): no block-wide reverse scan, no BlockExchange.
+// at a time (generic fallback: dstate < 16; the dstate == 16 case runs scan_bwd_q4.cuh).  Replaces
+// selective_scan_bwd_kernel (dis_mamba/csrc/selective_scan/selective_scan_bwd_kernel.cuh:75-489): no block-wide
+// reverse scan, no BlockExchange.
 //
 // Per chunk: (1) the forward recurrence is recomputed from the checkpoint the forward kernel wrote at
 // the chunk boundary (ckpt_every == 8), parking h_{l-1} of every step in shared memory

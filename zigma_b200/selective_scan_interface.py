@@ -8,6 +8,10 @@ the C-ABI of ``include/zigma_b200.h``; GEMMs that the reference leaves to cuBLAS
 ``@``) stay library GEMMs on this autograd path (the inference fast path in ``engine.py`` uses the
 fused kernels instead).  No CPU / eager fallback exists: without the native library a
 RuntimeError is raised.
+
+Besides the reference surface, ``MambaInnerTokFn`` / ``mamba_inner_tok_fn`` is the token-major training
+core that ``Mamba.forward`` uses (same math as ``MambaInnerFnNoOutProj`` on the permuted sequence; the
+permutation is folded into the conv / scan kernels in both directions).
 """
 import torch
 import torch.nn.functional as F
