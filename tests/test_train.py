@@ -140,3 +140,23 @@ def test_train_step_on_tiny_zigma_matches_unfused_reference_loop():
         torch.manual_seed(3)                                  # a fixed (t, x0): the loss must go down
         fixed.append(train_step(m, tr, opt, None, x1, {"y": None}).item())
     assert fixed[-1] < 0.7 * fixed[0], (fixed[0], fixed[-1])
+
+
+def test_flat_params_and_ema_module_drop_a_stale_engine():
+    """Host logic: a sampling engine cached on the module holds views of the old parameter storage (and CUDA graphs that
+    cannot be deep-copied) -- FlatParams drops it, ema_module() copies around it."""
+    from zigma_b200.train import FlatParams, FusedAdamWEMA
+    net = _net()
+    net._engine = object()
+    flat = FlatParams(net)
+    assert net._engine is None
+
+    class NoCopy:
+        def __deepcopy__(self, memo):
+            raise RuntimeError("engines must not be deep-copied")
+    net._engine = NoCopy()
+    opt = FusedAdamWEMA.__new__(FusedAdamWEMA)            # host-side part only (the step kernel is CUDA)
+    opt.flat, opt.ema, opt._versioned = flat, flat.flat.clone() + 1.0, []
+    em = opt.ema_module()
+    assert isinstance(net._engine, NoCopy) and getattr(em, "_engine", None) is None
+    assert torch.equal(em[0].weight, net[0].weight + 1.0) and not em[0].weight.requires_grad

@@ -55,6 +55,8 @@ class FlatParams:
                 v.copy_(p.data)
                 p.data = v
                 p.grad = self.grad[off:off + p.numel()].view(p.shape)
+        if getattr(module, "_engine", None) is not None:
+            module._engine = None          # a sampling engine built earlier packed views of the OLD parameter storage
 
     def view_of(self, buf, i):
         _, p = self.named[i]
@@ -188,7 +190,15 @@ class FusedAdamWEMA:
     def ema_module(self):
         """A copy of the module whose trainable parameters ARE the EMA buffer (always current, never trained):
         the reference's ``ema_model`` (train_acc.py:210,274,285)."""
-        m = copy.deepcopy(self.flat.module)
+        src = self.flat.module
+        eng = getattr(src, "_engine", None)      # CUDA graphs cannot be deep-copied; the copy builds its own engine on first use
+        if eng is not None:
+            src._engine = None
+        try:
+            m = copy.deepcopy(src)
+        finally:
+            if eng is not None:
+                src._engine = eng
         byname = dict(m.named_parameters())
         for i, (n, _) in enumerate(self.flat.named):
             byname[n].data = self.flat.view_of(self.ema, i)
