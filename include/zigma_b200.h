@@ -66,6 +66,16 @@ uint64_t zg_launch_count(void);
  *   (n_ckpt = ceil(seqlen / ckpt_every); ckpt_every must be a multiple of 8; the backward needs 8) -- the recompute
  *   seeds of the backward pass; plays the role of the reference's `x` (selective_scan.cpp:313).
  * dstate <= 64.
+ *
+ * Fused dt_proj prologue (optional; replaces the separate `delta = dt_proj.weight @ x_dbl[:, :R].t()` GEMM of
+ * selective_scan_interface.py:323 / mamba_simple.py:372-380 and the (batch, dim, seqlen) delta round trip through HBM):
+ * with dt_w != NULL, `delta` is ignored (may be NULL) and the kernel computes, per step,
+ *     delta[b, :, l] = round_to_io_dtype( dt_w (dim, dt_rank) . dt_x[b, l, 0:dt_rank] )      (fp32 accumulate, tensor cores)
+ * before adding delta_bias / softplus, i.e. with the rounding point of the reference's 16-bit GEMM output.
+ * Requirements (else an error is returned): dim-contiguous layout, 16-bit I/O, variable B and C with dstate 16 that live in
+ * the SAME rows as the dt input (B == dt_x + dt_rank, C == dt_x + dt_rank + 16, i.e. the x_dbl rows of x_proj), dt_rank in
+ * {8, 16, ..., 64}, seqlen % 8 == 0, (dim / groups) % 64 == 0, 16-byte aligned rows.  dt_w is in the I/O dtype, row stride
+ * dt_w_ld elements.
  */
 typedef struct {
     const void *u, *delta, *z, *B, *C;
@@ -81,6 +91,9 @@ typedef struct {
     int64_t C_sb, C_sg, C_sn, C_sl;
     int32_t batch, dim, seqlen, dstate, ngroups;
     int32_t dtype, flags, ckpt_every;
+    const void *dt_w, *dt_x;          /* fused dt_proj prologue: weight (dim, dt_rank), input rows (batch, seqlen, >= dt_rank) */
+    int64_t dt_w_ld, dt_x_sb, dt_x_sl;
+    int32_t dt_rank, reserved0;
 } zg_scan_params;
 
 int zg_selective_scan_fwd(const zg_scan_params *p, void *stream);
@@ -88,7 +101,8 @@ int zg_selective_scan_fwd(const zg_scan_params *p, void *stream);
 /* Backward of the above.  Extra inputs: dout (like out), ckpt from the forward.  Outputs: du,
  * ddelta (like u), dz (like z, NULL if no z), dA (dim, dstate), dD, ddelta_bias (dim) fp32
  * ACCUMULATED with atomics -> caller zero-fills (reference: selective_scan.cpp:460-466),
- * dB, dC (batch, groups, dstate, seqlen) fp32 accumulated likewise.  seq-contiguous layout only.
+ * dB, dC (batch, groups, dstate, seqlen) fp32 accumulated likewise.  Both layouts (like the forward); z_rowmap redirects
+ * the z reads and the dz writes.  The fused dt_proj fields of `fwd` must be NULL/0 (the backward takes delta explicitly).
  */
 typedef struct {
     zg_scan_params fwd;
@@ -228,7 +242,7 @@ int zg_block_tail_bwd(const zg_block_tail_bwd_params *p, void *stream);
  * C row-major ldc.  out_rowmap (int32[rows_per_batch] or NULL): output row m of batch
  * m / rows_per_batch is stored at row out_rowmap[m % rows_per_batch] of that batch (scatter of
  * the out_proj result back to raster order, mamba_simple.py:388-394).
- * Requires K % 64 == 0.  The CUtensorMaps are built on the host per call and passed to the
+ * Any M, N, K >= 1 with lda/ldb/ldc multiples of 8 (remainders come from TMA zero fill / clipped stores).  The CUtensorMaps are built on the host per call and passed to the
  * kernel by value (__grid_constant__), so nothing has to outlive the call.
  */
 typedef struct {

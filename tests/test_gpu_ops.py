@@ -133,6 +133,75 @@ def test_selective_scan_z_rowmap_fuses_permutation():
     check_close(out, ref, "scan z_rowmap")
 
 
+def _tok_inputs(Bt, E, L, N, seed, dtype):
+    """Token-major 16-bit scan inputs (rounded first) + their fp32 numpy copies for the C oracle."""
+    inp = synth.synth_scan_inputs(Bt, E, L, N, 1, seed=seed)
+    lo = {k: (v.to(dtype) if k in ("u", "delta", "z", "B", "C") else v) for k, v in inp.items()}
+    f32 = {k: v.float().numpy() for k, v in lo.items()}
+    d = {k: v.to(DEV) for k, v in lo.items()}
+    tm = lambda x: x.transpose(1, 2).contiguous().transpose(1, 2)
+    d["u"], d["delta"], d["z"] = tm(d["u"]), tm(d["delta"]), tm(d["z"])
+    d["B"] = d["B"].transpose(2, 3).contiguous().transpose(2, 3)
+    d["C"] = d["C"].transpose(2, 3).contiguous().transpose(2, 3)
+    return d, f32
+
+
+@pytest.mark.parametrize("dtype,rtol", [(torch.bfloat16, 1.6e-2), (torch.float16, 2e-3)])
+@pytest.mark.parametrize("shape", [(2, 192, 264), (3, 64, 8), (1, 128, 1024)])
+def test_selective_scan_tma_pipeline_kernel(dtype, rtol, shape):
+    """Shapes of the round-2 hot-path kernel (scan_fwd_tma.cuh: token-major, N = 16, L % 8 == 0, E % 64 == 0, 16-bit):
+    bulk-async staging + three-phase stages; with the zigzag z_rowmap, the last state and the backward's checkpoints."""
+    from zigma_b200.selective_scan_interface import _scan_fwd
+    Bt, E, L = shape
+    N = 16
+    d, f32 = _tok_inputs(Bt, E, L, N, 21, dtype)
+    perm = torch.from_numpy(np.random.RandomState(3).permutation(L))
+    ref, ref_last = c_oracle.scan_fwd(f32["u"], f32["delta"], f32["A"], f32["B"], f32["C"], f32["D"],
+                                      np.ascontiguousarray(f32["z"][:, :, perm.numpy()]), f32["delta_bias"], True)
+    out, last, ckpt, _ = _scan_fwd(d["u"], d["delta"], d["A"], d["B"], d["C"], d["D"], d["z"], d["delta_bias"], True,
+                                   z_rowmap=perm.to(DEV).to(torch.int32), want_last_state=True, want_ckpt=True)
+    check_close(out, ref, f"scan tma {dtype} {shape}", rtol=rtol, atol=1e-5, max_strict_viol=1.0)
+    check_close(last, ref_last, f"scan tma {dtype} {shape} last_state", max_strict_viol=1e-3)
+    check_close(ckpt[:, -1], ref_last, f"scan tma {dtype} {shape} last checkpoint", max_strict_viol=1e-3)
+    # no z, no D, no bias, no softplus
+    ref2, _ = c_oracle.scan_fwd(f32["u"], f32["delta"], f32["A"], f32["B"], f32["C"], None, None, None, False)
+    out2, _, _, _ = _scan_fwd(d["u"], d["delta"], d["A"], d["B"], d["C"], None, None, None, False, want_last_state=False)
+    check_close(out2, ref2, f"scan tma {dtype} {shape} plain", rtol=rtol, atol=1e-5, max_strict_viol=1.0)
+
+
+@pytest.mark.parametrize("dtype,rtol", [(torch.bfloat16, 1.6e-2), (torch.float16, 2e-3)])
+@pytest.mark.parametrize("R,E", [(40, 128), (48, 192)])
+def test_selective_scan_fused_dt_proj(dtype, rtol, R, E):
+    """Fused dt_proj prologue (zg_scan_params.dt_w): delta = round(dt_w @ x_dbl[:, :R]) formed inside the scan kernel on the
+    tensor cores, B / C read from the same x_dbl rows (selective_scan_interface.py:322-326 of the reference).  The dt inputs are
+    dyadic rationals, so the fp32 accumulation is exact in any order and delta rounds identically in kernel and oracle."""
+    from zigma_b200.selective_scan_interface import _scan_fwd
+    Bt, L, N = 2, 136, 16
+    d, f32 = _tok_inputs(Bt, E, L, N, 23, dtype)
+    rs = np.random.RandomState(5)
+    xdt = torch.from_numpy(rs.randint(-16, 17, size=(Bt, L, R)).astype(np.float32) / 8)
+    wdt = torch.from_numpy(rs.randint(-8, 9, size=(E, R)).astype(np.float32) / 64)
+    delta = torch.einsum("blr,er->bel", xdt, wdt).to(dtype)                 # exact sums, one rounding
+    x_dbl = torch.cat([xdt, torch.from_numpy(f32["B"][:, 0]).permute(0, 2, 1), torch.from_numpy(f32["C"][:, 0]).permute(0, 2, 1)], dim=2).to(dtype).to(DEV)
+    Bv = x_dbl[:, :, R:R + N].permute(0, 2, 1).unsqueeze(1)
+    Cv = x_dbl[:, :, R + N:].permute(0, 2, 1).unsqueeze(1)
+    perm = torch.from_numpy(np.random.RandomState(4).permutation(L))
+    ref, ref_last = c_oracle.scan_fwd(f32["u"], delta.float().numpy(), f32["A"], f32["B"], f32["C"], f32["D"],
+                                      np.ascontiguousarray(f32["z"][:, :, perm.numpy()]), f32["delta_bias"], True)
+    out, last, _, _ = _scan_fwd(d["u"], None, d["A"], Bv, Cv, d["D"], d["z"], d["delta_bias"], True, z_rowmap=perm.to(DEV).to(torch.int32),
+                                want_last_state=True, dt_proj=(wdt.to(dtype).to(DEV), x_dbl))
+    check_close(out, ref, f"scan fused dt_proj {dtype} R={R}", rtol=rtol, atol=1e-5, max_strict_viol=1.0)
+    check_close(last, ref_last, f"scan fused dt_proj {dtype} R={R} last_state", max_strict_viol=1e-3)
+    # same result as the two-kernel route (GEMM, then scan on the materialised delta), bit for bit
+    d_log = delta.to(DEV).transpose(1, 2).contiguous().transpose(1, 2)
+    out_u, _, _, _ = _scan_fwd(d["u"], d_log, d["A"], Bv, Cv, d["D"], d["z"], d["delta_bias"], True, z_rowmap=perm.to(DEV).to(torch.int32), want_last_state=False)
+    assert torch.equal(out, out_u)
+    # a request that does not fit the prologue is an error, not a silent fallback
+    with pytest.raises(RuntimeError):
+        _scan_fwd(d["u"][:, :, :12], None, d["A"], Bv[..., :12], Cv[..., :12], d["D"], d["z"][:, :, :12], d["delta_bias"], True,
+                  dt_proj=(wdt.to(dtype).to(DEV), x_dbl[:, :12]))
+
+
 def test_selective_scan_properties_full_size():
     """BASELINE config-2 layer shape (bs=64, E=1280, L=1024, N=16, bf16, token-major): too big for
     the CPU oracle in seconds, so size-independent properties instead:

@@ -48,8 +48,25 @@ def check_close(actual, expected, what, rtol=RTOL, atol=ATOL, scale_atol=True, m
     msg = (f"{what}: max|diff|={diff.max().item() if e.numel() else 0:.3e} max|ref|={emax:.3e} "
            f"viol(hard)={int(bad.sum())}/{e.numel()} strict_viol_frac={strict:.2e}")
     print("   ", msg)
+    _log_parity(what, diff.max().item() if e.numel() else 0.0, emax, strict, int(bad.sum()), e.numel(), rtol, atol, max_strict_viol)
     assert not bad.any(), msg
     assert strict <= max_strict_viol, msg + f" (strict fraction > {max_strict_viol})"
+
+
+def _log_parity(what, max_diff, max_ref, strict, hard_viol, numel, rtol, atol, max_strict_viol):
+    """Appends the achieved error of every check to gpurun_out/parity_log.jsonl (GPU runs only), so the numbers behind
+    "N passed" survive the run; scripts/parity_summary.py condenses the file into profiles/."""
+    if not torch.cuda.is_available():
+        return
+    try:
+        d = os.path.join(ROOT, "gpurun_out")
+        os.makedirs(d, exist_ok=True)
+        rec = dict(test=os.environ.get("PYTEST_CURRENT_TEST", "").split(" ")[0], what=what, max_diff=max_diff, max_ref=max_ref,
+                   strict_viol_frac=strict, hard_viol=hard_viol, numel=numel, rtol=rtol, atol=atol, max_strict_viol=max_strict_viol)
+        with open(os.path.join(d, "parity_log.jsonl"), "a") as f:
+            f.write(json.dumps(rec) + "\n")
+    except OSError:
+        pass
 
 
 def model_case(name):

@@ -22,7 +22,10 @@ class ScanParams(C.Structure):
     _fields_ = ([(n, vp) for n in ("u", "delta", "z", "B", "C", "A", "D", "delta_bias", "z_rowmap", "out", "last_state", "ckpt")]
                 + [(n, i64) for n in ("u_sb", "u_sd", "u_sl", "delta_sb", "delta_sd", "delta_sl", "z_sb", "z_sd", "z_sl",
                                       "out_sb", "out_sd", "out_sl", "B_sb", "B_sg", "B_sn", "B_sl", "C_sb", "C_sg", "C_sn", "C_sl")]
-                + [(n, i32) for n in ("batch", "dim", "seqlen", "dstate", "ngroups", "dtype", "flags", "ckpt_every")])
+                + [(n, i32) for n in ("batch", "dim", "seqlen", "dstate", "ngroups", "dtype", "flags", "ckpt_every")]
+                + [(n, vp) for n in ("dt_w", "dt_x")]
+                + [(n, i64) for n in ("dt_w_ld", "dt_x_sb", "dt_x_sl")]
+                + [(n, i32) for n in ("dt_rank", "reserved0")])
 
 
 class ScanBwdParams(C.Structure):

@@ -26,7 +26,8 @@ int zg_check_launch(const char *what) {
 
 extern "C" {
 
-int zg_abi_version(void) { return 2; }   // 2: block-tail rstd + backward, AdamW+EMA step, (batch, n_ckpt, dim, dstate) checkpoints
+int zg_abi_version(void) { return 3; }   // 3: fused dt_proj prologue fields in zg_scan_params
+// int zg_abi_version(void) { return 2; }   // 2: block-tail rstd + backward, AdamW+EMA step, (batch, n_ckpt, dim, dstate) checkpoints
 const char *zg_last_error(void) { return g_err; }
 uint64_t zg_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
@@ -37,9 +38,11 @@ int zg_selective_scan_fwd(const zg_scan_params *pp, void *stream) {
     ZG_REQUIRE(p.batch >= 0 && p.dim > 0 && p.seqlen >= 0, "selective_scan_fwd: bad shape (%d, %d, %d)", p.batch, p.dim, p.seqlen);
     ZG_REQUIRE(p.dstate >= 1 && p.dstate <= 64, "selective_scan_fwd: dstate must be in [1, 64], got %d", p.dstate);
     ZG_REQUIRE(p.ngroups >= 1 && p.dim % p.ngroups == 0, "selective_scan_fwd: dim %d not divisible by groups %d", p.dim, p.ngroups);
-    ZG_REQUIRE(p.u && p.delta && p.A && p.B && p.C && p.out, "selective_scan_fwd: null tensor pointer");
-    const bool seq = p.u_sl == 1 && p.delta_sl == 1 && p.out_sl == 1 && (!p.z || p.z_sl == 1);
-    const bool dimc = p.u_sd == 1 && p.delta_sd == 1 && p.out_sd == 1 && (!p.z || p.z_sd == 1);
+    const bool fused_dt = p.dt_w != nullptr;
+    ZG_REQUIRE(p.u && (p.delta || fused_dt) && p.A && p.B && p.C && p.out, "selective_scan_fwd: null tensor pointer");
+    ZG_REQUIRE(!fused_dt || (p.dt_x && p.dt_rank > 0), "selective_scan_fwd: fused dt_proj prologue needs dt_x and dt_rank");
+    const bool seq = !fused_dt && p.u_sl == 1 && p.delta_sl == 1 && p.out_sl == 1 && (!p.z || p.z_sl == 1);
+    const bool dimc = p.u_sd == 1 && (fused_dt || p.delta_sd == 1) && p.out_sd == 1 && (!p.z || p.z_sd == 1);
     ZG_REQUIRE(seq || dimc, "selective_scan_fwd: u, delta, z, out must all have seq stride 1 or all have dim stride 1");
     // (seqlen == 1 or dim == 1 tensors satisfy both; prefer the reference layout)
     const bool use_seq = seq;

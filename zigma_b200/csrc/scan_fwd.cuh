@@ -461,15 +461,19 @@ template <typename T, int NS, bool SEQ> int launch_scan_fwd_npoly(const zg_scan_
 }
 
 template <typename T> int try_launch_scan_fwd_tpc2(const zg_scan_params &p, cudaStream_t stream);   // scan_fwd_tpc2.cuh
+template <typename T> int try_launch_scan_fwd_tma(const zg_scan_params &p, cudaStream_t stream);    // scan_fwd_tma.cuh
 
 template <typename T> int dispatch_scan_fwd(const zg_scan_params &p, bool seq, bool constbc, cudaStream_t stream) {
     const int N = p.dstate;
     if constexpr (sizeof(T) == 2) {
-        if (!seq && !constbc) {     // hot-path specialisation (two threads per channel), when the call fits it
-            const int rc = try_launch_scan_fwd_tpc2<T>(p, stream);
+        if (!seq && !constbc) {     // hot-path specialisations, when the call fits them: round 2 (bulk-async pipeline), round 1
+            int rc = try_launch_scan_fwd_tma<T>(p, stream);
+            if (rc >= 0) return rc;
+            rc = try_launch_scan_fwd_tpc2<T>(p, stream);
             if (rc >= 0) return rc;
         }
     }
+    if (p.dt_w) return zg_set_error("selective_scan_fwd: the fused dt_proj prologue needs 16-bit dim-contiguous activations with input-dependent B/C");
 #define ZG_SCAN_CASE(NSV)                                                                   \
     if (N <= NSV) {                                                                         \
         if (seq) return launch_scan_fwd_npoly<T, NSV, true>(p, stream);                     \

@@ -1,0 +1,550 @@
+// Selective-scan forward, round-2 hot path: bulk-async (TMA engine) staging + mbarrier pipeline, three-phase stages,
+// optional fused dt_proj prologue on the tensor cores.
+//
+// Shape class: token-major (dim-contiguous) 16-bit activations, N = 16 states, input-dependent B/C, seqlen % 8 == 0,
+// 64-channel tiles -- every ZigMa sampling / training configuration.  Semantics: selective_scan_fwd_kernel.cuh:153-171
+// (delta bias + softplus), :216-261 (the recurrence h = exp(delta A) h + delta u B, y = C h), :280-298 (D skip, SiLU(z)
+// gate) and, for the fused prologue, selective_scan_interface.py:323 (delta = dt_proj.weight @ x_dbl[:, :R].t()).
+//
+// Why a rewrite (round-1 ncu of scan_fwd_tpc2_kernel, profiles/r01_kernels_ncu.txt): 141 issued instructions per
+// (b, e, l) against 48 of state arithmetic and 20 MUFU; issue 59 %, XU 67 %, `mio_throttle` + `wait` on top.  The
+// per-step scalar work (softplus, SiLU, bf16 unpacking, two SHFLs, per-thread LDGSTS address arithmetic, 2-byte stores)
+// sat inside the recurrence loop of every thread.  Here a stage of 8 steps is processed in three phases by the same
+// 128 threads, each phase with the thread mapping that suits it:
+//
+//   producer   warp 0, one instruction per lane: `cp.async.bulk` (SASS UBLKCP) of one 128-byte row each -- the u / delta
+//              / z rows of the stage (z through `z_rowmap`, the zigzag table: a gathered row is just another source
+//              address) and the B/C rows -- into a 3-deep ring; completion is counted on an mbarrier (no LDGSTS address
+//              math, no wait_group, no barrier between copy and use).  Rows land with a 144-byte pitch so that both
+//              the row-wise and the MMA-fragment readers below are bank-conflict free.
+//   pre        lane = channel pair: delta' = softplus(delta + bias) and delta'*u ONCE per (channel, step) with packed
+//              fp32x2 arithmetic, written as fp32 (delta', delta'u) pairs; B/C rows -> fp32.
+//              Fused variant: the delta tile of the stage is a 8(16) x R x 64 tensor-core product (ldmatrix + mma.sync
+//              m16n8k16 / m16n8k8) of the x_dbl rows already staged for B/C with the CTA's dt_proj rows (kept in shared
+//              memory), rounded to the I/O dtype like the reference's GEMM output; the (batch, dim, seqlen) delta tensor
+//              never exists in HBM and the dt_proj GEMM launch disappears.
+//   main       two threads per channel, 8 states (4 fp32x2 pairs) each: per step one LDS.64 (delta', delta'u), four
+//              LDS.128 (B, C), 4 x {FMUL2, 2 MUFU.EX2 | polynomial, FMUL2, FFMA2, FFMA2}, one FADD, one STS -- 34
+//              instructions per thread-step instead of 59.
+//   post       lane = channel pair: y = y_lo + y_hi + D u, SiLU(z) gate, bf16x2 pack, one 128-byte coalesced store
+//              per warp-row.
+//
+// Two __syncthreads per stage (after main, after post+pre); the ring slot of stage s is refilled right after the second
+// one, two stage times before it is needed again.
+#pragma once
+#include "scan_fwd.cuh"
+#include <cuda.h>
+#include <string.h>
+#include <type_traits>
+
+#ifndef ZG_SCAN_TMA_NPOLY_DEFAULT
+#define ZG_SCAN_TMA_NPOLY_DEFAULT 0
+#endif
+
+namespace zg {
+
+constexpr int PT_TL = 8;              // steps per stage
+constexpr int PT_CH = 64;             // channels per CTA
+constexpr int PT_THREADS = 128;
+constexpr int PT_F32ROW = 576;        // smem pitch of one step of the fp32 pair tiles (64 x 8 B + 64: bank shift of 16 words)
+
+__host__ __device__ constexpr int pt_pitch16(int bytes) { return ((bytes / 16) | 1) * 16; }   // odd number of 16-byte units
+
+// PROD: how a stage reaches shared memory.  1 = every row chunk by per-thread cp.async (LDGSTS), rows padded to 144 B;
+// 2 = the dense tensors (u, delta | x_dbl, z without a rowmap) as ONE TMA tensor tile each (cp.async.bulk.tensor, SASS
+// UTMALDG, issued by one thread), the gathered z rows and the unfused B/C rows by cp.async; dense 128-byte rows.
+template <int R, int PROD> struct PtLayout {           // R = dt_rank of the fused prologue, 0 = delta comes from HBM
+    static constexpr bool FUSE = R > 0;
+    static constexpr int NSTAGE = FUSE ? 2 : 3;
+    static constexpr int XBYTES = (R + 32) * 2;                       // one x_dbl row: dt | B | C
+    static constexpr int PT_ROW = PROD == 2 ? 128 : 144;              // pitch of a 64-channel 16-bit row
+    static constexpr int XROW = FUSE ? (PROD == 2 ? XBYTES : pt_pitch16(XBYTES)) : 0;
+    static constexpr int WROW = FUSE ? pt_pitch16(2 * R) : 0;
+    static constexpr int U_OFF = 0;
+    static constexpr int Z_OFF = PT_TL * PT_ROW;
+    static constexpr int D_OFF = 2 * PT_TL * PT_ROW;                  // delta rows | x_dbl rows
+    static constexpr int BC_OFF = D_OFF + PT_TL * PT_ROW;             // unfused only: raw B|C rows, 64 B each
+    static constexpr int STAGE = FUSE ? D_OFF + PT_TL * XROW : BC_OFF + PT_TL * 64;
+    static constexpr int DDU_OFF = NSTAGE * STAGE;
+    static constexpr int Y_OFF = DDU_OFF + PT_TL * PT_F32ROW;
+    static constexpr int BCF_OFF = Y_OFF + PT_TL * PT_F32ROW;
+    static constexpr int W_OFF = BCF_OFF + PT_TL * 32 * 4;
+    static constexpr int BAR_OFF = W_OFF + (FUSE ? PT_CH * WROW : 0);
+    static constexpr int TOTAL = BAR_OFF + NSTAGE * 8;
+};
+
+// 2^x for x <= 0 (two lanes) on the FMA / ALU pipes: see zg_ex2_poly2; only the underflow side needs a clamp here
+__device__ __forceinline__ zg_f2 zg_ex2_poly2_neg(zg_f2 x) {
+    x.x = fmaxf(x.x, -126.f);
+    x.y = fmaxf(x.y, -126.f);
+    const zg_f2 r = zg_add2(x, zg_splat2(12582912.f));
+    const zg_f2 xi = zg_add2(r, zg_splat2(-12582912.f));
+    const zg_f2 f = zg_add2(x, zg_mul2(xi, zg_splat2(-1.f)));
+    zg_f2 p = zg_splat2(0.001327647129073739f);
+    p = zg_fma2(p, f, zg_splat2(0.009675540961325169f));
+    p = zg_fma2(p, f, zg_splat2(0.05550713092088699f));
+    p = zg_fma2(p, f, zg_splat2(0.24022120237350464f));
+    p = zg_fma2(p, f, zg_splat2(0.6931469440460205f));
+    p = zg_fma2(p, f, zg_splat2(1.0000001192092896f));
+    p.x = __int_as_float(__float_as_int(p.x) + (__float_as_int(r.x) << 23));
+    p.y = __int_as_float(__float_as_int(p.y) + (__float_as_int(r.y) << 23));
+    return p;
+}
+
+template <typename T> __device__ __forceinline__ float2 pt_unpack2(uint32_t v);
+template <> __device__ __forceinline__ float2 pt_unpack2<__nv_bfloat16>(uint32_t v) {
+    return make_float2(__uint_as_float(v << 16), __uint_as_float(v & 0xffff0000u));
+}
+template <> __device__ __forceinline__ float2 pt_unpack2<__half>(uint32_t v) {
+    return __half22float2(*reinterpret_cast<const __half2 *>(&v));
+}
+template <typename T> __device__ __forceinline__ uint32_t pt_pack2(float a, float b);
+template <> __device__ __forceinline__ uint32_t pt_pack2<__nv_bfloat16>(float a, float b) {
+    const __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<const uint32_t *>(&v);
+}
+template <> __device__ __forceinline__ uint32_t pt_pack2<__half>(float a, float b) {
+    const __half2 v = __floats2half2_rn(a, b);
+    return *reinterpret_cast<const uint32_t *>(&v);
+}
+
+// softplus of a channel pair (reference threshold 20, selective_scan_fwd_kernel.cuh:153-156); numerics of zg_softplus20
+__device__ __forceinline__ float2 pt_softplus20_2(float2 x) {
+    float2 xm = make_float2(fminf(x.x, 20.f), fminf(x.y, 20.f));
+    xm = zg_mul2(xm, zg_splat2(ZG_LOG2E));
+    const float2 e = make_float2(zg_ex2(xm.x), zg_ex2(xm.y));
+    float2 s = zg_fma2(e, zg_splat2(0.2f), zg_splat2(-0.25f));
+    s = zg_fma2(e, s, zg_splat2(0.33333334f));
+    s = zg_fma2(e, s, zg_splat2(-0.5f));
+    s = zg_fma2(e, s, zg_splat2(1.f));
+    s = zg_mul2(e, s);
+    const float2 w = zg_add2(e, zg_splat2(1.f));
+    const float2 lg = zg_mul2(make_float2(zg_lg2(w.x), zg_lg2(w.y)), zg_splat2(ZG_LN2));
+    float2 r;
+    r.x = (e.x < 0.03125f) ? s.x : lg.x;
+    r.y = (e.y < 0.03125f) ? s.y : lg.y;
+    r.x = (x.x > 20.f) ? x.x : r.x;
+    r.y = (x.y > 20.f) ? x.y : r.y;
+    return r;
+}
+__device__ __forceinline__ float2 pt_silu2(float2 z) {
+    const float2 t = zg_mul2(z, zg_splat2(-ZG_LOG2E));
+    const float2 d = zg_add2(make_float2(zg_ex2(t.x), zg_ex2(t.y)), zg_splat2(1.f));
+    return zg_mul2(z, make_float2(zg_rcp(d.x), zg_rcp(d.y)));
+}
+
+__device__ __forceinline__ void pt_ldmatrix_x4(uint32_t &r0, uint32_t &r1, uint32_t &r2, uint32_t &r3, uint32_t saddr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(saddr));
+}
+__device__ __forceinline__ void pt_ldmatrix_x2(uint32_t &r0, uint32_t &r1, uint32_t saddr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0, %1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(saddr));
+}
+__device__ __forceinline__ void pt_ldmatrix_x1(uint32_t &r0, uint32_t saddr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x1.shared.b16 {%0}, [%1];" : "=r"(r0) : "r"(saddr));
+}
+// D(16x8, fp32) += A(16x16) B(16x8); rows 8..15 of A are zero here (a stage has 8 steps), so only d0, d1 carry data
+template <typename T> __device__ __forceinline__ void pt_mma_k16(float &d0, float &d1, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi) {
+    float d2 = 0.f, d3 = 0.f;
+    const uint32_t zero = 0u;
+    if constexpr (sizeof(T) == 2 && std::is_same<T, __nv_bfloat16>::value) {
+        asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                     : "+f"(d0), "+f"(d1), "+f"(d2), "+f"(d3) : "r"(a_lo), "r"(zero), "r"(a_hi), "r"(zero), "r"(b_lo), "r"(b_hi));
+    } else {
+        asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                     : "+f"(d0), "+f"(d1), "+f"(d2), "+f"(d3) : "r"(a_lo), "r"(zero), "r"(a_hi), "r"(zero), "r"(b_lo), "r"(b_hi));
+    }
+}
+template <typename T> __device__ __forceinline__ void pt_mma_k8(float &d0, float &d1, uint32_t a, uint32_t b) {
+    float d2 = 0.f, d3 = 0.f;
+    const uint32_t zero = 0u;
+    if constexpr (std::is_same<T, __nv_bfloat16>::value) {
+        asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5}, {%6}, {%0, %1, %2, %3};"
+                     : "+f"(d0), "+f"(d1), "+f"(d2), "+f"(d3) : "r"(a), "r"(zero), "r"(b));
+    } else {
+        asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5}, {%6}, {%0, %1, %2, %3};"
+                     : "+f"(d0), "+f"(d1), "+f"(d2), "+f"(d3) : "r"(a), "r"(zero), "r"(b));
+    }
+}
+
+// one stage (8 steps) of the recurrence for this thread's 8 states; NP of its 4 state pairs use the FMA-pipe exp2
+template <int NP>
+__device__ __forceinline__ void pt_main_stage(const unsigned char *ddu_c, const float *bcf_h, float *y_ch, zg_f2 (&h2)[4], const zg_f2 (&Al2p)[4]) {
+#pragma unroll
+    for (int t = 0; t < PT_TL; ++t) {
+        const float2 dd = *reinterpret_cast<const float2 *>(ddu_c + t * PT_F32ROW);      // (delta', delta' * u)
+        const float4 *bc = reinterpret_cast<const float4 *>(bcf_h + t * 32);
+        const float4 B0 = bc[0], B1 = bc[1], C0 = bc[4], C1 = bc[5];
+        const zg_f2 Bp[4] = {make_float2(B0.x, B0.y), make_float2(B0.z, B0.w), make_float2(B1.x, B1.y), make_float2(B1.z, B1.w)};
+        const zg_f2 Cp[4] = {make_float2(C0.x, C0.y), make_float2(C0.z, C0.w), make_float2(C1.x, C1.y), make_float2(C1.z, C1.w)};
+        const zg_f2 dl = zg_splat2(dd.x), du = zg_splat2(dd.y);
+        zg_f2 y2 = zg_splat2(0.f);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const zg_f2 x = zg_mul2(dl, Al2p[q]);
+            const zg_f2 a = (q < NP) ? zg_ex2_poly2_neg(x) : zg_ex2_mufu2(x);
+            h2[q] = zg_fma2(a, h2[q], zg_mul2(du, Bp[q]));
+            y2 = zg_fma2(Cp[q], h2[q], y2);
+        }
+        y_ch[t * (PT_F32ROW / 4)] = y2.x + y2.y;
+    }
+}
+
+struct PtMaps { CUtensorMap u, d, z; };    // (channels | x_dbl columns, seqlen, batch) tensor tiles of u, delta | x_dbl, z
+
+__device__ __forceinline__ void pt_tma_load_3d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(zg_smem_u32(dst)),
+                 "l"(map), "r"(zg_smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
+}
+// the thread's earlier cp.async copies arrive on `bar` when they land (the barrier's expected count includes this arrival)
+__device__ __forceinline__ void pt_cp_async_arrive(uint64_t *bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(zg_smem_u32(bar)) : "memory");
+}
+
+template <typename T, int R, int NPOLY, bool CKPT, int PROD>
+__global__ void __launch_bounds__(PT_THREADS, 9) scan_fwd_tma_kernel(const zg_scan_params p, const __grid_constant__ PtMaps maps) {
+    static_assert(sizeof(T) == 2, "16-bit I/O only");
+    using LY = PtLayout<R, PROD>;
+    constexpr bool FUSE = LY::FUSE;
+    constexpr int NSTAGE = LY::NSTAGE, TL = PT_TL, CH = PT_CH, PT_ROW = LY::PT_ROW;
+    extern __shared__ __align__(1024) unsigned char smem[];
+    unsigned char *ddu = smem + LY::DDU_OFF;
+    unsigned char *ytile = smem + LY::Y_OFF;
+    float *bcf = reinterpret_cast<float *>(smem + LY::BCF_OFF);
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem + LY::BAR_OFF);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int c = tid >> 1, hf = tid & 1;
+    const int E = p.dim, L = p.seqlen;
+    const int per_group = E / p.ngroups;
+    const int tiles_per_group = per_group / CH;
+    const int tiles = tiles_per_group * p.ngroups;
+    const int b = blockIdx.x / tiles;
+    const int tile = blockIdx.x % tiles;
+    const int g = tile / tiles_per_group;
+    const int e0 = g * per_group + (tile % tiles_per_group) * CH;
+    const int e = e0 + c;
+    const bool has_z = p.z != nullptr;
+    const bool z_gather = has_z && (PROD == 1 || p.z_rowmap != nullptr);     // z rows by per-thread cp.async
+    const bool softplus = (p.flags & ZG_SCAN_DELTA_SOFTPLUS) != 0;
+    const int nstages = L / TL;
+
+    // ---- per-thread constants -----------------------------------------------------------------------------------
+    zg_f2 Al2p[4], h2[4];
+    bool a_pos = false;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const float2 a = *reinterpret_cast<const float2 *>(p.A + (int64_t)e * 16 + 8 * hf + 2 * q);
+        Al2p[q] = zg_mul2(a, zg_splat2(ZG_LOG2E));
+        a_pos = a_pos || a.x > 0.f || a.y > 0.f;
+        h2[q] = zg_splat2(0.f);
+    }
+    // row-wise phases: this lane's channel pair (D skip, delta bias)
+    const int cp = e0 + 2 * lane;
+    const float2 Dv = p.D ? *reinterpret_cast<const float2 *>(p.D + cp) : make_float2(0.f, 0.f);
+
+    // full[s]: one arrival per thread and stage (its cp.async copies, possibly none) + the TMA issuer's expect_tx arrival
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < NSTAGE; ++s) zg_mbar_init(&full[s], PT_THREADS + (PROD == 2 ? 1 : 0));
+        zg_mbar_fence_init();
+    }
+    if constexpr (FUSE) {   // this CTA's 64 dt_proj rows -> shared memory (pitch WROW: conflict-free ldmatrix)
+        constexpr int CPR = 2 * R / 16;   // 16-byte chunks per row
+        const T *gw = reinterpret_cast<const T *>(p.dt_w) + (int64_t)e0 * p.dt_w_ld;
+        for (int i = tid; i < CH * CPR; i += PT_THREADS) {
+            const int row = i / CPR, ch = i % CPR;
+            *reinterpret_cast<uint4 *>(smem + LY::W_OFF + row * LY::WROW + ch * 16) =
+                *reinterpret_cast<const uint4 *>(gw + (int64_t)row * p.dt_w_ld + ch * 8);
+        }
+    }
+    // NPOLY > 0 needs delta' A <= 0 (softplus'ed delta, non-positive A) for the one-sided clamp of the polynomial
+    const bool use_poly = NPOLY > 0 && softplus && !__syncthreads_or(a_pos);
+    __syncthreads();
+
+    // ---- producer: every thread moves at most two 16-byte chunks per stage; thread 0 issues the tensor tiles ------
+    constexpr int XC = LY::XBYTES / 16;                   // 16-byte chunks per x_dbl row
+    const int zr = (tid >> 3) & 7, zj = tid & 7;          // threads 64..127: z row / chunk of the stage
+    int zrow_next = zr;                                   // (permuted) source row of the NEXT stage to issue
+    if (z_gather && tid >= 64 && p.z_rowmap) zrow_next = p.z_rowmap[zr];
+    const uint32_t tx_bytes = TL * 128 + (FUSE ? TL * LY::XBYTES : TL * 128) + ((has_z && !z_gather) ? TL * 128 : 0);
+    auto issue_stage = [&](int s) {                       // all threads
+        if (s >= nstages) return;
+        unsigned char *st = smem + (s % NSTAGE) * LY::STAGE;
+        uint64_t *bar = &full[s % NSTAGE];
+        const int l0 = s * TL;
+        if (PROD == 2 && tid == 0) {
+            zg_mbar_expect_tx(bar, tx_bytes);
+            pt_tma_load_3d(st + LY::U_OFF, &maps.u, bar, e0, l0, b);
+            pt_tma_load_3d(st + LY::D_OFF, &maps.d, bar, FUSE ? 0 : e0, l0, b);
+            if (has_z && !z_gather) pt_tma_load_3d(st + LY::Z_OFF, &maps.z, bar, e0, l0, b);
+        }
+        if (tid >= 64) {
+            if (z_gather) {
+                const T *gz = reinterpret_cast<const T *>(p.z) + (int64_t)b * p.z_sb + e0;
+                zg_cp_async16(st + LY::Z_OFF + zr * PT_ROW + zj * 16, gz + (int64_t)zrow_next * p.z_sl + zj * 8);
+                const int ln = l0 + TL + zr;
+                zrow_next = (ln < L) ? (p.z_rowmap ? p.z_rowmap[ln] : ln) : 0;
+            }
+            if (!FUSE && tid < 96) {                      // B | C rows: 8 steps x (2 + 2) chunks
+                const int r = (tid >> 2) & 7, w = (tid >> 1) & 1, j = tid & 1;
+                const T *src = w ? reinterpret_cast<const T *>(p.C) + (int64_t)b * p.C_sb + (int64_t)g * p.C_sg + (int64_t)(l0 + r) * p.C_sl
+                                 : reinterpret_cast<const T *>(p.B) + (int64_t)b * p.B_sb + (int64_t)g * p.B_sg + (int64_t)(l0 + r) * p.B_sl;
+                zg_cp_async16(st + LY::BC_OFF + r * 64 + w * 32 + j * 16, src + j * 8);
+            }
+        } else if (PROD == 1) {
+            const int r = tid >> 3, j = tid & 7;
+            zg_cp_async16(st + LY::U_OFF + r * PT_ROW + j * 16, reinterpret_cast<const T *>(p.u) + (int64_t)b * p.u_sb + e0 + (int64_t)(l0 + r) * p.u_sl + j * 8);
+            if (!FUSE) zg_cp_async16(st + LY::D_OFF + r * PT_ROW + j * 16, reinterpret_cast<const T *>(p.delta) + (int64_t)b * p.delta_sb + e0 + (int64_t)(l0 + r) * p.delta_sl + j * 8);
+        }
+        if (PROD == 1 && FUSE && tid < TL * XC) {
+            const int r = tid / XC, j = tid % XC;
+            zg_cp_async16(st + LY::D_OFF + r * LY::XROW + j * 16, reinterpret_cast<const T *>(p.dt_x) + (int64_t)b * p.dt_x_sb + (int64_t)(l0 + r) * p.dt_x_sl + j * 8);
+        }
+        pt_cp_async_arrive(bar);
+    };
+#pragma unroll
+    for (int s = 0; s < NSTAGE; ++s) issue_stage(s);
+
+    // ---- pre phase: raw stage -> (delta', delta' u) fp32 pairs + fp32 B/C ----------------------------------------
+    float2 biasv = make_float2(0.f, 0.f);                 // unfused: bias of the lane's channel pair
+    float2 biasf[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};   // fused: bias of the two fragment channel pairs
+    if constexpr (FUSE) {
+        if (p.delta_bias) {
+#pragma unroll
+            for (int j = 0; j < 2; ++j) biasf[j] = *reinterpret_cast<const float2 *>(p.delta_bias + e0 + 16 * warp + 8 * j + 2 * (lane & 3));
+        }
+    } else {
+        if (p.delta_bias) biasv = *reinterpret_cast<const float2 *>(p.delta_bias + cp);
+    }
+    auto pre = [&](int s) {
+        const unsigned char *st = smem + (s % NSTAGE) * LY::STAGE;
+        zg_mbar_wait(&full[s % NSTAGE], (uint32_t)((s / NSTAGE) & 1));
+        // B | C rows -> fp32 [step][B0..15 C0..15]: one 16-bit pair per thread
+        {
+            const int t = tid >> 4, j = tid & 15;
+            const uint32_t raw = FUSE ? *reinterpret_cast<const uint32_t *>(st + LY::D_OFF + t * LY::XROW + 2 * R + j * 4)
+                                      : *reinterpret_cast<const uint32_t *>(st + LY::BC_OFF + t * 64 + j * 4);
+            *reinterpret_cast<float2 *>(bcf + t * 32 + 2 * j) = pt_unpack2<T>(raw);
+        }
+        if constexpr (FUSE) {
+            // delta tile = x_dbl[8 steps, 0:R] . W[64 ch, 0:R]^T on the tensor cores; this warp: channels 16 warp .. +15
+            const uint32_t xs = zg_smem_u32(st + LY::D_OFF), ws = zg_smem_u32(smem + LY::W_OFF);
+            const int gq = lane >> 2, q = lane & 3;
+            float d[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+            const uint32_t a_addr = xs + (lane & 7) * LY::XROW + (lane >> 3) * 16;
+            const uint32_t b_addr = ws + (16 * warp + (lane & 7) + 8 * (lane >> 4)) * LY::WROW + ((lane >> 3) & 1) * 16;
+#pragma unroll
+            for (int k2 = 0; k2 < R / 32; ++k2) {           // two k16 steps per iteration
+                uint32_t a0, a1, a2, a3, b0, b1, b2, b3;
+                pt_ldmatrix_x4(a0, a1, a2, a3, a_addr + 64 * k2);
+                pt_ldmatrix_x4(b0, b1, b2, b3, b_addr + 64 * k2);
+                pt_mma_k16<T>(d[0][0], d[0][1], a0, a1, b0, b1);
+                pt_mma_k16<T>(d[1][0], d[1][1], a0, a1, b2, b3);
+                pt_ldmatrix_x4(b0, b1, b2, b3, b_addr + 64 * k2 + 32);
+                pt_mma_k16<T>(d[0][0], d[0][1], a2, a3, b0, b1);
+                pt_mma_k16<T>(d[1][0], d[1][1], a2, a3, b2, b3);
+            }
+            constexpr int KREM = R % 32;                    // 0, 8, 16 or 24 columns left
+            constexpr int KB = (R / 32) * 64;               // their byte offset in a row
+            if constexpr (KREM >= 16) {
+                uint32_t a0, a1, b0, b1, b2, b3;
+                pt_ldmatrix_x2(a0, a1, xs + (lane & 7) * LY::XROW + ((lane >> 3) & 1) * 16 + KB);
+                pt_ldmatrix_x4(b0, b1, b2, b3, b_addr + KB);
+                pt_mma_k16<T>(d[0][0], d[0][1], a0, a1, b0, b1);
+                pt_mma_k16<T>(d[1][0], d[1][1], a0, a1, b2, b3);
+            }
+            if constexpr (KREM % 16 == 8) {
+                constexpr int KB8 = KB + (KREM >= 16 ? 32 : 0);
+                uint32_t a0, b0, b1;
+                pt_ldmatrix_x1(a0, xs + (lane & 7) * LY::XROW + KB8);
+                pt_ldmatrix_x2(b0, b1, ws + (16 * warp + (lane & 7) + 8 * ((lane >> 3) & 1)) * LY::WROW + KB8);
+                pt_mma_k8<T>(d[0][0], d[0][1], a0, b0);
+                pt_mma_k8<T>(d[1][0], d[1][1], a0, b1);
+            }
+            // fragment (step gq, channels 16 warp + 8 j + 2 q, +1): round like the reference's GEMM output, bias, softplus, * u
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const int cj = 16 * warp + 8 * j + 2 * q;
+                float2 dl = zg_add2(pt_unpack2<T>(pt_pack2<T>(d[j][0], d[j][1])), biasf[j]);
+                if (softplus) dl = pt_softplus20_2(dl);
+                const float2 u2 = pt_unpack2<T>(*reinterpret_cast<const uint32_t *>(st + LY::U_OFF + gq * PT_ROW + cj * 2));
+                const float2 du = zg_mul2(dl, u2);
+                *reinterpret_cast<float4 *>(ddu + gq * PT_F32ROW + cj * 8) = make_float4(dl.x, du.x, dl.y, du.y);
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                const int t = warp + 4 * k;
+                float2 dl = zg_add2(pt_unpack2<T>(*reinterpret_cast<const uint32_t *>(st + LY::D_OFF + t * PT_ROW + lane * 4)), biasv);
+                if (softplus) dl = pt_softplus20_2(dl);
+                const float2 u2 = pt_unpack2<T>(*reinterpret_cast<const uint32_t *>(st + LY::U_OFF + t * PT_ROW + lane * 4));
+                const float2 du = zg_mul2(dl, u2);
+                *reinterpret_cast<float4 *>(ddu + t * PT_F32ROW + lane * 16) = make_float4(dl.x, du.x, dl.y, du.y);
+            }
+        }
+    };
+
+    // ---- post phase: y partial sums -> gated output rows -----------------------------------------------------------
+    T *gout = reinterpret_cast<T *>(p.out) + (int64_t)b * p.out_sb + cp;
+    auto post = [&](int s) {
+        const unsigned char *st = smem + (s % NSTAGE) * LY::STAGE;
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const int t = warp + 4 * k;
+            const float4 yy = *reinterpret_cast<const float4 *>(ytile + t * PT_F32ROW + lane * 16);   // (lo, hi) halves of 2 channels
+            const float2 u2 = pt_unpack2<T>(*reinterpret_cast<const uint32_t *>(st + LY::U_OFF + t * PT_ROW + lane * 4));
+            float2 y = zg_fma2(Dv, u2, zg_add2(make_float2(yy.x, yy.z), make_float2(yy.y, yy.w)));
+            if (has_z) y = zg_mul2(y, pt_silu2(pt_unpack2<T>(*reinterpret_cast<const uint32_t *>(st + LY::Z_OFF + t * PT_ROW + lane * 4))));
+            *reinterpret_cast<uint32_t *>(gout + (int64_t)(s * TL + t) * p.out_sl) = pt_pack2<T>(y.x, y.y);
+        }
+    };
+
+    // ---- the pipeline ------------------------------------------------------------------------------------------------
+    const unsigned char *ddu_c = ddu + c * 8;
+    const float *bcf_h = bcf + 8 * hf;
+    float *y_ch = reinterpret_cast<float *>(ytile) + 2 * c + hf;
+    pre(0);
+    __syncthreads();
+    for (int s = 0; s < nstages; ++s) {
+        if (NPOLY > 0 && use_poly) pt_main_stage<NPOLY>(ddu_c, bcf_h, y_ch, h2, Al2p);
+        else pt_main_stage<0>(ddu_c, bcf_h, y_ch, h2, Al2p);
+        if constexpr (CKPT) {       // recompute seeds of the backward: state after every 8 steps, (batch, n_ckpt, dim, dstate)
+            float4 *dst = reinterpret_cast<float4 *>(p.ckpt + (((int64_t)b * (L >> 3) + s) * E + e) * 16 + 8 * hf);
+            dst[0] = make_float4(h2[0].x, h2[0].y, h2[1].x, h2[1].y);
+            dst[1] = make_float4(h2[2].x, h2[2].y, h2[3].x, h2[3].y);
+        }
+        __syncthreads();            // y tile complete; (delta', delta' u) and B/C tiles free
+        post(s);
+        if (s + 1 < nstages) pre(s + 1);
+        __syncthreads();            // raw slot of stage s free; tiles of stage s + 1 complete
+        issue_stage(s + NSTAGE);
+    }
+    if (p.last_state) {
+        float4 *dst = reinterpret_cast<float4 *>(p.last_state + ((int64_t)b * E + e) * 16 + 8 * hf);
+        dst[0] = make_float4(h2[0].x, h2[0].y, h2[1].x, h2[1].y);
+        dst[1] = make_float4(h2[2].x, h2[2].y, h2[3].x, h2[3].y);
+    }
+}
+
+inline int pt_env_int(const char *name, int dflt) {
+    const char *e = getenv(name);
+    return e ? atoi(e) : dflt;
+}
+
+typedef CUresult (*PtEncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                    const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+inline PtEncodeTiledFn pt_get_encode() {
+    static PtEncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PtEncodeTiledFn>(p);
+    }
+    return fn;
+}
+// (cols, seqlen, batch) view of a token-major 16-bit tensor -> tensor map with a (box_cols x 8 steps x 1) box, rows dense in smem
+template <typename T>
+inline int pt_make_map(CUtensorMap *m, const void *base, int64_t cols, int64_t seqlen, int64_t batch, int64_t sl, int64_t sb, int box_cols) {
+    PtEncodeTiledFn enc = pt_get_encode();
+    if (!enc) return zg_set_error("scan_fwd(tma): cuTensorMapEncodeTiled not available from the driver");
+    cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)seqlen, (cuuint64_t)batch};
+    cuuint64_t strides[2] = {(cuuint64_t)sl * 2, (cuuint64_t)(batch > 1 ? sb : sl * seqlen) * 2};
+    cuuint32_t box[3] = {(cuuint32_t)box_cols, (cuuint32_t)PT_TL, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    const CUtensorMapDataType dt = std::is_same<T, __nv_bfloat16>::value ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+    CUresult r = enc(m, dt, 3, const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                     CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return -2;        // not expressible as a tensor map (e.g. stride limits): the caller falls back to PROD 1
+    return 0;
+}
+
+template <typename T, int R, int NPOLY, bool CKPT, int PROD> int pt_launch(const zg_scan_params &p, cudaStream_t stream) {
+    using LY = PtLayout<R, PROD>;
+    PtMaps maps;
+    memset(&maps, 0, sizeof(maps));
+    if (PROD == 2) {
+        int rc = pt_make_map<T>(&maps.u, p.u, p.dim, p.seqlen, p.batch, p.u_sl, p.u_sb, PT_CH);
+        if (!rc) rc = R > 0 ? pt_make_map<T>(&maps.d, p.dt_x, R + 32, p.seqlen, p.batch, p.dt_x_sl, p.dt_x_sb, R + 32)
+                            : pt_make_map<T>(&maps.d, p.delta, p.dim, p.seqlen, p.batch, p.delta_sl, p.delta_sb, PT_CH);
+        if (!rc && p.z && !p.z_rowmap) rc = pt_make_map<T>(&maps.z, p.z, p.dim, p.seqlen, p.batch, p.z_sl, p.z_sb, PT_CH);
+        if (rc == -2) return pt_launch<T, R, NPOLY, CKPT, 1>(p, stream);
+        if (rc) return rc;
+    }
+    auto kern = scan_fwd_tma_kernel<T, R, NPOLY, CKPT, PROD>;
+    static bool attr_set = false;       // per instantiation (the library drives one device per process)
+    if (!attr_set) {
+        cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, LY::TOTAL);
+        if (err != cudaSuccess) return zg_set_error("scan_fwd(tma): cudaFuncSetAttribute(%d B smem): %s", LY::TOTAL, cudaGetErrorString(err));
+        cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        attr_set = true;
+    }
+    const long long nblk = (long long)(p.dim / PT_CH) * p.batch;
+    kern<<<(unsigned)nblk, PT_THREADS, LY::TOTAL, stream>>>(p, maps);
+    zg_count_launch();
+    return zg_check_launch("scan_fwd(tma)");
+}
+
+template <typename T, int R, int PROD> int pt_launch_npoly(const zg_scan_params &p, cudaStream_t stream) {
+    static int npoly = -1;
+    if (npoly < 0) { npoly = pt_env_int("ZG_SCAN_TMA_NPOLY", ZG_SCAN_TMA_NPOLY_DEFAULT); if (npoly < 0 || npoly > 2) npoly = 0; }
+    if (p.ckpt) return pt_launch<T, R, 0, true, PROD>(p, stream);        // training forward (writes the recompute seeds)
+    if (npoly == 1) return pt_launch<T, R, 1, false, PROD>(p, stream);
+    if (npoly == 2) return pt_launch<T, R, 2, false, PROD>(p, stream);
+    return pt_launch<T, R, 0, false, PROD>(p, stream);
+}
+
+template <typename T, int R> int pt_launch_variant(const zg_scan_params &p, cudaStream_t stream) {
+    static int prod = -1;
+    if (prod < 0) { prod = pt_env_int("ZG_SCAN_PROD", 2); if (prod != 1) prod = 2; }
+    return prod == 1 ? pt_launch_npoly<T, R, 1>(p, stream) : pt_launch_npoly<T, R, 2>(p, stream);
+}
+
+// host-side eligibility test + launch; returns -1 when the call does not fit the specialisation (never for a fused request:
+// that one is an error, reported through zg_set_error with a positive return code)
+template <typename T> int try_launch_scan_fwd_tma(const zg_scan_params &p, cudaStream_t stream) {
+    const bool fuse = p.dt_w != nullptr;
+    auto decline = [&](const char *why) -> int {
+        if (fuse) return zg_set_error("selective_scan_fwd: fused dt_proj prologue not applicable: %s", why);
+        return -1;
+    };
+    static int enabled = -1;
+    if (enabled < 0) enabled = pt_env_int("ZG_SCAN_TMA", 1);
+    if (!enabled && !fuse) return -1;
+    if (sizeof(T) != 2) return decline("needs 16-bit I/O");
+    const bool varBC = (p.flags & ZG_SCAN_VARIABLE_B) && (p.flags & ZG_SCAN_VARIABLE_C);
+    if (!varBC || p.dstate != 16) return decline("needs input-dependent B and C with dstate 16");
+    if (p.seqlen % PT_TL != 0 || p.seqlen == 0) return decline("seqlen must be a multiple of 8");
+    if (p.ckpt && p.ckpt_every != 8) return decline("checkpoints every 8 steps only");
+    if ((p.dim / p.ngroups) % PT_CH != 0) return decline("dim / groups must be a multiple of 64");
+    if (!(p.u_sd == 1 && p.out_sd == 1 && (!p.z || p.z_sd == 1) && p.B_sn == 1 && p.C_sn == 1) || (!fuse && p.delta_sd != 1))
+        return decline("needs the dim-contiguous (token-major) layout");
+    uintptr_t al = reinterpret_cast<uintptr_t>(p.u) | reinterpret_cast<uintptr_t>(p.z) | reinterpret_cast<uintptr_t>(p.B) |
+                   reinterpret_cast<uintptr_t>(p.C) | reinterpret_cast<uintptr_t>(p.ckpt) | reinterpret_cast<uintptr_t>(p.last_state);
+    int64_t so = p.u_sb | (p.z ? (p.z_sb | p.z_sl) : 0) | p.B_sb | p.B_sg | p.C_sb | p.C_sg | p.u_sl | p.B_sl | p.C_sl;
+    if (!fuse) { al |= reinterpret_cast<uintptr_t>(p.delta); so |= p.delta_sb | p.delta_sl; }
+    else { al |= reinterpret_cast<uintptr_t>(p.dt_w) | reinterpret_cast<uintptr_t>(p.dt_x); so |= p.dt_w_ld | p.dt_x_sb | p.dt_x_sl; }
+    if (al % 16 != 0 || so % 8 != 0) return decline("rows must be 16-byte aligned");
+    if (reinterpret_cast<uintptr_t>(p.out) % 4 != 0 || (p.out_sb | p.out_sl) % 2 != 0) return decline("output rows must be 4-byte aligned");
+    if ((reinterpret_cast<uintptr_t>(p.A) | reinterpret_cast<uintptr_t>(p.D) | reinterpret_cast<uintptr_t>(p.delta_bias)) % 8 != 0) return decline("A / D / delta_bias must be 8-byte aligned");
+    const int64_t lim = 0x7fffffffLL;   // byte offsets inside one batch element fit 32 bits
+    if ((int64_t)p.seqlen * p.u_sl * 2 > lim || (!fuse && (int64_t)p.seqlen * p.delta_sl * 2 > lim) || (p.z && (int64_t)p.seqlen * p.z_sl * 2 > lim))
+        return decline("batch element too large for 32-bit offsets");
+    if ((long long)(p.dim / PT_CH) * p.batch > 0x7fffffffLL) return decline("grid too large");
+    if (!fuse) return pt_launch_variant<T, 0>(p, stream);
+    // fused prologue: B and C must be the tail of the dt_x rows (the x_dbl rows of x_proj)
+    const T *x = reinterpret_cast<const T *>(p.dt_x);
+    if (p.ngroups != 1 || reinterpret_cast<const T *>(p.B) != x + p.dt_rank || reinterpret_cast<const T *>(p.C) != x + p.dt_rank + 16 ||
+        p.B_sb != p.dt_x_sb || p.C_sb != p.dt_x_sb || p.B_sl != p.dt_x_sl || p.C_sl != p.dt_x_sl)
+        return decline("B and C must be columns dt_rank .. dt_rank + 31 of the dt_x rows (one group)");
+    if ((int64_t)p.seqlen * p.dt_x_sl * 2 > lim) return decline("batch element too large for 32-bit offsets");
+    switch (p.dt_rank) {
+        case 40: return pt_launch_variant<T, 40>(p, stream);
+        case 48: return pt_launch_variant<T, 48>(p, stream);
+        default: return decline("dt_rank must be 40 or 48 in this build (embed_dim 640 / 768)");
+    }
+}
+
+}  // namespace zg

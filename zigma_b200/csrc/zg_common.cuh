@@ -113,3 +113,34 @@ __device__ __forceinline__ float zg_warp_sum(float v) {
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
 }
+
+// ---- mbarrier + bulk async copy (TMA engine, SASS: UBLKCP / SYNCS) -------------------------------------------
+__device__ __forceinline__ uint32_t zg_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void zg_mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(zg_smem_u32(bar)), "r"(count) : "memory");
+}
+// makes the initialised barriers visible to the async proxy (the TMA engine signals them)
+__device__ __forceinline__ void zg_mbar_fence_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void zg_mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(zg_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void zg_mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "ZG_WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra ZG_WAIT_DONE;\n\t"
+        "bra ZG_WAIT_LOOP;\n\t"
+        "ZG_WAIT_DONE:\n\t"
+        "}\n" ::"r"(zg_smem_u32(bar)), "r"(parity) : "memory");
+}
+// global -> shared bulk copy of `bytes` (multiple of 16; both addresses 16-byte aligned), completion counted on `bar`
+__device__ __forceinline__ void zg_bulk_g2s(void *smem_dst, const void *gmem_src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(zg_smem_u32(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"(zg_smem_u32(bar))
+                 : "memory");
+}

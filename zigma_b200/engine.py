@@ -41,6 +41,12 @@ def _linear(x2d, weight, bias=None):
     return F.linear(x2d, weight, bias)
 
 
+def fused_dt_ok(dtype, E, L, N, R, dt_w):
+    """Shape class of the scan kernel's fused dt_proj prologue (include/zigma_b200.h, zg_scan_params.dt_w)."""
+    return (dtype in (torch.bfloat16, torch.float16) and N == 16 and R in (40, 48) and L % 8 == 0 and E % 64 == 0
+            and dt_w.dtype == dtype and dt_w.stride(1) == 1 and dt_w.stride(0) % 8 == 0 and (R + 2 * N) % 8 == 0)
+
+
 def block_tail(x, mix, gate, shift, scale, norm_w, residual, rowmap, eps, final=False, mod_div=1, want_modded=True, want_rstd=False):
     """zg_block_tail_fwd wrapper.  x: (Bt, L, D) contiguous; gate/shift/scale: (Bt // mod_div, D)
     views with a common row stride.  Returns residual_out (fp32), normed, modded."""
@@ -84,6 +90,7 @@ class ZigMaEngine:
         self._versions = None
         self._graphs = {}
         self.use_graph = os.environ.get("ZIGMA_CUDA_GRAPH", "1") != "0"
+        self.fuse_dt = os.environ.get("ZIGMA_FUSE_DT", "1") != "0"
         self.refresh()
 
     # ---- derived, cached tensors ------------------------------------------------------------------
@@ -142,13 +149,18 @@ class ZigMaEngine:
         xc = _conv_fwd(x_log, w["conv_w"], w["conv_b"], True, x_rowmap=rowmap)           # logical (Bt, E, L), token-major memory
         xc_flat = xc.transpose(1, 2).reshape(Bt * L, E)
         x_dbl = _linear(xc_flat, w["x_proj"])                                              # (Bt*L, R + 2N)
-        delta = _linear(x_dbl[:, :R], w["dt_proj"])                                        # (Bt*L, E)
-        d_log = delta.view(Bt, L, E).transpose(1, 2)
         xd3 = x_dbl.view(Bt, L, R + 2 * N)
         B_log = xd3[:, :, R:R + N].permute(0, 2, 1).unsqueeze(1)                           # (Bt, 1, N, L) view
         C_log = xd3[:, :, R + N:].permute(0, 2, 1).unsqueeze(1)
-        y, _, _, _ = _scan_fwd(xc, d_log, w["A"], B_log, C_log, w["D"], z_log, w["dt_bias"], True,
-                               z_rowmap=rowmap, want_last_state=False, want_ckpt=False)
+        if self.fuse_dt and fused_dt_ok(xz.dtype, E, L, N, R, w["dt_proj"]):
+            # dt_proj inside the scan kernel (tensor-core prologue): no delta tensor, no dt_proj GEMM launch
+            y, _, _, _ = _scan_fwd(xc, None, w["A"], B_log, C_log, w["D"], z_log, w["dt_bias"], True,
+                                   z_rowmap=rowmap, want_last_state=False, want_ckpt=False, dt_proj=(w["dt_proj"], xd3))
+        else:
+            delta = _linear(x_dbl[:, :R], w["dt_proj"])                                    # (Bt*L, E)
+            d_log = delta.view(Bt, L, E).transpose(1, 2)
+            y, _, _, _ = _scan_fwd(xc, d_log, w["A"], B_log, C_log, w["D"], z_log, w["dt_bias"], True,
+                                   z_rowmap=rowmap, want_last_state=False, want_ckpt=False)
         return y.transpose(1, 2)                                                            # (Bt, L, E) contiguous
 
     def _mixer(self, modded, lay):

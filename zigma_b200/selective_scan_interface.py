@@ -27,10 +27,14 @@ def _strides3(t):
 
 
 def _scan_fwd(u, delta, A, B, C, D=None, z=None, delta_bias=None, delta_softplus=False,
-              z_rowmap=None, want_last_state=True, want_ckpt=False, out=None):
+              z_rowmap=None, want_last_state=True, want_ckpt=False, out=None, dt_proj=None):
     """Raw forward.  u, delta, z: logical (batch, dim, seqlen) tensors (either memory layout, see
     include/zigma_b200.h); B, C: (batch, groups, dstate, seqlen) variable or (dim, dstate) fp32.
-    Returns (out, last_state | None, ckpt | None).  Mirrors the checks of selective_scan.cpp:238-300."""
+    Returns (out, last_state | None, ckpt | None).  Mirrors the checks of selective_scan.cpp:238-300.
+
+    dt_proj = (dt_weight (dim, R), x_dbl (batch, seqlen, >= R + 2 dstate)) with delta=None: the fused dt_proj prologue --
+    delta = dt_weight @ x_dbl[..., :R] is formed inside the kernel (tensor cores), B and C must be the views
+    x_dbl[..., R:R+N] / x_dbl[..., R+N:R+2N] of the same rows (selective_scan_interface.py:323 of the reference)."""
     _lib.require_cuda(u, delta, A, B, C, D, z, delta_bias)
     if u.dim() != 3:
         raise RuntimeError("selective_scan: u must be (batch, dim, seqlen)")
@@ -38,7 +42,16 @@ def _scan_fwd(u, delta, A, B, C, D=None, z=None, delta_bias=None, delta_softplus
     if A.is_complex():
         raise NotImplementedError("zigma_b200: complex A is not supported (ZigMa never uses it)")
     dstate = A.shape[1]
-    if delta.shape != u.shape or delta.dtype != u.dtype:
+    if dt_proj is not None:
+        if delta is not None:
+            raise RuntimeError("selective_scan: pass either delta or dt_proj, not both")
+        dt_w, dt_x = dt_proj
+        _lib.require_cuda(dt_w, dt_x)
+        if dt_w.dim() != 2 or dt_w.shape[0] != dim or dt_w.dtype != u.dtype or dt_w.stride(1) != 1:
+            raise RuntimeError("selective_scan: dt_proj weight must be (dim, dt_rank) in the dtype of u, rows contiguous")
+        if dt_x.dim() != 3 or dt_x.shape[0] != batch or dt_x.shape[1] != seqlen or dt_x.dtype != u.dtype or dt_x.stride(2) != 1:
+            raise RuntimeError("selective_scan: dt_proj input must be (batch, seqlen, >= dt_rank) rows in the dtype of u")
+    elif delta.shape != u.shape or delta.dtype != u.dtype:
         raise RuntimeError("selective_scan: delta must match u in shape and dtype")
     if A.shape != (dim, dstate) or A.dtype != torch.float32:
         raise RuntimeError("selective_scan: A must be fp32 (dim, dstate)")
@@ -112,7 +125,11 @@ def _scan_fwd(u, delta, A, B, C, D=None, z=None, delta_bias=None, delta_softplus
     p.A, p.D, p.delta_bias, p.z_rowmap = _lib.ptr(A), _lib.ptr(D), _lib.ptr(delta_bias), _lib.ptr(z_rowmap)
     p.out, p.last_state, p.ckpt = _lib.ptr(out), _lib.ptr(last), _lib.ptr(ckpt)
     p.u_sb, p.u_sd, p.u_sl = _strides3(u)
-    p.delta_sb, p.delta_sd, p.delta_sl = _strides3(delta)
+    if delta is not None:
+        p.delta_sb, p.delta_sd, p.delta_sl = _strides3(delta)
+    else:
+        p.dt_w, p.dt_x = _lib.ptr(dt_w), _lib.ptr(dt_x)
+        p.dt_w_ld, p.dt_x_sb, p.dt_x_sl, p.dt_rank = dt_w.stride(0), dt_x.stride(0), dt_x.stride(1), dt_w.shape[1]
     if z is not None:
         p.z_sb, p.z_sd, p.z_sl = _strides3(z)
     p.out_sb, p.out_sd, p.out_sl = _strides3(out)
@@ -168,7 +185,11 @@ def _scan_bwd(saved, ckpt, dout, delta_softplus, dz_out=None, z_rowmap=None):
     p.ckpt = _lib.ptr(ckpt)
     p.z_rowmap = _lib.ptr(z_rowmap)     # z read / dz written in token order (dstate == 16 kernel only)
     p.u_sb, p.u_sd, p.u_sl = _strides3(u)
-    p.delta_sb, p.delta_sd, p.delta_sl = _strides3(delta)
+    if delta is not None:
+        p.delta_sb, p.delta_sd, p.delta_sl = _strides3(delta)
+    else:
+        p.dt_w, p.dt_x = _lib.ptr(dt_w), _lib.ptr(dt_x)
+        p.dt_w_ld, p.dt_x_sb, p.dt_x_sl, p.dt_rank = dt_w.stride(0), dt_x.stride(0), dt_x.stride(1), dt_w.shape[1]
     if z is not None:
         p.z_sb, p.z_sd, p.z_sl = _strides3(z)
     p.B_sb, p.B_sg, p.B_sn, p.B_sl = B.stride()
