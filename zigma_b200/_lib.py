@@ -9,7 +9,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libzigma_b200.so")
+LIB_PATH = os.environ.get("ZIGMA_B200_LIB") or os.path.join(_HERE, "lib", "libzigma_b200.so")   # (override: kernel timing experiments)
 
 ZG_F32, ZG_F16, ZG_BF16 = 0, 1, 2
 SCAN_DELTA_SOFTPLUS, SCAN_VARIABLE_B, SCAN_VARIABLE_C = 1, 2, 4

@@ -1,4 +1,4 @@
-// Selective-scan forward, round-2 hot path: bulk-async (TMA engine) staging + mbarrier pipeline, three-phase stages,
+// Selective-scan forward, round-2 hot path: TMA-staged tiles + mbarrier pipeline, three-phase stages,
 // optional fused dt_proj prologue on the tensor cores.
 //
 // Shape class: token-major (dim-contiguous) 16-bit activations, N = 16 states, input-dependent B/C, seqlen % 8 == 0,
@@ -7,36 +7,40 @@
 // gate) and, for the fused prologue, selective_scan_interface.py:323 (delta = dt_proj.weight @ x_dbl[:, :R].t()).
 //
 // Why a rewrite (round-1 ncu of scan_fwd_tpc2_kernel, profiles/r01_kernels_ncu.txt): 141 issued instructions per
-// (b, e, l) against 48 of state arithmetic and 20 MUFU; issue 59 %, XU 67 %, `mio_throttle` + `wait` on top.  The
-// per-step scalar work (softplus, SiLU, bf16 unpacking, two SHFLs, per-thread LDGSTS address arithmetic, 2-byte stores)
-// sat inside the recurrence loop of every thread.  Here a stage of 8 steps is processed in three phases by the same
-// 128 threads, each phase with the thread mapping that suits it:
+// (b, e, l) against 48 of state arithmetic and 20 MUFU; issue 59 %, XU 67 %.  The per-step scalar work (softplus, SiLU,
+// bf16 unpacking, two SHFLs, per-thread LDGSTS address arithmetic, 2-byte stores) sat inside the recurrence loop of every
+// thread, and three block barriers per 16 steps kept the four warps of a CTA in lock step.  Here:
 //
-//   producer   warp 0, one instruction per lane: `cp.async.bulk` (SASS UBLKCP) of one 128-byte row each -- the u / delta
-//              / z rows of the stage (z through `z_rowmap`, the zigzag table: a gathered row is just another source
-//              address) and the B/C rows -- into a 3-deep ring; completion is counted on an mbarrier (no LDGSTS address
-//              math, no wait_group, no barrier between copy and use).  Rows land with a 144-byte pitch so that both
-//              the row-wise and the MMA-fragment readers below are bank-conflict free.
-//   pre        lane = channel pair: delta' = softplus(delta + bias) and delta'*u ONCE per (channel, step) with packed
-//              fp32x2 arithmetic, written as fp32 (delta', delta'u) pairs; B/C rows -> fp32.
-//              Fused variant: the delta tile of the stage is a 8(16) x R x 64 tensor-core product (ldmatrix + mma.sync
-//              m16n8k16 / m16n8k8) of the x_dbl rows already staged for B/C with the CTA's dt_proj rows (kept in shared
-//              memory), rounded to the I/O dtype like the reference's GEMM output; the (batch, dim, seqlen) delta tensor
-//              never exists in HBM and the dt_proj GEMM launch disappears.
-//   main       two threads per channel, 8 states (4 fp32x2 pairs) each: per step one LDS.64 (delta', delta'u), four
-//              LDS.128 (B, C), 4 x {FMUL2, 2 MUFU.EX2 | polynomial, FMUL2, FFMA2, FFMA2}, one FADD, one STS -- 34
-//              instructions per thread-step instead of 59.
-//   post       lane = channel pair: y = y_lo + y_hi + D u, SiLU(z) gate, bf16x2 pack, one 128-byte coalesced store
-//              per warp-row.
-//
-// Two __syncthreads per stage (after main, after post+pre); the ring slot of stage s is refilled right after the second
-// one, two stage times before it is needed again.
+//   staging    a stage = 8 steps x 64 channels.  The dense tensors (u, delta or the x_dbl rows, z when it is not gathered)
+//              arrive as ONE TMA tensor tile each (cp.async.bulk.tensor.3d, SASS UTMALDG, 128-byte swizzle so that both
+//              the row-wise and the MMA-fragment readers are bank-conflict free), the z rows gathered through `z_rowmap`
+//              (the zigzag table) and the unfused B/C rows as 16-byte cp.async chunks; everything is counted on one
+//              mbarrier per ring slot.  [A first version issued one `cp.async.bulk` (UBLKCP) per row from 32 lanes: UBLKCP
+//              takes uniform registers, ptxas serialises the lanes in a waterfall loop of ~8 instructions per copy, and the
+//              producer warp needed 2x the instructions of a compute warp -- 0.60 ms, slower than round 1.]
+//   phases     the 128 threads of a CTA run a stage in three phases, each with the thread mapping that suits it, two
+//              __syncthreads per stage (after main; after post + pre of the next stage).  [A warp-autonomous variant --
+//              every warp walking the stages on its own, the last warp to release a ring slot refilling it -- was
+//              measured SLOWER (0.577 vs 0.508 ms): with a 2-3 deep ring the fast warps only run ahead until they
+//              block on a refill that is gated by the slowest warp, and then wait for the slowest warp AND the TMA latency.]
+//   pre        delta' = softplus(delta + bias) and delta' u ONCE per (channel, step), packed fp32x2 arithmetic, written as
+//              fp32 (delta', delta' u) pairs; B/C rows -> fp32.  Fused variant: the delta tile of the stage is
+//              a tensor-core product (ldmatrix + mma.sync m16n8k16 / m16n8k8) of the x_dbl rows already staged for B/C with
+//              the CTA's dt_proj rows (kept in shared memory), rounded to the I/O dtype like the reference's GEMM output:
+//              the (batch, dim, seqlen) delta tensor never exists in HBM and the dt_proj GEMM launch disappears.
+//   main       two threads per channel, 8 states (4 fp32x2 pairs) each: per step one LDS.64 (delta', delta' u), four
+//              LDS.128 (B, C), 4 x {FMUL2, 2 MUFU.EX2 | polynomial, FMUL2, FFMA2, FFMA2}, one FADD, one STS (the partial
+//              y overwrites the (delta', delta' u) slot it came from).
+//   post       y = y_lo + y_hi + D u, SiLU(z) gate, bf16x2 pack, 4-byte stores.
 #pragma once
 #include "scan_fwd.cuh"
 #include <cuda.h>
 #include <string.h>
 #include <type_traits>
 
+#ifndef ZG_SCAN_EXP
+#define ZG_SCAN_EXP 0      // 1, 2: timing experiments (wrong results), see DESIGN.md
+#endif
 #ifndef ZG_SCAN_TMA_NPOLY_DEFAULT
 #define ZG_SCAN_TMA_NPOLY_DEFAULT 0
 #endif
@@ -46,28 +50,23 @@ namespace zg {
 constexpr int PT_TL = 8;              // steps per stage
 constexpr int PT_CH = 64;             // channels per CTA
 constexpr int PT_THREADS = 128;
-constexpr int PT_F32ROW = 576;        // smem pitch of one step of the fp32 pair tiles (64 x 8 B + 64: bank shift of 16 words)
+constexpr int PT_F32ROW = 576;        // pitch of one step of the fp32 pair tile (64 channels x 8 B + 64: bank shift of 16 words)
 
 __host__ __device__ constexpr int pt_pitch16(int bytes) { return ((bytes / 16) | 1) * 16; }   // odd number of 16-byte units
 
-// PROD: how a stage reaches shared memory.  1 = every row chunk by per-thread cp.async (LDGSTS), rows padded to 144 B;
-// 2 = the dense tensors (u, delta | x_dbl, z without a rowmap) as ONE TMA tensor tile each (cp.async.bulk.tensor, SASS
-// UTMALDG, issued by one thread), the gathered z rows and the unfused B/C rows by cp.async; dense 128-byte rows.
-template <int R, int PROD> struct PtLayout {           // R = dt_rank of the fused prologue, 0 = delta comes from HBM
+template <int R> struct PtLayout {           // R = dt_rank of the fused prologue, 0 = delta comes from HBM
     static constexpr bool FUSE = R > 0;
-    static constexpr int NSTAGE = FUSE ? 2 : 3;
-    static constexpr int XBYTES = (R + 32) * 2;                       // one x_dbl row: dt | B | C
-    static constexpr int PT_ROW = PROD == 2 ? 128 : 144;              // pitch of a 64-channel 16-bit row
-    static constexpr int XROW = FUSE ? (PROD == 2 ? XBYTES : pt_pitch16(XBYTES)) : 0;
+    static constexpr int NSTAGE = 3;
+    static constexpr int NSWZ = FUSE ? 2 : 3;                         // swizzled 8 x 128 B tiles per stage: u, z (, delta)
+    static constexpr int XBYTES = (R + 32) * 2;                       // one x_dbl row: dt | B | C (dense, unswizzled)
     static constexpr int WROW = FUSE ? pt_pitch16(2 * R) : 0;
-    static constexpr int U_OFF = 0;
-    static constexpr int Z_OFF = PT_TL * PT_ROW;
-    static constexpr int D_OFF = 2 * PT_TL * PT_ROW;                  // delta rows | x_dbl rows
-    static constexpr int BC_OFF = D_OFF + PT_TL * PT_ROW;             // unfused only: raw B|C rows, 64 B each
-    static constexpr int STAGE = FUSE ? D_OFF + PT_TL * XROW : BC_OFF + PT_TL * 64;
-    static constexpr int DDU_OFF = NSTAGE * STAGE;
-    static constexpr int Y_OFF = DDU_OFF + PT_TL * PT_F32ROW;
-    static constexpr int BCF_OFF = Y_OFF + PT_TL * PT_F32ROW;
+    // 1024-byte tiles first (the 128-byte swizzle needs 1024-byte alignment), then the odd-sized ones
+    static constexpr int TILE = PT_TL * 128;
+    static constexpr int SWZ_OFF = 0;                                 // [stage][u, z, (delta)]
+    static constexpr int X_OFF = NSTAGE * NSWZ * TILE;                // fused: x_dbl rows; unfused: raw B|C rows (64 B each)
+    static constexpr int XSTAGE = FUSE ? ((PT_TL * XBYTES + 127) / 128) * 128 : PT_TL * 64;
+    static constexpr int DDU_OFF = X_OFF + NSTAGE * XSTAGE;           // (delta', delta' u) fp32 pairs; the partial y overwrite them
+    static constexpr int BCF_OFF = DDU_OFF + PT_TL * PT_F32ROW;       // fp32 [step][B0..15 C0..15]
     static constexpr int W_OFF = BCF_OFF + PT_TL * 32 * 4;
     static constexpr int BAR_OFF = W_OFF + (FUSE ? PT_CH * WROW : 0);
     static constexpr int TOTAL = BAR_OFF + NSTAGE * 8;
@@ -166,12 +165,13 @@ template <typename T> __device__ __forceinline__ void pt_mma_k8(float &d0, float
     }
 }
 
-// one stage (8 steps) of the recurrence for this thread's 8 states; NP of its 4 state pairs use the FMA-pipe exp2
+// one stage (8 steps) of the recurrence for this thread's 8 states; NP of its 4 state pairs use the FMA-pipe exp2.
+// ddu_c: this channel's (delta', delta' u) pairs, one per step; the partial y of the step overwrites the pair (lo half | hi half).
 template <int NP>
-__device__ __forceinline__ void pt_main_stage(const unsigned char *ddu_c, const float *bcf_h, float *y_ch, zg_f2 (&h2)[4], const zg_f2 (&Al2p)[4]) {
+__device__ __forceinline__ void pt_main_stage(unsigned char *ddu_c, const float *bcf_h, int hf, zg_f2 (&h2)[4], const zg_f2 (&Al2p)[4], bool store = true) {
 #pragma unroll
     for (int t = 0; t < PT_TL; ++t) {
-        const float2 dd = *reinterpret_cast<const float2 *>(ddu_c + t * PT_F32ROW);      // (delta', delta' * u)
+        const float2 dd = *reinterpret_cast<const float2 *>(ddu_c + t * PT_F32ROW);       // (delta', delta' * u)
         const float4 *bc = reinterpret_cast<const float4 *>(bcf_h + t * 32);
         const float4 B0 = bc[0], B1 = bc[1], C0 = bc[4], C1 = bc[5];
         const zg_f2 Bp[4] = {make_float2(B0.x, B0.y), make_float2(B0.z, B0.w), make_float2(B1.x, B1.y), make_float2(B1.z, B1.w)};
@@ -181,11 +181,20 @@ __device__ __forceinline__ void pt_main_stage(const unsigned char *ddu_c, const 
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             const zg_f2 x = zg_mul2(dl, Al2p[q]);
+#if ZG_SCAN_EXP == 5
+            const zg_f2 a = zg_add2(x, zg_splat2(1.f));      // experiment: everything but the exponentials
+#else
             const zg_f2 a = (q < NP) ? zg_ex2_poly2_neg(x) : zg_ex2_mufu2(x);
+#endif
             h2[q] = zg_fma2(a, h2[q], zg_mul2(du, Bp[q]));
             y2 = zg_fma2(Cp[q], h2[q], y2);
         }
-        y_ch[t * (PT_F32ROW / 4)] = y2.x + y2.y;
+        // both threads of the channel have read the pair (one converged LDS) before either overwrites its half
+#if ZG_SCAN_EXP == 3
+        if (store) reinterpret_cast<float *>(ddu_c + t * PT_F32ROW)[hf] = y2.x + y2.y;
+#else
+        reinterpret_cast<float *>(ddu_c + t * PT_F32ROW)[hf] = y2.x + y2.y;
+#endif
     }
 }
 
@@ -201,20 +210,19 @@ __device__ __forceinline__ void pt_cp_async_arrive(uint64_t *bar) {
     asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(zg_smem_u32(bar)) : "memory");
 }
 
-template <typename T, int R, int NPOLY, bool CKPT, int PROD>
+template <typename T, int R, int NPOLY, bool CKPT>
 __global__ void __launch_bounds__(PT_THREADS, 9) scan_fwd_tma_kernel(const zg_scan_params p, const __grid_constant__ PtMaps maps) {
     static_assert(sizeof(T) == 2, "16-bit I/O only");
-    using LY = PtLayout<R, PROD>;
+    using LY = PtLayout<R>;
     constexpr bool FUSE = LY::FUSE;
-    constexpr int NSTAGE = LY::NSTAGE, TL = PT_TL, CH = PT_CH, PT_ROW = LY::PT_ROW;
+    constexpr int NSTAGE = LY::NSTAGE, TL = PT_TL, CH = PT_CH, TILE = LY::TILE;
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char *ddu = smem + LY::DDU_OFF;
-    unsigned char *ytile = smem + LY::Y_OFF;
     float *bcf = reinterpret_cast<float *>(smem + LY::BCF_OFF);
     uint64_t *full = reinterpret_cast<uint64_t *>(smem + LY::BAR_OFF);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int c = tid >> 1, hf = tid & 1;
+    const int hf = tid & 1;
     const int E = p.dim, L = p.seqlen;
     const int per_group = E / p.ngroups;
     const int tiles_per_group = per_group / CH;
@@ -223,9 +231,9 @@ __global__ void __launch_bounds__(PT_THREADS, 9) scan_fwd_tma_kernel(const zg_sc
     const int tile = blockIdx.x % tiles;
     const int g = tile / tiles_per_group;
     const int e0 = g * per_group + (tile % tiles_per_group) * CH;
-    const int e = e0 + c;
+    const int e = e0 + (tid >> 1);                                  // main phase: this thread's channel
     const bool has_z = p.z != nullptr;
-    const bool z_gather = has_z && (PROD == 1 || p.z_rowmap != nullptr);     // z rows by per-thread cp.async
+    const bool z_gather = has_z && p.z_rowmap != nullptr;           // z rows by cp.async through the table
     const bool softplus = (p.flags & ZG_SCAN_DELTA_SOFTPLUS) != 0;
     const int nstages = L / TL;
 
@@ -233,20 +241,32 @@ __global__ void __launch_bounds__(PT_THREADS, 9) scan_fwd_tma_kernel(const zg_sc
     zg_f2 Al2p[4], h2[4];
     bool a_pos = false;
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        const float2 a = *reinterpret_cast<const float2 *>(p.A + (int64_t)e * 16 + 8 * hf + 2 * q);
-        Al2p[q] = zg_mul2(a, zg_splat2(ZG_LOG2E));
+    for (int k = 0; k < 4; ++k) {
+        const float2 a = *reinterpret_cast<const float2 *>(p.A + (int64_t)e * 16 + 8 * hf + 2 * k);
+        Al2p[k] = zg_mul2(a, zg_splat2(ZG_LOG2E));
         a_pos = a_pos || a.x > 0.f || a.y > 0.f;
-        h2[q] = zg_splat2(0.f);
+        h2[k] = zg_splat2(0.f);
     }
-    // row-wise phases: this lane's channel pair (D skip, delta bias)
-    const int cp = e0 + 2 * lane;
-    const float2 Dv = p.D ? *reinterpret_cast<const float2 *>(p.D + cp) : make_float2(0.f, 0.f);
+    // The two (step, channel pair) items a thread owns in the pre and post phases (same items in both: the post phase reads
+    // the partial y from the 16 bytes its own pre phase filled, so a thread may run pre(s + 1) right after post(s)):
+    //   unfused: lane = channel pair, steps warp and warp + 4  (128-byte coalesced output rows)
+    //   fused:   step lane / 4, channel pairs 16 warp + 8 k + 2 (lane % 4) -- the m16n8 accumulator layout of the delta tile
+    int it_swz[2], it_ddu[2];                              // byte offsets inside a swizzled 8 x 128 B tile / the fp32 pair tile
+    float2 Dv[2], biasv[2];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        const int row = FUSE ? (lane >> 2) : warp + 4 * k;
+        const int pair = FUSE ? 8 * warp + 4 * k + (lane & 3) : lane;                  // channel pair 0..31 of the tile
+        it_swz[k] = row * 128 + (((pair >> 2) ^ row) << 4) + (pair & 3) * 4;
+        it_ddu[k] = row * PT_F32ROW + pair * 16;
+        Dv[k] = p.D ? *reinterpret_cast<const float2 *>(p.D + e0 + 2 * pair) : make_float2(0.f, 0.f);
+        biasv[k] = p.delta_bias ? *reinterpret_cast<const float2 *>(p.delta_bias + e0 + 2 * pair) : make_float2(0.f, 0.f);
+    }
 
-    // full[s]: one arrival per thread and stage (its cp.async copies, possibly none) + the TMA issuer's expect_tx arrival
+    // full[s]: one cp.async arrival per thread and stage (its gathered chunk, possibly none) + the TMA issuer's expect_tx
     if (tid == 0) {
 #pragma unroll
-        for (int s = 0; s < NSTAGE; ++s) zg_mbar_init(&full[s], PT_THREADS + (PROD == 2 ? 1 : 0));
+        for (int s = 0; s < NSTAGE; ++s) zg_mbar_init(&full[s], PT_THREADS + 1);
         zg_mbar_fence_init();
     }
     if constexpr (FUSE) {   // this CTA's 64 dt_proj rows -> shared memory (pitch WROW: conflict-free ldmatrix)
@@ -262,77 +282,59 @@ __global__ void __launch_bounds__(PT_THREADS, 9) scan_fwd_tma_kernel(const zg_sc
     const bool use_poly = NPOLY > 0 && softplus && !__syncthreads_or(a_pos);
     __syncthreads();
 
-    // ---- producer: every thread moves at most two 16-byte chunks per stage; thread 0 issues the tensor tiles ------
-    constexpr int XC = LY::XBYTES / 16;                   // 16-byte chunks per x_dbl row
-    const int zr = (tid >> 3) & 7, zj = tid & 7;          // threads 64..127: z row / chunk of the stage
-    int zrow_next = zr;                                   // (permuted) source row of the NEXT stage to issue
-    if (z_gather && tid >= 64 && p.z_rowmap) zrow_next = p.z_rowmap[zr];
-    const uint32_t tx_bytes = TL * 128 + (FUSE ? TL * LY::XBYTES : TL * 128) + ((has_z && !z_gather) ? TL * 128 : 0);
-    auto issue_stage = [&](int s) {                       // all threads
+    // ---- producer: thread 0 issues the tensor tiles; threads 64..127 gather one z chunk each, 64..95 a B|C chunk ----
+    const uint32_t tx_bytes = TILE + (FUSE ? TL * LY::XBYTES : TILE) + ((has_z && !z_gather) ? TILE : 0);
+    const int zr = (tid >> 3) & 7, zj = tid & 7;          // threads 64..127: z row / 16-byte column of the stage
+    const unsigned char *zsrc = (z_gather && tid >= 64) ? reinterpret_cast<const unsigned char *>(reinterpret_cast<const T *>(p.z) + (int64_t)b * p.z_sb + e0 + zj * 8) : nullptr;
+    const uint32_t z_sl2 = (uint32_t)p.z_sl * 2u;            // byte offsets inside a batch element fit 32 bits (host check)
+    int zrow_next = (zsrc != nullptr) ? p.z_rowmap[zr] : 0;   // (permuted) source row of the NEXT stage to issue
+    auto issue_stage = [&](int s, int slot) {             // all threads
         if (s >= nstages) return;
-        unsigned char *st = smem + (s % NSTAGE) * LY::STAGE;
-        uint64_t *bar = &full[s % NSTAGE];
+        unsigned char *sw = smem + LY::SWZ_OFF + slot * LY::NSWZ * TILE;
+        unsigned char *xt = smem + LY::X_OFF + slot * LY::XSTAGE;
+        uint64_t *bar = &full[slot];
         const int l0 = s * TL;
-        if (PROD == 2 && tid == 0) {
+        if (tid == 0) {
             zg_mbar_expect_tx(bar, tx_bytes);
-            pt_tma_load_3d(st + LY::U_OFF, &maps.u, bar, e0, l0, b);
-            pt_tma_load_3d(st + LY::D_OFF, &maps.d, bar, FUSE ? 0 : e0, l0, b);
-            if (has_z && !z_gather) pt_tma_load_3d(st + LY::Z_OFF, &maps.z, bar, e0, l0, b);
+            pt_tma_load_3d(sw, &maps.u, bar, e0, l0, b);
+            if (has_z && !z_gather) pt_tma_load_3d(sw + TILE, &maps.z, bar, e0, l0, b);
+            if constexpr (FUSE) pt_tma_load_3d(xt, &maps.d, bar, 0, l0, b);
+            else pt_tma_load_3d(sw + 2 * TILE, &maps.d, bar, e0, l0, b);
         }
         if (tid >= 64) {
-            if (z_gather) {
-                const T *gz = reinterpret_cast<const T *>(p.z) + (int64_t)b * p.z_sb + e0;
-                zg_cp_async16(st + LY::Z_OFF + zr * PT_ROW + zj * 16, gz + (int64_t)zrow_next * p.z_sl + zj * 8);
+            if (zsrc != nullptr) {                        // chunk (row zr, column zj) lands swizzled like the TMA tiles
+                zg_cp_async16(sw + TILE + zr * 128 + ((zj ^ zr) << 4), zsrc + (uint32_t)zrow_next * z_sl2);
                 const int ln = l0 + TL + zr;
-                zrow_next = (ln < L) ? (p.z_rowmap ? p.z_rowmap[ln] : ln) : 0;
+                zrow_next = (ln < L) ? p.z_rowmap[ln] : 0;
             }
-            if (!FUSE && tid < 96) {                      // B | C rows: 8 steps x (2 + 2) chunks
+            if (!FUSE && tid < 96) {                      // raw B | C rows: 8 steps x (2 + 2) chunks
                 const int r = (tid >> 2) & 7, w = (tid >> 1) & 1, j = tid & 1;
                 const T *src = w ? reinterpret_cast<const T *>(p.C) + (int64_t)b * p.C_sb + (int64_t)g * p.C_sg + (int64_t)(l0 + r) * p.C_sl
                                  : reinterpret_cast<const T *>(p.B) + (int64_t)b * p.B_sb + (int64_t)g * p.B_sg + (int64_t)(l0 + r) * p.B_sl;
-                zg_cp_async16(st + LY::BC_OFF + r * 64 + w * 32 + j * 16, src + j * 8);
+                zg_cp_async16(xt + r * 64 + w * 32 + j * 16, src + j * 8);
             }
-        } else if (PROD == 1) {
-            const int r = tid >> 3, j = tid & 7;
-            zg_cp_async16(st + LY::U_OFF + r * PT_ROW + j * 16, reinterpret_cast<const T *>(p.u) + (int64_t)b * p.u_sb + e0 + (int64_t)(l0 + r) * p.u_sl + j * 8);
-            if (!FUSE) zg_cp_async16(st + LY::D_OFF + r * PT_ROW + j * 16, reinterpret_cast<const T *>(p.delta) + (int64_t)b * p.delta_sb + e0 + (int64_t)(l0 + r) * p.delta_sl + j * 8);
-        }
-        if (PROD == 1 && FUSE && tid < TL * XC) {
-            const int r = tid / XC, j = tid % XC;
-            zg_cp_async16(st + LY::D_OFF + r * LY::XROW + j * 16, reinterpret_cast<const T *>(p.dt_x) + (int64_t)b * p.dt_x_sb + (int64_t)(l0 + r) * p.dt_x_sl + j * 8);
         }
         pt_cp_async_arrive(bar);
     };
 #pragma unroll
-    for (int s = 0; s < NSTAGE; ++s) issue_stage(s);
+    for (int s = 0; s < NSTAGE; ++s) issue_stage(s, s);
 
-    // ---- pre phase: raw stage -> (delta', delta' u) fp32 pairs + fp32 B/C ----------------------------------------
-    float2 biasv = make_float2(0.f, 0.f);                 // unfused: bias of the lane's channel pair
-    float2 biasf[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};   // fused: bias of the two fragment channel pairs
-    if constexpr (FUSE) {
-        if (p.delta_bias) {
-#pragma unroll
-            for (int j = 0; j < 2; ++j) biasf[j] = *reinterpret_cast<const float2 *>(p.delta_bias + e0 + 16 * warp + 8 * j + 2 * (lane & 3));
-        }
-    } else {
-        if (p.delta_bias) biasv = *reinterpret_cast<const float2 *>(p.delta_bias + cp);
-    }
-    auto pre = [&](int s) {
-        const unsigned char *st = smem + (s % NSTAGE) * LY::STAGE;
-        zg_mbar_wait(&full[s % NSTAGE], (uint32_t)((s / NSTAGE) & 1));
-        // B | C rows -> fp32 [step][B0..15 C0..15]: one 16-bit pair per thread
-        {
-            const int t = tid >> 4, j = tid & 15;
-            const uint32_t raw = FUSE ? *reinterpret_cast<const uint32_t *>(st + LY::D_OFF + t * LY::XROW + 2 * R + j * 4)
-                                      : *reinterpret_cast<const uint32_t *>(st + LY::BC_OFF + t * 64 + j * 4);
-            *reinterpret_cast<float2 *>(bcf + t * 32 + 2 * j) = pt_unpack2<T>(raw);
-        }
+    // ---- pre / post work of a thread's two items.  post(s) and pre(s + 1) run in the same barrier interval and touch the same
+    // 16 bytes of the pair tile (y read, then (delta', delta' u) written), so they are interleaved item by item: four
+    // independent MUFU chains (SiLU of two items, softplus of two items) per thread instead of two after two.
+    auto bc_convert = [&](const unsigned char *xt) {      // B | C rows -> fp32 [step][B0..15 C0..15]: one 16-bit pair per thread
+        const int t = tid >> 4, j = tid & 15;
+        const uint32_t raw = FUSE ? *reinterpret_cast<const uint32_t *>(xt + t * LY::XBYTES + 2 * R + j * 4)
+                                  : *reinterpret_cast<const uint32_t *>(xt + t * 64 + j * 4);
+        *reinterpret_cast<float2 *>(bcf + t * 32 + 2 * j) = pt_unpack2<T>(raw);
+    };
+    // raw (rounded) delta of the thread's two items: from the delta tile, or (fused) from the tensor-core product
+    //     x_dbl[8 steps, 0:R] . W[64 ch, 0:R]^T      (this warp: channels 16 warp .. +15; rows 8..15 of the m16 tile are zero)
+    auto delta_items = [&](const unsigned char *sw, const unsigned char *xt, float2 (&dlt)[2]) {
         if constexpr (FUSE) {
-            // delta tile = x_dbl[8 steps, 0:R] . W[64 ch, 0:R]^T on the tensor cores; this warp: channels 16 warp .. +15
-            const uint32_t xs = zg_smem_u32(st + LY::D_OFF), ws = zg_smem_u32(smem + LY::W_OFF);
-            const int gq = lane >> 2, q = lane & 3;
+            const uint32_t xs = zg_smem_u32(xt), ws = zg_smem_u32(smem + LY::W_OFF);
             float d[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
-            const uint32_t a_addr = xs + (lane & 7) * LY::XROW + (lane >> 3) * 16;
+            const uint32_t a_addr = xs + (lane & 7) * LY::XBYTES + (lane >> 3) * 16;
             const uint32_t b_addr = ws + (16 * warp + (lane & 7) + 8 * (lane >> 4)) * LY::WROW + ((lane >> 3) & 1) * 16;
 #pragma unroll
             for (int k2 = 0; k2 < R / 32; ++k2) {           // two k16 steps per iteration
@@ -349,7 +351,7 @@ __global__ void __launch_bounds__(PT_THREADS, 9) scan_fwd_tma_kernel(const zg_sc
             constexpr int KB = (R / 32) * 64;               // their byte offset in a row
             if constexpr (KREM >= 16) {
                 uint32_t a0, a1, b0, b1, b2, b3;
-                pt_ldmatrix_x2(a0, a1, xs + (lane & 7) * LY::XROW + ((lane >> 3) & 1) * 16 + KB);
+                pt_ldmatrix_x2(a0, a1, xs + (lane & 7) * LY::XBYTES + ((lane >> 3) & 1) * 16 + KB);
                 pt_ldmatrix_x4(b0, b1, b2, b3, b_addr + KB);
                 pt_mma_k16<T>(d[0][0], d[0][1], a0, a1, b0, b1);
                 pt_mma_k16<T>(d[1][0], d[1][1], a0, a1, b2, b3);
@@ -357,68 +359,94 @@ __global__ void __launch_bounds__(PT_THREADS, 9) scan_fwd_tma_kernel(const zg_sc
             if constexpr (KREM % 16 == 8) {
                 constexpr int KB8 = KB + (KREM >= 16 ? 32 : 0);
                 uint32_t a0, b0, b1;
-                pt_ldmatrix_x1(a0, xs + (lane & 7) * LY::XROW + KB8);
+                pt_ldmatrix_x1(a0, xs + (lane & 7) * LY::XBYTES + KB8);
                 pt_ldmatrix_x2(b0, b1, ws + (16 * warp + (lane & 7) + 8 * ((lane >> 3) & 1)) * LY::WROW + KB8);
                 pt_mma_k8<T>(d[0][0], d[0][1], a0, b0);
                 pt_mma_k8<T>(d[1][0], d[1][1], a0, b1);
             }
-            // fragment (step gq, channels 16 warp + 8 j + 2 q, +1): round like the reference's GEMM output, bias, softplus, * u
+            // round like the reference's GEMM output (selective_scan_interface.py:323 produces delta in the I/O dtype)
 #pragma unroll
-            for (int j = 0; j < 2; ++j) {
-                const int cj = 16 * warp + 8 * j + 2 * q;
-                float2 dl = zg_add2(pt_unpack2<T>(pt_pack2<T>(d[j][0], d[j][1])), biasf[j]);
-                if (softplus) dl = pt_softplus20_2(dl);
-                const float2 u2 = pt_unpack2<T>(*reinterpret_cast<const uint32_t *>(st + LY::U_OFF + gq * PT_ROW + cj * 2));
-                const float2 du = zg_mul2(dl, u2);
-                *reinterpret_cast<float4 *>(ddu + gq * PT_F32ROW + cj * 8) = make_float4(dl.x, du.x, dl.y, du.y);
-            }
+            for (int j = 0; j < 2; ++j) dlt[j] = pt_unpack2<T>(pt_pack2<T>(d[j][0], d[j][1]));
         } else {
 #pragma unroll
-            for (int k = 0; k < 2; ++k) {
-                const int t = warp + 4 * k;
-                float2 dl = zg_add2(pt_unpack2<T>(*reinterpret_cast<const uint32_t *>(st + LY::D_OFF + t * PT_ROW + lane * 4)), biasv);
-                if (softplus) dl = pt_softplus20_2(dl);
-                const float2 u2 = pt_unpack2<T>(*reinterpret_cast<const uint32_t *>(st + LY::U_OFF + t * PT_ROW + lane * 4));
-                const float2 du = zg_mul2(dl, u2);
-                *reinterpret_cast<float4 *>(ddu + t * PT_F32ROW + lane * 16) = make_float4(dl.x, du.x, dl.y, du.y);
-            }
+            for (int k = 0; k < 2; ++k) dlt[k] = pt_unpack2<T>(*reinterpret_cast<const uint32_t *>(sw + 2 * TILE + it_swz[k]));
         }
     };
-
-    // ---- post phase: y partial sums -> gated output rows -----------------------------------------------------------
-    T *gout = reinterpret_cast<T *>(p.out) + (int64_t)b * p.out_sb + cp;
-    auto post = [&](int s) {
-        const unsigned char *st = smem + (s % NSTAGE) * LY::STAGE;
-#pragma unroll
-        for (int k = 0; k < 2; ++k) {
-            const int t = warp + 4 * k;
-            const float4 yy = *reinterpret_cast<const float4 *>(ytile + t * PT_F32ROW + lane * 16);   // (lo, hi) halves of 2 channels
-            const float2 u2 = pt_unpack2<T>(*reinterpret_cast<const uint32_t *>(st + LY::U_OFF + t * PT_ROW + lane * 4));
-            float2 y = zg_fma2(Dv, u2, zg_add2(make_float2(yy.x, yy.z), make_float2(yy.y, yy.w)));
-            if (has_z) y = zg_mul2(y, pt_silu2(pt_unpack2<T>(*reinterpret_cast<const uint32_t *>(st + LY::Z_OFF + t * PT_ROW + lane * 4))));
-            *reinterpret_cast<uint32_t *>(gout + (int64_t)(s * TL + t) * p.out_sl) = pt_pack2<T>(y.x, y.y);
-        }
+    auto pre_item = [&](int k, float2 dl, const unsigned char *sw) {     // bias, softplus, * u -> (delta', delta' u) pairs
+        dl = zg_add2(dl, biasv[k]);
+#if ZG_SCAN_EXP == 1
+        if (softplus) dl = zg_mul2(dl, dl);
+#else
+        if (softplus) dl = pt_softplus20_2(dl);
+#endif
+        const float2 du = zg_mul2(dl, pt_unpack2<T>(*reinterpret_cast<const uint32_t *>(sw + it_swz[k])));
+        float2 *dst = reinterpret_cast<float2 *>(ddu + it_ddu[k]);
+        dst[0] = make_float2(dl.x, du.x);
+        dst[1] = make_float2(dl.y, du.y);
+    };
+    const int64_t out_step = FUSE ? 8 : 4 * p.out_sl;     // element distance between the thread's two output pairs
+    T *gout = reinterpret_cast<T *>(p.out) + (int64_t)b * p.out_sb + (int64_t)(FUSE ? (lane >> 2) : warp) * p.out_sl + e0 +
+              (FUSE ? 16 * warp + 2 * (lane & 3) : 2 * lane);
+    const int64_t out_stage = (int64_t)TL * p.out_sl;
+    auto post_item = [&](int k, const unsigned char *sw) {               // y = y_lo + y_hi + D u, SiLU(z) gate, store
+        const float4 yy = *reinterpret_cast<const float4 *>(ddu + it_ddu[k]);   // (lo, hi) halves of 2 channels
+        const float2 u2 = pt_unpack2<T>(*reinterpret_cast<const uint32_t *>(sw + it_swz[k]));
+        float2 y = zg_fma2(Dv[k], u2, zg_add2(make_float2(yy.x, yy.z), make_float2(yy.y, yy.w)));
+#if ZG_SCAN_EXP == 1
+        if (has_z) y = zg_mul2(y, pt_unpack2<T>(*reinterpret_cast<const uint32_t *>(sw + TILE + it_swz[k])));
+#else
+        if (has_z) y = zg_mul2(y, pt_silu2(pt_unpack2<T>(*reinterpret_cast<const uint32_t *>(sw + TILE + it_swz[k]))));
+#endif
+        *reinterpret_cast<uint32_t *>(gout + (k ? out_step : 0)) = pt_pack2<T>(y.x, y.y);
     };
 
     // ---- the pipeline ------------------------------------------------------------------------------------------------
-    const unsigned char *ddu_c = ddu + c * 8;
+    unsigned char *ddu_c = ddu + (tid >> 1) * 8;
     const float *bcf_h = bcf + 8 * hf;
-    float *y_ch = reinterpret_cast<float *>(ytile) + 2 * c + hf;
-    pre(0);
+    {   // stage 0: pre only
+        const unsigned char *sw = smem + LY::SWZ_OFF, *xt = smem + LY::X_OFF;
+        zg_mbar_wait(&full[0], 0);
+        float2 dlt[2];
+        delta_items(sw, xt, dlt);
+        pre_item(0, dlt[0], sw);
+        pre_item(1, dlt[1], sw);
+        bc_convert(xt);
+    }
     __syncthreads();
+    int slot = 0, nslot = 1;
+    uint32_t npar = 0;                                       // phase parity of the next stage's slot
     for (int s = 0; s < nstages; ++s) {
-        if (NPOLY > 0 && use_poly) pt_main_stage<NPOLY>(ddu_c, bcf_h, y_ch, h2, Al2p);
-        else pt_main_stage<0>(ddu_c, bcf_h, y_ch, h2, Al2p);
+        if (NPOLY > 0 && use_poly) pt_main_stage<NPOLY>(ddu_c, bcf_h, hf, h2, Al2p);
+        else pt_main_stage<0>(ddu_c, bcf_h, hf, h2, Al2p, s == nstages - 1);
         if constexpr (CKPT) {       // recompute seeds of the backward: state after every 8 steps, (batch, n_ckpt, dim, dstate)
             float4 *dst = reinterpret_cast<float4 *>(p.ckpt + (((int64_t)b * (L >> 3) + s) * E + e) * 16 + 8 * hf);
             dst[0] = make_float4(h2[0].x, h2[0].y, h2[1].x, h2[1].y);
             dst[1] = make_float4(h2[2].x, h2[2].y, h2[3].x, h2[3].y);
         }
-        __syncthreads();            // y tile complete; (delta', delta' u) and B/C tiles free
-        post(s);
-        if (s + 1 < nstages) pre(s + 1);
+        const unsigned char *sw = smem + LY::SWZ_OFF + slot * LY::NSWZ * TILE;
+        const unsigned char *swn = smem + LY::SWZ_OFF + nslot * LY::NSWZ * TILE;
+        const unsigned char *xtn = smem + LY::X_OFF + nslot * LY::XSTAGE;
+#if ZG_SCAN_EXP == 2 || ZG_SCAN_EXP == 3
+        if (s == nstages - 1) { post_item(0, sw); post_item(1, sw); }   // experiment: the recurrence alone
+#else
+        __syncthreads();            // y complete; B/C tile free
+        if (s + 1 < nstages) {      // post(s) interleaved with pre(s + 1)
+            zg_mbar_wait(&full[nslot], npar);
+            float2 dlt[2];
+            delta_items(swn, xtn, dlt);
+#pragma unroll
+            for (int k = 0; k < 2; ++k) { post_item(k, sw); pre_item(k, dlt[k], swn); }
+            bc_convert(xtn);
+        } else {
+            post_item(0, sw);
+            post_item(1, sw);
+        }
+        gout += out_stage;
         __syncthreads();            // raw slot of stage s free; tiles of stage s + 1 complete
-        issue_stage(s + NSTAGE);
+        issue_stage(s + NSTAGE, slot);
+#endif
+        slot = nslot;
+        if (++nslot == NSTAGE) { nslot = 0; npar ^= 1; }
     }
     if (p.last_state) {
         float4 *dst = reinterpret_cast<float4 *>(p.last_state + ((int64_t)b * E + e) * 16 + 8 * hf);
@@ -446,8 +474,10 @@ inline PtEncodeTiledFn pt_get_encode() {
     return fn;
 }
 // (cols, seqlen, batch) view of a token-major 16-bit tensor -> tensor map with a (box_cols x 8 steps x 1) box, rows dense in smem
+// (cols, seqlen, batch) view of a token-major 16-bit tensor -> tensor map with a (box_cols x 8 steps x 1) box.
+// swizzle: the 64-channel tiles use the 128-byte swizzle (rows of exactly 128 B), the x_dbl rows land dense.
 template <typename T>
-inline int pt_make_map(CUtensorMap *m, const void *base, int64_t cols, int64_t seqlen, int64_t batch, int64_t sl, int64_t sb, int box_cols) {
+inline int pt_make_map(CUtensorMap *m, const void *base, int64_t cols, int64_t seqlen, int64_t batch, int64_t sl, int64_t sb, int box_cols, bool swizzle) {
     PtEncodeTiledFn enc = pt_get_encode();
     if (!enc) return zg_set_error("scan_fwd(tma): cuTensorMapEncodeTiled not available from the driver");
     cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)seqlen, (cuuint64_t)batch};
@@ -455,25 +485,22 @@ inline int pt_make_map(CUtensorMap *m, const void *base, int64_t cols, int64_t s
     cuuint32_t box[3] = {(cuuint32_t)box_cols, (cuuint32_t)PT_TL, 1};
     cuuint32_t estr[3] = {1, 1, 1};
     const CUtensorMapDataType dt = std::is_same<T, __nv_bfloat16>::value ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
-    CUresult r = enc(m, dt, 3, const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-                     CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return -2;        // not expressible as a tensor map (e.g. stride limits): the caller falls back to PROD 1
+    CUresult r = enc(m, dt, 3, const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     swizzle ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return -1;        // not expressible as a tensor map (stride limits): the caller falls back to the round-1 kernel
     return 0;
 }
 
-template <typename T, int R, int NPOLY, bool CKPT, int PROD> int pt_launch(const zg_scan_params &p, cudaStream_t stream) {
-    using LY = PtLayout<R, PROD>;
+template <typename T, int R, int NPOLY, bool CKPT> int pt_launch(const zg_scan_params &p, cudaStream_t stream) {
+    using LY = PtLayout<R>;
     PtMaps maps;
     memset(&maps, 0, sizeof(maps));
-    if (PROD == 2) {
-        int rc = pt_make_map<T>(&maps.u, p.u, p.dim, p.seqlen, p.batch, p.u_sl, p.u_sb, PT_CH);
-        if (!rc) rc = R > 0 ? pt_make_map<T>(&maps.d, p.dt_x, R + 32, p.seqlen, p.batch, p.dt_x_sl, p.dt_x_sb, R + 32)
-                            : pt_make_map<T>(&maps.d, p.delta, p.dim, p.seqlen, p.batch, p.delta_sl, p.delta_sb, PT_CH);
-        if (!rc && p.z && !p.z_rowmap) rc = pt_make_map<T>(&maps.z, p.z, p.dim, p.seqlen, p.batch, p.z_sl, p.z_sb, PT_CH);
-        if (rc == -2) return pt_launch<T, R, NPOLY, CKPT, 1>(p, stream);
-        if (rc) return rc;
-    }
-    auto kern = scan_fwd_tma_kernel<T, R, NPOLY, CKPT, PROD>;
+    int rc = pt_make_map<T>(&maps.u, p.u, p.dim, p.seqlen, p.batch, p.u_sl, p.u_sb, PT_CH, true);
+    if (!rc) rc = R > 0 ? pt_make_map<T>(&maps.d, p.dt_x, R + 32, p.seqlen, p.batch, p.dt_x_sl, p.dt_x_sb, R + 32, false)
+                        : pt_make_map<T>(&maps.d, p.delta, p.dim, p.seqlen, p.batch, p.delta_sl, p.delta_sb, PT_CH, true);
+    if (!rc && p.z && !p.z_rowmap) rc = pt_make_map<T>(&maps.z, p.z, p.dim, p.seqlen, p.batch, p.z_sl, p.z_sb, PT_CH, true);
+    if (rc) return rc;
+    auto kern = scan_fwd_tma_kernel<T, R, NPOLY, CKPT>;
     static bool attr_set = false;       // per instantiation (the library drives one device per process)
     if (!attr_set) {
         cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, LY::TOTAL);
@@ -487,19 +514,13 @@ template <typename T, int R, int NPOLY, bool CKPT, int PROD> int pt_launch(const
     return zg_check_launch("scan_fwd(tma)");
 }
 
-template <typename T, int R, int PROD> int pt_launch_npoly(const zg_scan_params &p, cudaStream_t stream) {
+template <typename T, int R> int pt_launch_variant(const zg_scan_params &p, cudaStream_t stream) {
     static int npoly = -1;
     if (npoly < 0) { npoly = pt_env_int("ZG_SCAN_TMA_NPOLY", ZG_SCAN_TMA_NPOLY_DEFAULT); if (npoly < 0 || npoly > 2) npoly = 0; }
-    if (p.ckpt) return pt_launch<T, R, 0, true, PROD>(p, stream);        // training forward (writes the recompute seeds)
-    if (npoly == 1) return pt_launch<T, R, 1, false, PROD>(p, stream);
-    if (npoly == 2) return pt_launch<T, R, 2, false, PROD>(p, stream);
-    return pt_launch<T, R, 0, false, PROD>(p, stream);
-}
-
-template <typename T, int R> int pt_launch_variant(const zg_scan_params &p, cudaStream_t stream) {
-    static int prod = -1;
-    if (prod < 0) { prod = pt_env_int("ZG_SCAN_PROD", 2); if (prod != 1) prod = 2; }
-    return prod == 1 ? pt_launch_npoly<T, R, 1>(p, stream) : pt_launch_npoly<T, R, 2>(p, stream);
+    if (p.ckpt) return pt_launch<T, R, 0, true>(p, stream);        // training forward (writes the recompute seeds)
+    if (npoly == 1) return pt_launch<T, R, 1, false>(p, stream);
+    if (npoly == 2) return pt_launch<T, R, 2, false>(p, stream);
+    return pt_launch<T, R, 0, false>(p, stream);
 }
 
 // host-side eligibility test + launch; returns -1 when the call does not fit the specialisation (never for a fused request:

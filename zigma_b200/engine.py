@@ -90,7 +90,10 @@ class ZigMaEngine:
         self._versions = None
         self._graphs = {}
         self.use_graph = os.environ.get("ZIGMA_CUDA_GRAPH", "1") != "0"
-        self.fuse_dt = os.environ.get("ZIGMA_FUSE_DT", "1") != "0"
+        # dt_proj inside the scan kernel (zg_scan_params.dt_w): correct and tested, but measured SLOWER on B200 than GEMM + scan
+        # (0.600 ms vs 0.507 + 0.042 ms per layer at config 2: the MMA + fragment epilogue lengthens the latency-bound
+        # pre phase of every stage), so it is opt-in
+        self.fuse_dt = os.environ.get("ZIGMA_FUSE_DT", "0") == "1"
         self.refresh()
 
     # ---- derived, cached tensors ------------------------------------------------------------------
