@@ -11,13 +11,19 @@ from zigma_b200.train import FlatParams, GradSync  # noqa: E402
 
 dist.init_process_group("gloo")
 rank, world = dist.get_rank(), dist.get_world_size()
-torch.manual_seed(0)                                   # same weights and data on every rank
+torch.manual_seed(100 + rank)                          # DIFFERENT initial weights per rank, like set_seed(device_specific=True) (train_acc.py:125)
 net = torch.nn.Sequential(torch.nn.Linear(7, 13), torch.nn.Tanh(), torch.nn.Linear(13, 5), torch.nn.Tanh(), torch.nn.Linear(5, 3))
-X, Y = torch.randn(8, 7), torch.randn(8, 3)
+gen = torch.Generator().manual_seed(0)                 # the same data on every rank
+X, Y = torch.randn(8, 7, generator=gen), torch.randn(8, 3, generator=gen)
 ref = [p.detach().clone() for p in net.parameters()]
 flat = FlatParams(net)
 assert all(torch.equal(a, b) for a, b in zip(ref, net.parameters()))
 sync = GradSync(flat, bucket_mb=1e-4)                  # tiny buckets: several all-reduces, launched from the hooks
+# GradSync starts every replica from rank 0's weights (what DDP / accelerate do at wrap time)
+w0 = [torch.empty_like(flat.flat) for _ in range(world)]
+dist.all_gather(w0, flat.flat)
+assert all(torch.equal(w0[0], w) for w in w0), "replicas must start from rank 0's weights"
+assert (rank == 0) == all(torch.equal(a, b) for a, b in zip(ref, net.parameters()))
 assert len(sync.buckets) >= 3, sync.buckets
 for it in range(2):                                    # two steps: counters re-arm, zero_grad keeps the views
     flat.zero_grad()

@@ -106,6 +106,25 @@ def test_euler_sampling_loop_matches_oracle():
     check_close(got, want, "5-step Euler sampling", atol=5e-5)
 
 
+def test_whole_loop_graph_euler_matches_sampler_and_oracle():
+    """ZigMa.sample_euler (the whole fixed-grid Euler loop as ONE CUDA-graph replay) == the step-by-step
+    Sampler.sample_ode("euler") == the oracle's loop around the oracle's forward."""
+    from zigma_b200 import create_transport, Sampler
+    g, cfg, shapes = model_case("tiny_zigzag8")
+    m, sd = _build(cfg, shapes)
+    x0 = synth.synth_latents((2, 4, 8, 8), seed=8)
+    with torch.no_grad():
+        traj = Sampler(create_transport()).sample_ode(sampling_method="euler", num_steps=6)(x0.to(DEV), m.forward)
+        got = m.sample_euler(x0.to(DEV), num_steps=6)
+        got_traj = m.sample_euler(x0.to(DEV), num_steps=6, return_trajectory=True)
+        again = m.sample_euler(x0.to(DEV) * 1.0, num_steps=6)          # second call: pure replay
+    assert torch.equal(got, again) and torch.equal(got_traj[-1], got) and got_traj.shape == traj.shape
+    check_close(got, traj[-1], "whole-loop graph vs step-by-step sampler", atol=5e-5)
+    ocfg = dict(cfg, norm_epsilon=1e-5)
+    want = zo.sample_ode_fixed(lambda x, t: zo.zigma_forward(sd, ocfg, x, t), x0, num_steps=6)
+    check_close(got, want, "whole-loop graph Euler vs oracle", atol=5e-5)
+
+
 # ---- the other BASELINE.json configs at their real widths (parity-test cases, not bench lines) ---------------
 def _oracle_forward(cfg, sd, x, t, y=None):
     """CPU oracle with the plain-C scan (fp32): seconds at bs=1 even for L = 4096."""

@@ -160,3 +160,96 @@ def test_flat_params_and_ema_module_drop_a_stale_engine():
     em = opt.ema_module()
     assert isinstance(net._engine, NoCopy) and getattr(em, "_engine", None) is None
     assert torch.equal(em[0].weight, net[0].weight + 1.0) and not em[0].weight.requires_grad
+
+
+def test_optimizer_state_dict_round_trip_host_logic():
+    """FusedAdamWEMA.state_dict() has torch.optim.AdamW's layout (loads into a real AdamW) and load_state_dict restores the
+    moments, the step count and the EMA (host-side logic only: no kernel launch)."""
+    from zigma_b200.train import FlatParams, FusedAdamWEMA
+    net = _net()
+    flat = FlatParams(net)
+    opt = FusedAdamWEMA.__new__(FusedAdamWEMA)
+    opt.flat, opt.lr, opt.weight_decay, opt.betas, opt.eps, opt.ema_decay = flat, 3e-4, 0.01, (0.9, 0.999), 1e-8, 0.999
+    opt.exp_avg, opt.exp_avg_sq, opt.ema, opt.steps = torch.randn_like(flat.flat), torch.rand_like(flat.flat), flat.flat.clone() + 0.5, 17
+    sd = opt.state_dict()
+    ref_opt = torch.optim.AdamW([p for _, p in flat.named], lr=1.0)
+    ref_opt.load_state_dict({k: v for k, v in sd.items() if k != "ema_flat"})       # AdamW accepts the layout
+    st0 = ref_opt.state[flat.named[0][1]]
+    assert float(st0["step"]) == 17 and torch.equal(st0["exp_avg"], flat.view_of(opt.exp_avg, 0))
+    assert ref_opt.param_groups[0]["lr"] == 3e-4 and ref_opt.param_groups[0]["weight_decay"] == 0.01
+    opt2 = FusedAdamWEMA.__new__(FusedAdamWEMA)
+    opt2.flat, opt2.lr, opt2.weight_decay, opt2.betas, opt2.eps, opt2.ema_decay = flat, 0.0, 0.0, (0.5, 0.5), 1.0, 0.999
+    opt2.exp_avg, opt2.exp_avg_sq, opt2.ema, opt2.steps = torch.zeros_like(flat.flat), torch.zeros_like(flat.flat), torch.zeros_like(flat.flat), 0
+    opt2.load_state_dict(sd)
+    assert opt2.steps == 17 and opt2.lr == 3e-4 and opt2.betas == (0.9, 0.999)
+    for i in range(len(flat.named)):      # (the flat buffers have alignment padding between parameters: compare the views)
+        assert torch.equal(flat.view_of(opt2.exp_avg, i), flat.view_of(opt.exp_avg, i))
+        assert torch.equal(flat.view_of(opt2.exp_avg_sq, i), flat.view_of(opt.exp_avg_sq, i))
+    assert torch.equal(opt2.ema, opt.ema)
+    # a real AdamW state loads too (resuming a reference 'opt' entry)
+    real = torch.optim.AdamW([p for _, p in flat.named], lr=2e-4)
+    for _, p in flat.named:
+        p.grad = torch.ones_like(p)
+    real.step()
+    opt2.load_state_dict(real.state_dict())
+    assert opt2.steps == 1 and opt2.lr == 2e-4
+
+
+@pytest.mark.gpu
+def test_autocast_with_fp32_pos_embed_train_and_sample():
+    """bf16 autocast over fp32 master weights with use_pe=2 -- embed() returns fp32 tokens (bf16 linear +
+    fp32 pos_embed) while the adaLN chunks and the mixer output are bf16.  The block-tail kernels must not reinterpret the
+    mixed buffers: train step (fused tail, drop_path 0) and eval sampling both agree with the fp32 run to bf16 accuracy."""
+    from zigma_b200 import ZigMa
+    cfg = dict(img_dim=8, patch_size=1, in_channels=4, embed_dim=64, depth=3, scan_type="zigzagN8", use_pe=2, drop_path_rate=0.0)
+    torch.manual_seed(0)
+    m = ZigMa(device="cuda", **cfg)
+    with torch.no_grad():
+        for p in m.parameters():
+            if p.requires_grad and p.abs().sum() == 0:
+                p.normal_(0, 0.02)
+    x = torch.randn(3, 4, 8, 8, device="cuda")
+    t = torch.rand(3, device="cuda")
+    m.train()
+    ref = m(x, t)
+    ref.square().mean().backward()
+    g_ref = {n: p.grad.clone() for n, p in m.named_parameters() if p.grad is not None}
+    m.zero_grad()
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        out = m(x, t)
+        loss = out.float().square().mean()
+    loss.backward()
+    assert torch.isfinite(out.float()).all()
+    assert (out.float() - ref).abs().max() <= 5e-2 * max(1.0, ref.abs().max().item())
+    rels = []
+    for n, p in m.named_parameters():
+        if p.grad is not None and g_ref[n].abs().max() > 0:
+            rel = ((p.grad - g_ref[n]).norm() / g_ref[n].norm()).item()
+            assert torch.isfinite(p.grad).all() and rel < 0.4, (n, rel)     # (bf16 noise; garbage reads give rel >> 1 or NaN)
+            rels.append(rel)
+    assert sorted(rels)[len(rels) // 2] < 0.05, sorted(rels)
+    m.eval()
+    with torch.no_grad():
+        want = m(x, t)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            got = m(x, t)
+    assert torch.isfinite(got.float()).all()
+    assert (got.float() - want).abs().max() <= 5e-2 * max(1.0, want.abs().max().item())
+
+
+@pytest.mark.gpu
+def test_engine_not_used_for_layernorm_models():
+    """rms_norm=False builds nn.LayerNorm blocks; the RMSNorm-only sampling engine must not run them."""
+    from zigma_b200 import ZigMa
+    cfg = dict(img_dim=8, patch_size=1, in_channels=4, embed_dim=64, depth=2, scan_type="zigzagN8", use_pe=0, rms_norm=False)
+    torch.manual_seed(0)
+    m = ZigMa(device="cuda", **cfg).eval()
+    with torch.no_grad():
+        for p in m.parameters():
+            if p.requires_grad and p.abs().sum() == 0:
+                p.normal_(0, 0.02)
+        x, t = torch.randn(2, 4, 8, 8, device="cuda"), torch.rand(2, device="cuda")
+        got = m(x, t)
+        want = m.forward_autograd(x, t)
+    assert m._engine is None
+    assert torch.allclose(got, want, rtol=1e-5, atol=1e-6)

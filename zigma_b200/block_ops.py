@@ -28,6 +28,14 @@ class BlockTailFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, mix, gate, shift, scale, norm_w, residual, rowmap, eps):
         x, mix, residual = _contig(x), _contig(mix), _contig(residual)
+        # one dtype for every operand of the kernels (x's): see engine.block_tail.  The casts happen HERE so that the
+        # tensors saved for the backward are the ones the forward kernel actually read.
+        ctx.in_dtypes = tuple(None if t is None else t.dtype for t in (mix, gate, shift, scale))
+        cast = lambda t: t if (t is None or t.dtype == x.dtype) else t.to(x.dtype)
+        mix, gate, shift, scale = cast(mix), cast(gate), cast(shift), cast(scale)
+        mods = [m for m in (gate, shift, scale) if m is not None]
+        if mods and any(m.stride(0) != mods[0].stride(0) or m.stride(1) != 1 for m in mods):
+            gate, shift, scale = [None if m is None else m.contiguous() for m in (gate, shift, scale)]
         res_out, normed, modded, rstd = block_tail(x, mix, gate, shift, scale, norm_w, residual, rowmap, eps, want_rstd=True)
         ctx.save_for_backward(res_out, rstd, mix, gate, scale, norm_w, rowmap)
         ctx.has_res = residual is not None
@@ -56,8 +64,9 @@ class BlockTailFn(torch.autograd.Function):
         q.mod_rs = scale.stride(0)
         q.batch, q.seqlen, q.dim, q.dtype, q.nparts = B, L, D, _lib.dt(act), nparts
         _lib.call("zg_block_tail_bwd", q)
-        return (d_x, d_mix, acc[0].to(act) if mix is not None else None, acc[1].to(act), acc[2].to(act), d_w.sum(0).to(norm_w.dtype),
-                d_res_in, None, None)
+        dt_mix, dt_gate, dt_shift, dt_scale = ctx.in_dtypes
+        return (d_x, None if d_mix is None else d_mix.to(dt_mix), acc[0].to(dt_gate) if mix is not None else None,
+                acc[1].to(dt_shift or act), acc[2].to(dt_scale or act), d_w.sum(0).to(norm_w.dtype), d_res_in, None, None)
 
 
 def block_tail_fn(x, mix, gate, shift, scale, norm_w, residual, rowmap, eps):

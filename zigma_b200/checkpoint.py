@@ -24,9 +24,11 @@ def load_reference_checkpoint(model, path_or_dict, which="ema", strict=True):
     return out
 
 
-def save_reference_checkpoint(path, model, ema_model=None, opt_state=None, args=None, ddp_prefix=False):
-    """Writes the dictionary train_acc.py:492-503 writes ({"model", "ema", "opt", "args"})."""
+def save_reference_checkpoint(path, model, ema_model=None, opt_state=None, args=None, ddp_prefix=False, train_steps=0, best_fid=None):
+    """Writes the dictionary train_acc.py:492-503 writes ({"model", "ema", "opt", "args", "train_steps", "best_fid"}).
+    ``opt_state``: ``optimizer.state_dict()`` -- ``FusedAdamWEMA.state_dict()`` emits torch.optim.AdamW's layout."""
     pre = (lambda sd: {"module." + k: v for k, v in sd.items()}) if ddp_prefix else (lambda sd: dict(sd))
-    ck = {"model": pre(model.state_dict()), "ema": pre((ema_model or model).state_dict()), "opt": opt_state, "args": args}
+    ck = {"model": pre(model.state_dict()), "ema": pre((ema_model or model).state_dict()), "opt": opt_state, "args": args,
+          "train_steps": int(train_steps), "best_fid": best_fid}
     torch.save(ck, path)
     return ck

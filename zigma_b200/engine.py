@@ -64,6 +64,24 @@ def block_tail(x, mix, gate, shift, scale, norm_w, residual, rowmap, eps, final=
             raise RuntimeError("block_tail: modulation views must share one row stride")
     if norm_w.dtype != x.dtype:
         norm_w = norm_w.to(x.dtype)
+    # the kernel reads every operand with ONE dtype (x's).  Under bf16 autocast with fp32 master weights the tokens can be
+    # fp32 (embed() adds an fp32 pos_embed) while the adaLN chunks and the mixer output are bf16: bring them to x.dtype
+    # instead of letting the kernel reinterpret the buffers.
+    def _as_x(t):
+        return t if (t is None or t.dtype == x.dtype) else t.to(x.dtype)
+    mix = _as_x(mix)
+    if mix is not None and not mix.is_contiguous():
+        mix = mix.contiguous()
+    if any(m is not None and m.dtype != x.dtype for m in (gate, shift, scale)):
+        # re-materialise the three views in x.dtype with one common row stride
+        D_ = x.shape[-1]
+        packed = torch.zeros((x.shape[0] // mod_div if mod_div != 1 else x.shape[0], 3 * D_), dtype=x.dtype, device=x.device)
+        for i_, m in enumerate((gate, shift, scale)):
+            if m is not None:
+                packed[:, i_ * D_:(i_ + 1) * D_] = m
+        gate = None if gate is None else packed[:, :D_]
+        shift = None if shift is None else packed[:, D_:2 * D_]
+        scale = None if scale is None else packed[:, 2 * D_:]
     if residual is not None and residual.dtype != torch.float32:
         raise RuntimeError("block_tail: the residual stream must be fp32 (residual_in_fp32=True)")
     res_out = torch.empty((Bt, L, D), dtype=torch.float32, device=x.device) if not final else None
@@ -273,3 +291,60 @@ class ZigMaEngine:
             sy.copy_(y)
         graph.replay()
         return sout.clone()
+
+    @torch.no_grad()
+    def sample_euler(self, x0, ts, y=None, return_trajectory=False, dts=None):
+        """Fixed-grid Euler integration x_{i+1} = x_i + (t_{i+1} - t_i) * model(x_i, t_i) over the grid ``ts`` -- what
+        ``Sampler.sample_ode(sampling_method="euler")`` makes torchdiffeq do for a velocity model on the linear path
+        (transport/integrators.py:105-123, transport.py:372-417) -- with the WHOLE loop captured as one CUDA graph: the
+        time vector is filled in-graph (one fill per step with the step's constant), the update runs in-graph, nothing is
+        copied or cloned between the steps.  Returns the final state (or the (len(ts), ...) trajectory)."""
+        if self._versions != self._param_versions():
+            self.refresh()
+        ts = [float(v) for v in ts]
+        dts = [b - a for a, b in zip(ts, ts[1:])] if dts is None else [float(v) for v in dts]   # (fp32 differences of an fp32 grid, if given)
+        key = ("euler", tuple(x0.shape), x0.dtype, tuple(ts), tuple(dts), None if y is None else (tuple(y.shape), y.dtype), bool(return_trajectory))
+        g = self._graphs.get(key)
+        if g is None:
+            sx, sy = x0.clone(), None if y is None else y.clone()
+            tvec = torch.empty(x0.shape[0], device=x0.device, dtype=x0.dtype)
+
+            def loop():
+                x, traj = sx, [sx]
+                for t0, dt in zip(ts, dts):
+                    tvec.fill_(t0)
+                    x = torch.add(x, self._forward_impl(x, tvec, sy), alpha=dt)
+                    if return_trajectory:
+                        traj.append(x)
+                return torch.stack(traj, 0) if return_trajectory else x
+            if not self.use_graph:
+                return loop_eager(self, x0, ts, dts, y, return_trajectory)
+            s = torch.cuda.Stream()
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                tvec.fill_(ts[0])
+                for _ in range(2):
+                    self._forward_impl(sx, tvec, sy)          # warm-up: kernel attributes, workspaces
+            torch.cuda.current_stream().wait_stream(s)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                sout = loop()
+            g = (graph, sx, sy, sout)
+            self._graphs[key] = g
+        graph, sx, sy, sout = g
+        sx.copy_(x0)
+        if y is not None:
+            sy.copy_(y)
+        graph.replay()
+        return sout.clone()
+
+
+def loop_eager(engine, x0, ts, dts, y, return_trajectory):
+    x, traj = x0, [x0]
+    tvec = torch.empty(x0.shape[0], device=x0.device, dtype=x0.dtype)
+    for t0, dt in zip(ts, dts):
+        tvec.fill_(t0)
+        x = torch.add(x, engine._forward_impl(x, tvec, y), alpha=dt)
+        if return_trajectory:
+            traj.append(x)
+    return torch.stack(traj, 0) if return_trajectory else x

@@ -395,13 +395,33 @@ class ZigMa(nn.Module):
     def forward(self, hidden_states, t, y=None):
         """x: (N, C, H, W) latents (video: (N, T, C, H, W)); t: (N,) timesteps; y: (N,) labels."""
         use_engine = (not torch.is_grad_enabled()) and (not self.training) and hidden_states.is_cuda \
-            and self.fused_add_norm and self.residual_in_fp32 and self.use_pe != 3 and not (self.has_text and self.video_frames > 0)
+            and self.fused_add_norm and self.residual_in_fp32 and self.use_pe != 3 and not (self.has_text and self.video_frames > 0) \
+            and self._engine_norms_ok()
         if use_engine:
             from .engine import ZigMaEngine
             if self._engine is None:
                 self._engine = ZigMaEngine(self)
             return self._engine.forward(hidden_states, t, y)
         return self.forward_autograd(hidden_states, t, y)
+
+    @torch.no_grad()
+    def sample_euler(self, x0, num_steps=50, y=None, t0=0.0, t1=1.0, return_trajectory=False):
+        """The flow-matching sampler's fixed-grid Euler loop over ``linspace(t0, t1, num_steps)`` (num_steps - 1 evaluations;
+        transport/integrators.py:83-123 with sampler_type "euler") as ONE CUDA-graph replay on the sampling engine."""
+        if self.training or not x0.is_cuda or not (self.fused_add_norm and self.residual_in_fp32 and self.use_pe != 3
+                                                  and not (self.has_text and self.video_frames > 0) and self._engine_norms_ok()):
+            raise RuntimeError("ZigMa.sample_euler: needs an eval-mode CUDA model the sampling engine supports")
+        from .engine import ZigMaEngine
+        if self._engine is None:
+            self._engine = ZigMaEngine(self)
+        grid = torch.linspace(t0, t1, num_steps)
+        return self._engine.sample_euler(x0, grid.tolist(), y, return_trajectory, dts=(grid[1:] - grid[:-1]).tolist())
+
+    def _engine_norms_ok(self):
+        """The engine's block-tail kernel is RMSNorm-only (no mean subtraction, no bias) and has no skip connection: a model
+        built with rms_norm=False (nn.LayerNorm) or with skip linears samples through forward_autograd instead."""
+        return (all(isinstance(b.norm, RMSNorm) and getattr(b, "skip_linear", None) is None for b in self.blocks)
+                and isinstance(self.norm_f, RMSNorm))
 
     def _fused_tail_ok(self, hidden_states):
         """The fused training loop (block_ops.BlockTailFn) covers the configuration every shipped config uses."""

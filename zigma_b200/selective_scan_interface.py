@@ -264,8 +264,8 @@ def _inner_fwd(xz, conv1d_weight, conv1d_bias, x_proj_weight, delta_proj_weight,
     R = delta_proj_weight.shape[1]
     N = A.shape[-1]
     if torch.is_autocast_enabled():
-        x_proj_weight = x_proj_weight.to(dtype=torch.get_autocast_gpu_dtype())
-        delta_proj_weight = delta_proj_weight.to(dtype=torch.get_autocast_gpu_dtype())
+        x_proj_weight = x_proj_weight.to(dtype=torch.get_autocast_dtype('cuda'))
+        delta_proj_weight = delta_proj_weight.to(dtype=torch.get_autocast_dtype('cuda'))
     if xz.stride(-1) != 1:
         xz = xz.contiguous()
     conv_w = conv1d_weight.reshape(conv1d_weight.shape[0], conv1d_weight.shape[-1])
@@ -377,8 +377,8 @@ class MambaInnerFn(torch.autograd.Function):
                 B_proj_bias=None, C_proj_bias=None, delta_softplus=True, checkpoint_lvl=1):
         assert checkpoint_lvl in [0, 1]
         if torch.is_autocast_enabled():
-            out_proj_weight = out_proj_weight.to(dtype=torch.get_autocast_gpu_dtype())
-            out_proj_bias = out_proj_bias.to(dtype=torch.get_autocast_gpu_dtype()) if out_proj_bias is not None else None
+            out_proj_weight = out_proj_weight.to(dtype=torch.get_autocast_dtype('cuda'))
+            out_proj_bias = out_proj_bias.to(dtype=torch.get_autocast_dtype('cuda')) if out_proj_bias is not None else None
         need_grad = any(t is not None and t.requires_grad for t in
                         (xz, conv1d_weight, conv1d_bias, x_proj_weight, delta_proj_weight, out_proj_weight,
                          out_proj_bias, A, B, C, D, delta_bias))
@@ -450,8 +450,8 @@ class MambaInnerTokFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, xz, conv1d_weight, conv1d_bias, x_proj_weight, delta_proj_weight, A, D, delta_bias, rowmap, bt, L):
         if torch.is_autocast_enabled():
-            x_proj_weight = x_proj_weight.to(dtype=torch.get_autocast_gpu_dtype())
-            delta_proj_weight = delta_proj_weight.to(dtype=torch.get_autocast_gpu_dtype())
+            x_proj_weight = x_proj_weight.to(dtype=torch.get_autocast_dtype('cuda'))
+            delta_proj_weight = delta_proj_weight.to(dtype=torch.get_autocast_dtype('cuda'))
         if not xz.is_contiguous():
             xz = xz.contiguous()
         conv_w = conv1d_weight.reshape(conv1d_weight.shape[0], conv1d_weight.shape[-1]).contiguous()

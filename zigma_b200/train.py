@@ -82,6 +82,10 @@ class GradSync:
         self.group = process_group
         self.world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
         self.overlap = overlap
+        if self.world > 1:
+            # what DDP / accelerate do at wrap time (the reference seeds every rank differently, train_acc.py:125, and relies on
+            # it): every replica starts from rank 0's weights.  The parameters are views of flat.flat, so one broadcast does it.
+            dist.broadcast(flat.flat, src=dist.get_global_rank(process_group, 0) if process_group is not None else 0, group=process_group)
         # buckets = contiguous ranges of the flat buffer, filled from the END (gradients arrive in reverse order)
         cap = max(1, int(bucket_mb * (1 << 20) / 4))
         self.buckets, self.bucket_of = [], [0] * len(flat.named)
@@ -160,6 +164,45 @@ class FusedAdamWEMA:
 
     def zero_grad(self):
         self.flat.zero_grad()
+
+    def resync_ema(self):
+        """ema <- current weights (call after the weights were replaced, e.g. by GradSync's initial broadcast)."""
+        if self.ema is not None:
+            self.ema.copy_(self.flat.flat)
+
+    def state_dict(self):
+        """torch.optim.AdamW's layout (per-parameter 'step', 'exp_avg', 'exp_avg_sq' keyed by parameter index, one param
+        group) so a reference 'opt' checkpoint entry (train_acc.py:492-501) round-trips; plus the EMA as a flat tensor."""
+        state = {}
+        for i, (_, p) in enumerate(self.flat.named):
+            state[i] = {"step": torch.tensor(float(self.steps)), "exp_avg": self.flat.view_of(self.exp_avg, i).clone(),
+                        "exp_avg_sq": self.flat.view_of(self.exp_avg_sq, i).clone()}
+        group = {"lr": self.lr, "betas": tuple(self.betas), "eps": self.eps, "weight_decay": self.weight_decay, "amsgrad": False,
+                 "params": list(range(len(self.flat.named)))}
+        out = {"state": state, "param_groups": [group]}
+        if self.ema is not None:
+            out["ema_flat"] = self.ema.clone()
+        return out
+
+    def load_state_dict(self, sd):
+        state, groups = sd["state"], sd["param_groups"]
+        if len(state) not in (0, len(self.flat.named)):
+            raise ValueError(f"FusedAdamWEMA.load_state_dict: {len(state)} parameter states for {len(self.flat.named)} parameters")
+        steps = 0
+        with torch.no_grad():
+            for i in range(len(self.flat.named)):
+                st = state.get(i, state.get(str(i)))
+                if st is None:
+                    continue
+                self.flat.view_of(self.exp_avg, i).copy_(st["exp_avg"])
+                self.flat.view_of(self.exp_avg_sq, i).copy_(st["exp_avg_sq"])
+                steps = max(steps, int(float(st["step"])))
+            if sd.get("ema_flat") is not None and self.ema is not None:
+                self.ema.copy_(sd["ema_flat"])
+        self.steps = steps
+        if groups:
+            g = groups[0]
+            self.lr, self.betas, self.eps, self.weight_decay = g["lr"], tuple(g["betas"]), g["eps"], g["weight_decay"]
 
     def step(self, grad_scale=1.0, grad_scale_tensor=None):
         """grad_scale: host float (1/world, 1/loss_scale ...); grad_scale_tensor: optional fp32 device scalar multiplied
