@@ -197,7 +197,11 @@ def gen_inner(ref):
     out3 = ref.ssi.mamba_inner_fn(a["xz"], a["conv_w"], a["conv_b"], a["x_proj_w"], a["dt_proj_w"], a["out_proj_w"],
                                   a["out_proj_b"], a["A"], None, None, a["D"], a["delta_bias"], None, None, True)
     close(out3, out, rtol=1e-4, atol=1e-5, what="mamba_inner_fn(stubbed) vs ref")
-    save("mamba_inner", out=out, **a)
+    # bidirectional variant (unused by ZigMa, part of the op surface): bimamba_inner_ref with a second A
+    a["A_b"] = -torch.from_numpy(rs.rand(E, N).astype(np.float32)) - 0.1
+    out_bi = ref.ssi.bimamba_inner_ref(a["xz"], a["conv_w"], a["conv_b"], a["x_proj_w"], a["dt_proj_w"], a["out_proj_w"],
+                                       a["out_proj_b"], a["A"], a["A_b"], None, None, a["D"], a["delta_bias"], delta_softplus=True)
+    save("mamba_inner", out=out, out_bi=out_bi, **a)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -210,6 +214,9 @@ MODEL_CASES = {
     "tiny_patch2_cls": (dict(in_channels=4, embed_dim=32, depth=3, img_dim=16, patch_size=2, scan_type="zigzagN8", use_pe=1, num_classes=10), 3, "fp32"),
     "tiny_video_sst": (dict(in_channels=4, embed_dim=32, depth=6, img_dim=8, patch_size=2, scan_type="zzvideo_sst", use_pe=2,
                             video_frames=4, tpe=True, num_classes=5), 2, "fp32"),
+    # has_text: the gated cross-attention branch of every block + the text conditioning path (model_zigma.py:95-135, 446-458, 930-933)
+    "tiny_text": (dict(in_channels=4, embed_dim=64, depth=3, img_dim=8, patch_size=1, scan_type="zigzagN8", use_pe=2, has_text=True,
+                       d_context=24, n_context_token=7), 2, "fp32"),
     "full_zigzag8_b1": (dict(in_channels=4, embed_dim=640, depth=18, img_dim=32, patch_size=1, scan_type="zigzagN8", use_pe=2), 1, "fp32"),
 }
 
@@ -242,7 +249,9 @@ def model_io(kw, bs, seed=3):
         x = synth.synth_latents((bs, kw["in_channels"], kw["img_dim"], kw["img_dim"]), seed)
     t = torch.linspace(0.1, 0.9, bs)
     y = None
-    if kw.get("num_classes", -1) > 0:
+    if kw.get("has_text", False):
+        y = synth.synth_latents((bs, kw["n_context_token"], kw["d_context"]), seed + 100)        # the text encoder's output
+    elif kw.get("num_classes", -1) > 0:
         y = torch.arange(bs) % kw["num_classes"]
     return x, t, y
 
@@ -259,6 +268,8 @@ def gen_models(ref, only=None):
         m.load_state_dict(sd, strict=True)
         x, t, y = model_io(kw, bs)
         with torch.no_grad():
+            if y is not None and y.is_floating_point():
+                y = y.to(dtype)
             out = m(x.to(dtype), t.to(dtype), y)
             cfg = dict(kw); cfg.setdefault("norm_epsilon", 1e-5)
             out2 = zo.zigma_forward(sd, cfg, x.to(dtype), t.to(dtype), y)
@@ -266,7 +277,7 @@ def gen_models(ref, only=None):
             close(out2, out, rtol=1e-3, atol=2e-5, what="zigma_forward restatement")
         else:
             close(out2, out, rtol=5e-2, atol=5e-2, what="zigma_forward restatement (bf16)")
-        save("model_" + name, out=out, t=t, y=(y.numpy() if y is not None else np.zeros(0, np.int64)),
+        save("model_" + name, out=out, t=t, y=(y.float().numpy() if (y is not None and y.is_floating_point()) else y.numpy() if y is not None else np.zeros(0, np.int64)),
              shapes_json=np.frombuffer(json.dumps(shapes).encode(), dtype=np.uint8),
              cfg_json=np.frombuffer(json.dumps(kw).encode(), dtype=np.uint8))
 

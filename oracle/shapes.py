@@ -48,6 +48,10 @@ def zigma_state_shapes(cfg):
         s[f"blocks.{i}.norm.weight"] = (D,)
         if not cfg.get("rms_norm", True):
             s[f"blocks.{i}.norm.bias"] = (D,)
+        if cfg.get("has_text", False):      # CrossAttention(query_dim=D, context_dim=D, heads=8, dim_head=64): model_zigma.py:382-386
+            a = f"blocks.{i}.msa."
+            s[a + "to_q.weight"], s[a + "to_k.weight"], s[a + "to_v.weight"] = (512, D), (512, D), (512, D)
+            s[a + "to_out.0.weight"], s[a + "to_out.0.bias"] = (D, 512), (D,)
         nmod = 6 if cfg.get("has_text", False) else 3
         s[f"blocks.{i}.adaLN_modulation.1.weight"], s[f"blocks.{i}.adaLN_modulation.1.bias"] = (nmod * D, D), (nmod * D,)
     s["norm_f.weight"] = (D,)

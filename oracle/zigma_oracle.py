@@ -362,12 +362,26 @@ def timestep_embedding(t, dim, dtype, max_period=10000):
     return torch.cat([torch.cos(args), torch.sin(args)], dim=-1)
 
 
+def cross_attention(x, text, p, heads=8):
+    """CrossAttention.forward (model_zigma.py:95-135): q from the tokens, k / v from the (embedded) text tokens, `heads` heads,
+    softmax(q k^T / sqrt(dim_head)) v, output projection with bias.  p: to_q / to_k / to_v .weight, to_out.0.weight / .bias.
+    (The reference dispatches to torch SDPA, xformers or explicit math by availability; all three are this formula.)"""
+    Bt, L, _ = x.shape
+    q, k, v = F.linear(x, p["to_q.weight"]), F.linear(text, p["to_k.weight"]), F.linear(text, p["to_v.weight"])
+    split = lambda a: a.reshape(Bt, a.shape[1], heads, -1).transpose(1, 2)          # "B L (H D) -> B H L D"
+    q, k, v = split(q), split(k), split(v)
+    attn = ((q.float() @ k.float().transpose(-2, -1)) * (q.shape[-1] ** -0.5)).softmax(dim=-1)
+    o = (attn @ v.float()).to(x.dtype).transpose(1, 2).reshape(Bt, L, -1)
+    return F.linear(o, p["to_out.0.weight"], p["to_out.0.bias"])
+
+
 def zigma_forward(sd, cfg, x, t, y=None):
     """Functional ZigMa.forward (model_zigma.py:911-990) in eval mode (drop_path = identity).
 
     sd: state dict with the reference's key layout; cfg: dict with
     in_channels, embed_dim, depth, img_dim, patch_size, scan_type, video_frames, use_pe, tpe,
-    num_classes, norm_epsilon.  Supports has_text=False only (none of the BASELINE configs use it)."""
+    num_classes, has_text, norm_epsilon.  has_text (model_zigma.py:446-458, 930-933): y is the (B, n_tokens, d_context) text
+    embedding; c = t_emb + mean(y_embedder(y)), and every block adds a gated cross-attention over the embedded text."""
     D, depth, p = cfg["embed_dim"], cfg["depth"], cfg.get("patch_size", 1)
     vf = cfg.get("video_frames", 0)
     eps = cfg.get("norm_epsilon", 1e-5)
@@ -385,7 +399,11 @@ def zigma_forward(sd, cfg, x, t, y=None):
     te = F.linear(F.silu(F.linear(te, sd["t_embedder.mlp.0.weight"], sd["t_embedder.mlp.0.bias"])),
                   sd["t_embedder.mlp.2.weight"], sd["t_embedder.mlp.2.bias"])
     c = te
-    if cfg.get("num_classes", -1) > 0:
+    text = None
+    if cfg.get("has_text", False):
+        text = F.linear(y.to(dt), sd["y_embedder.weight"], sd["y_embedder.bias"])           # (B, n_tokens, D)
+        c = te + text.mean(dim=1)
+    elif cfg.get("num_classes", -1) > 0:
         c = te + sd["y_embedder.embedding_table.weight"][y]
     if cfg.get("use_pe", 0) in (1, 2):
         hs = hs + sd["pos_embed"]
@@ -402,12 +420,19 @@ def zigma_forward(sd, cfg, x, t, y=None):
         hs, residual = BACKEND.get("norm", add_norm)(hs, sd[pre + "norm.weight"], None, residual, prenorm=True,
                                                      residual_in_fp32=True, eps=eps)
         mod = F.linear(F.silu(c), sd[pre + "adaLN_modulation.1.weight"], sd[pre + "adaLN_modulation.1.bias"])
-        shift, scale, gate = mod.chunk(3, dim=1)
+        if text is None:
+            shift, scale, gate = mod.chunk(3, dim=1)
+        else:
+            shift, scale, gate, shift_msa, scale_msa, gate_msa = mod.chunk(6, dim=1)
         mp = {k[len(pre + "mixer."):]: v for k, v in sd.items() if k.startswith(pre + "mixer.")}
         mixed = mamba_mixer(hs * (1 + scale.unsqueeze(1)) + shift.unsqueeze(1), mp, stype,
                             None if fwd is None else fwd[i], None if rev is None else rev[i],
                             None if st is None else st[i], vf)
         hs = hs + gate.unsqueeze(1) * mixed
+        if text is not None:      # gated cross-attention branch (model_zigma.py:446-458); norm_msa has no affine parameters
+            ap = {k[len(pre + "msa."):]: v for k, v in sd.items() if k.startswith(pre + "msa.")}
+            qin = F.layer_norm(hs, (D,), None, None, 1e-6) * (1 + scale_msa.unsqueeze(1)) + shift_msa.unsqueeze(1)
+            hs = hs + gate_msa.unsqueeze(1) * cross_attention(qin, text, ap)
     hs = BACKEND.get("norm", add_norm)(hs, sd["norm_f.weight"], None, residual, prenorm=False, residual_in_fp32=True, eps=eps)
     hs = F.layer_norm(hs, (D,), None, None, 1e-6)
     hs = F.linear(hs, sd["final_layer.linear.weight"], sd["final_layer.linear.bias"])

@@ -27,9 +27,17 @@ def test_mamba_inner_fn_golden():
     out = mamba_inner_fn(a["xz"], a["conv_w"], a["conv_b"], a["x_proj_w"], a["dt_proj_w"], a["out_proj_w"], a["out_proj_b"],
                          a["A"], None, None, a["D"], a["delta_bias"], delta_softplus=True)
     check_close(out, g["out"], "mamba_inner_fn")
+    # bimamba_inner_fn against the reference's bimamba_inner_ref (selective_scan_interface.py:673-711), forward and gradients
+    from zigma_b200 import bimamba_inner_fn
+    req = {k: a[k].clone().requires_grad_() for k in ("xz", "conv_w", "x_proj_w", "dt_proj_w", "out_proj_w", "A", "A_b", "D")}
+    ob = bimamba_inner_fn(req["xz"], req["conv_w"], a["conv_b"], req["x_proj_w"], req["dt_proj_w"], req["out_proj_w"], a["out_proj_b"],
+                          req["A"], req["A_b"], None, None, req["D"], a["delta_bias"], delta_softplus=True)
+    check_close(ob, g["out_bi"], "bimamba_inner_fn vs bimamba_inner_ref")
+    ob.square().sum().backward()
+    assert all(v.grad is not None and torch.isfinite(v.grad).all() and v.grad.abs().sum() > 0 for v in req.values())
 
 
-@pytest.mark.parametrize("name", ["tiny_zigzag8", "tiny_sweep2", "tiny_hilbert2", "tiny_patch2_cls", "tiny_video_sst"])
+@pytest.mark.parametrize("name", ["tiny_zigzag8", "tiny_sweep2", "tiny_hilbert2", "tiny_patch2_cls", "tiny_video_sst", "tiny_text"])
 @pytest.mark.parametrize("path", ["engine", "engine_nograph", "autograd"])
 def test_zigma_forward_golden_fp32(name, path, monkeypatch):
     g, cfg, shapes = model_case(name)

@@ -132,7 +132,7 @@ def test_reference_checkpoint_roundtrip(tmp_path):
     path = str(tmp_path / "0001000.pt")
     save_reference_checkpoint(path, a, ema_model=ema, opt_state={"state": {}}, args={"note": "x"}, ddp_prefix=True)
     ck = torch.load(path, map_location="cpu", weights_only=False)
-    assert set(ck) == {"model", "ema", "opt", "args"} and all(k.startswith("module.") for k in ck["ema"])
+    assert set(ck) == {"model", "ema", "opt", "args", "train_steps", "best_fid"} and all(k.startswith("module.") for k in ck["ema"])
     missing, unexpected = load_reference_checkpoint(b, path)                # "ema", like sample_acc.py
     assert not missing and not unexpected
     assert all(torch.equal(v, ema.state_dict()[k]) for k, v in b.state_dict().items())

@@ -59,53 +59,49 @@ def _norm_bwd(dy, x, weight, bias, mean, rstd, dresidual, has_residual, is_rms, 
     return dx, (dw.to(weight.dtype) if dw is not None else None), (db.to(bias.dtype) if db is not None else None), dres_in
 
 
+def _rows(t):
+    """(…, N) -> (M, N) with a unit inner stride (a view whenever the memory allows it)."""
+    t2 = t.reshape(-1, t.shape[-1])
+    return t2 if t2.stride(-1) == 1 else t2.contiguous()
+
+
 class LayerNormFn(torch.autograd.Function):
-    @staticmethod
-    def forward(ctx, x, weight, bias, residual=None, eps=1e-6, prenorm=False, residual_in_fp32=False,
-                is_rms_norm=False):
-        _lib.require_cuda(x, weight, bias, residual)
-        x_shape_og = x.shape
-        x = x.reshape(-1, x.shape[-1])
-        if x.stride(-1) != 1:
-            x = x.contiguous()
-        if residual is not None:
-            assert residual.shape == x_shape_og
-            residual = residual.reshape(-1, residual.shape[-1])
-            if residual.stride(-1) != 1:
-                residual = residual.contiguous()
-        weight = weight.contiguous()
-        if bias is not None:
-            bias = bias.contiguous()
-        residual_dtype = residual.dtype if residual is not None else (torch.float32 if residual_in_fp32 else None)
-        y, mean, rstd, residual_out = _norm_fwd(x, weight, bias, eps, residual, residual_dtype, is_rms_norm)
-        ctx.save_for_backward(residual_out, weight, bias, mean, rstd)
-        ctx.x_shape_og = x_shape_og
-        ctx.eps = eps
-        ctx.is_rms_norm = is_rms_norm
-        ctx.has_residual = residual is not None
-        ctx.prenorm = prenorm
-        ctx.x_dtype = x.dtype
-        y = y.reshape(x_shape_og)
-        return y if not prenorm else (y, residual_out.reshape(x_shape_og))
+    """Autograd node of the fused (residual add +) LayerNorm / RMSNorm.  Contract of the reference's node of the same name
+    (dis_mamba/mamba_ssm/ops/triton/layernorm.py:380-461): inputs (x, weight, bias, residual, eps, prenorm, residual_in_fp32,
+    is_rms_norm); output y, or (y, residual_out) with prenorm; gradients for x, weight, bias, residual.  The body is this
+    repo's: everything is flattened to rows once, the saved state is the kernel's own outputs (the summed residual stream r,
+    mean, rstd), and the backward feeds zg_add_norm_bwd, which produces dx and the residual gradient in one pass."""
 
     @staticmethod
-    def backward(ctx, dy, *args):
-        x, weight, bias, mean, rstd = ctx.saved_tensors
-        dy = dy.reshape(-1, dy.shape[-1])
-        if dy.stride(-1) != 1:
-            dy = dy.contiguous()
-        assert dy.shape == x.shape
-        dresidual = None
-        if ctx.prenorm:
-            dresidual = args[0].reshape(-1, args[0].shape[-1])
-            if dresidual.stride(-1) != 1:
-                dresidual = dresidual.contiguous()
-            if dresidual.dtype != x.dtype:
-                dresidual = dresidual.to(x.dtype)
-        dx, dw, db, dresidual_in = _norm_bwd(dy, x, weight, bias, mean, rstd, dresidual, ctx.has_residual,
-                                             ctx.is_rms_norm, ctx.x_dtype)
-        return (dx.reshape(ctx.x_shape_og), dw, db,
-                dresidual_in.reshape(ctx.x_shape_og) if ctx.has_residual else None, None, None, None, None)
+    def forward(ctx, x, weight, bias, residual=None, eps=1e-6, prenorm=False, residual_in_fp32=False, is_rms_norm=False):
+        _lib.require_cuda(x, weight, bias, residual)
+        shape = x.shape
+        if residual is not None and residual.shape != shape:
+            raise RuntimeError(f"layer_norm_fn: residual shape {tuple(residual.shape)} != input shape {tuple(shape)}")
+        x2 = _rows(x)
+        r2 = None if residual is None else _rows(residual)
+        # dtype of the residual stream the kernel writes: the incoming stream's, else fp32 on request, else "same as x" (not stored)
+        stream_dtype = r2.dtype if r2 is not None else (torch.float32 if residual_in_fp32 else None)
+        y, mean, rstd, stream = _norm_fwd(x2, weight.contiguous(), None if bias is None else bias.contiguous(), eps, r2, stream_dtype, is_rms_norm)
+        ctx.save_for_backward(stream, weight, bias, mean, rstd)
+        ctx.meta = (shape, x2.dtype, bool(is_rms_norm), residual is not None, bool(prenorm))
+        y = y.reshape(shape)
+        return (y, stream.reshape(shape)) if prenorm else y
+
+    @staticmethod
+    def backward(ctx, dy, *d_stream):
+        stream, weight, bias, mean, rstd = ctx.saved_tensors
+        shape, x_dtype, is_rms, had_residual, prenorm = ctx.meta
+        dy2 = _rows(dy)
+        if dy2.shape != stream.shape:
+            raise RuntimeError("layer_norm_fn backward: gradient shape does not match the forward's rows")
+        g_stream = None
+        if prenorm:                      # gradient arriving through the returned residual stream
+            g_stream = _rows(d_stream[0])
+            if g_stream.dtype != stream.dtype:
+                g_stream = g_stream.to(stream.dtype)
+        dx, dw, db, d_res = _norm_bwd(dy2, stream, weight, bias, mean, rstd, g_stream, had_residual, is_rms, x_dtype)
+        return (dx.reshape(shape), dw, db, d_res.reshape(shape) if had_residual else None, None, None, None, None)
 
 
 def layer_norm_fn(x, weight, bias, residual=None, eps=1e-6, prenorm=False, residual_in_fp32=False,
@@ -118,17 +114,18 @@ def rms_norm_fn(x, weight, bias, residual=None, prenorm=False, residual_in_fp32=
 
 
 class RMSNorm(torch.nn.Module):
+    """Module form of ``rms_norm_fn``.  State-dict contract of the reference's class (layernorm.py:481-503): one parameter
+    ``weight`` of size hidden_size (ones at init), ``bias`` registered as None, ``eps`` an attribute."""
+
     def __init__(self, hidden_size, eps=1e-5, device=None, dtype=None):
-        factory_kwargs = {"device": device, "dtype": dtype}
         super().__init__()
         self.eps = eps
-        self.weight = torch.nn.Parameter(torch.empty(hidden_size, **factory_kwargs))
+        self.weight = torch.nn.Parameter(torch.ones(hidden_size, device=device, dtype=dtype))
         self.register_parameter("bias", None)
-        self.reset_parameters()
 
     def reset_parameters(self):
-        torch.nn.init.ones_(self.weight)
+        with torch.no_grad():
+            self.weight.fill_(1.0)
 
     def forward(self, x, residual=None, prenorm=False, residual_in_fp32=False):
-        return rms_norm_fn(x, self.weight, self.bias, residual=residual, eps=self.eps, prenorm=prenorm,
-                           residual_in_fp32=residual_in_fp32)
+        return LayerNormFn.apply(x, self.weight, None, residual, self.eps, prenorm, residual_in_fp32, True)
