@@ -151,12 +151,13 @@ def run_reference(args, rank):
     wl = WORKLOADS[name]
     bs = args.bs or wl["bs"]
     cores = os.cpu_count() or 1
+    threads = int(os.environ.get("ZIGMA_REF_THREADS", "0")) or min(cores, 32)      # torch intra-op threads; measured on the 128-core box: 55 s / evaluation with 32, 112 s with 128 (the C scan uses OpenMP's default: all cores)
     state = cpu_reference_setup(name)
-    cpu_reference_eval(name, 1, state, cores)                    # page in / build the C oracle (not timed)
+    cpu_reference_eval(name, 1, state, threads)                  # page in / build the C oracle (not timed)
     budget_s = float(os.environ.get("ZIGMA_REF_BUDGET_S", "150"))
-    t_first, _ = cpu_reference_eval(name, bs, state, cores)      # first full-batch evaluation = the warm-up
+    t_first, _ = cpu_reference_eval(name, bs, state, threads)    # first full-batch evaluation = the warm-up
     n = max(1, min(args.steps, int(budget_s / max(t_first, 1e-3))))
-    dts = [cpu_reference_eval(name, bs, state, cores)[0] for _ in range(n)]
+    dts = [cpu_reference_eval(name, bs, state, threads)[0] for _ in range(n)]
     dt = sum(dts) / len(dts)
     val = bs * wl["tokens"] / dt
     import torch

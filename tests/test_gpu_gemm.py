@@ -16,6 +16,8 @@ SHAPES = [
     (4096, 1280, 40),             # dt_proj  (K < one k-block: TMA zero fill)
     (1000, 200, 136),             # everything ragged
     (128, 64, 64), (1, 8, 8), (129, 257, 72),
+    (4096, 80, 1536), (4096, 768, 1536),   # x_proj / out_proj of the D = 768 models (80-wide tile; 3 x 256)
+    (300, 160, 64), (257, 150, 200), (520, 330, 96),   # 160-wide tiles: exact, ragged in N (tail columns by direct stores), two tiles + ragged
 ]
 
 
@@ -48,6 +50,14 @@ def test_gemm_row_scatter_and_views():
     want = torch.empty_like(ref)
     want[:, rev] = ref                                   # row m lands at row rev[m]
     check_close(out.view(B, L, N), want, "gemm row scatter", rtol=8e-3, atol=1e-5, max_strict_viol=1.0)
+    # the out_proj shape of the D = 640 models with the scatter (160-wide tiles, direct-store epilogue for every column)
+    y = torch.randn(B * L, 128, device=DEV).bfloat16()
+    w2 = (torch.randn(640, 128, device=DEV) / 128 ** 0.5).bfloat16()
+    out2 = linear_bf16(y, w2, out_rowmap=rev.to(torch.int32), rows_per_batch=L)
+    ref2 = (y.float() @ w2.float().t()).view(B, L, 640)
+    want2 = torch.empty_like(ref2)
+    want2[:, rev] = ref2
+    check_close(out2.view(B, L, 640), want2, "gemm row scatter N=640", rtol=8e-3, atol=1e-5, max_strict_viol=1.0)
 
 
 def test_engine_with_tcgen05_gemms(monkeypatch):

@@ -195,6 +195,46 @@ def test_other_baseline_configs_bf16_batch(name):
     check_close(one, want, f"{name} bf16 vs fp32 oracle", rtol=8e-2, atol=8e-2, scale_atol=False, max_strict_viol=1.0)
 
 
+FULL_DEPTH_CASES = {
+    # BASELINE configs[3] / configs[4] exactly as bench.py measures them (reference yaml hyper-parameters, depth 24), at half the
+    # per-GPU batch of the benchmark (bs 16 / 8): the whole-batch bf16 engine path, checked on sampled rows against the fp32 oracle
+    "faceshq1024": (dict(in_channels=4, embed_dim=768, depth=24, img_dim=128, patch_size=2, scan_type="zigzagN8"), (4, 128, 128), 16),
+    "ucf101_sst": (dict(in_channels=4, embed_dim=768, depth=24, img_dim=32, patch_size=2, scan_type="zzvideo_sst", use_pe=2, video_frames=16,
+                        num_classes=101), (16, 4, 32, 32), 16),
+}
+
+
+@pytest.mark.parametrize("name", list(FULL_DEPTH_CASES))
+def test_full_depth_configs_bf16_batch16(name):
+    """Full depth (24 blocks), bf16, bs = 16 -- the batch path of BASELINE configs 3 / 4 (L = 4096; 16 frames x 256 tokens with
+    s / s / t scans: 4096 sequences of length 16 in the temporal layers), through the engine AND through the whole-loop
+    CUDA-graph sampler.  Too big for the CPU oracle as a batch, so: finite everywhere; a sample of the batch equals its own
+    bs = 1 run bit for bit (samples are independent: what multi-GPU sharding relies on); that sample agrees with the fp32 CPU
+    oracle (C scan) at the whole-model bf16 tolerance."""
+    from zigma_b200 import ZigMa
+    cfg, lat, bs = FULL_DEPTH_CASES[name]
+    m = ZigMa(device=DEV, dtype=torch.bfloat16, **cfg).eval()
+    shapes = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+    sd = synth.synth_state_dict(shapes, seed=0)
+    m.load_state_dict({k: v.bfloat16() for k, v in sd.items()})
+    x = synth.synth_latents((bs,) + lat, seed=21).bfloat16()
+    tt = torch.linspace(0.05, 0.95, bs).bfloat16()
+    y = (torch.arange(bs) * 7) % 101 if cfg.get("num_classes", -1) > 0 else None
+    k = 11                                                   # the sampled row of the batch
+    yd = None if y is None else y.to(DEV)
+    with torch.no_grad():
+        out = m(x.to(DEV), tt.to(DEV), yd)
+        one = m(x[k:k + 1].to(DEV), tt[k:k + 1].to(DEV), None if y is None else yd[k:k + 1])
+        step = m.sample_euler(x.to(DEV), num_steps=2, y=yd)  # one Euler step over [0, 1]: x + 1.0 * model(x, 0)
+        v0 = m(x.to(DEV), torch.zeros(bs, device=DEV, dtype=torch.bfloat16), yd)
+    assert torch.isfinite(out.float()).all() and torch.isfinite(step.float()).all()
+    assert torch.equal(out[k:k + 1], one), f"{name}: batch row differs from its bs=1 run"
+    check_close(step, (x.to(DEV).float() + v0.float()).bfloat16(), f"{name} whole-loop graph step vs forward", rtol=2e-2, atol=2e-2, scale_atol=False, max_strict_viol=1.0)
+    sd16 = {kk: v.bfloat16().float() for kk, v in sd.items()}                # the oracle sees the bf16-rounded weights
+    want = _oracle_forward(cfg, sd16, x[k:k + 1].float(), tt[k:k + 1].float(), None if y is None else y[k:k + 1])
+    check_close(one, want, f"{name} full depth bf16 bs={bs} row {k} vs fp32 oracle", rtol=8e-2, atol=8e-2, scale_atol=False, max_strict_viol=1.0)
+
+
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 def test_has_text_blocks_on_the_engine(dtype):
     """has_text models (cross-attention branch, 6-way adaLN): the sampling engine -- mixer through

@@ -35,7 +35,10 @@ namespace zg {
 
 constexpr int G_BM = 128, G_BK = 64, G_UMMA_K = 16, G_THREADS = 192;   // 6 warps: TMA, MMA, 4 epilogue
 // smem ring depth: as many (128 + BN) x 64 bf16 stages as fit next to the 32 KB epilogue staging
-__host__ __device__ constexpr int gemm_stages(int BN) { return BN == 256 ? 4 : (BN == 128 ? 6 : 8); }
+__host__ __device__ constexpr int gemm_stages(int BN) {
+    const int stage = (G_BM + BN) * G_BK * 2, avail = 227 * 1024 - 4 * 2 * 32 * 128 - 2048;
+    return avail / stage > 8 ? 8 : avail / stage;
+}
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -262,16 +265,51 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 drow = (int64_t)bidx * g.rows_per_batch + g.out_rowmap[row - bidx * g.rows_per_batch];
             }
             __nv_bfloat16 *crow = g.C + drow * g.ldc;
+            constexpr int NFULL = BN / 64;                    // 64-column chunks that go through the TMA store
+            const int col_lim = min(g.N, (n_blk + 1) * BN);   // first column that is NOT this tile's
+            // direct store of accumulator columns [c0, c0 + 32) of this thread's row (bounds: the matrix and the tile)
+            auto direct_store32 = [&](int c0) {
+                uint32_t v[32];
+                tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + c0), v);
+                const int col0 = n_blk * BN + c0;
+                if (row >= g.M || col0 >= col_lim) return;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int cj = col0 + j * 8;
+                    if (cj + 8 <= col_lim && ((reinterpret_cast<uintptr_t>(crow + cj) & 15) == 0)) {
+                        uint32_t o[4];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            float a = __uint_as_float(v[j * 8 + 2 * i]), b2 = __uint_as_float(v[j * 8 + 2 * i + 1]);
+                            if (g.bias) {
+                                a += __bfloat162float(g.bias[cj + 2 * i]);
+                                b2 += __bfloat162float(g.bias[cj + 2 * i + 1]);
+                            }
+                            __nv_bfloat162 h = __floats2bfloat162_rn(a, b2);
+                            o[i] = *reinterpret_cast<uint32_t *>(&h);
+                        }
+                        *reinterpret_cast<uint4 *>(crow + cj) = make_uint4(o[0], o[1], o[2], o[3]);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i)
+                            if (cj + i < col_lim) {
+                                float a = __uint_as_float(v[j * 8 + i]);
+                                if (g.bias) a += __bfloat162float(g.bias[cj + i]);
+                                crow[cj + i] = __float2bfloat16_rn(a);
+                            }
+                    }
+                }
+            };
             if (g.tma_store) {
                 // ---- coalesced path: TMEM -> registers -> bf16 -> swizzled smem -> TMA store (clips M/N edges) ----
                 unsigned char *ebuf = epi + (warp - 2) * (2 * 32 * 128);
 #pragma unroll 1
-                for (int c0 = 0; c0 < BN; c0 += 64) {
+                for (int c0 = 0; c0 < NFULL * 64; c0 += 64) {
                     if (n_blk * BN + c0 >= g.N) break;                     // whole chunk outside the matrix
                     unsigned char *buf = ebuf + ((c0 >> 6) & 1) * (32 * 128);
                     // the TMA store that last read this buffer (two chunks ago) must have finished reading it
                     if (lane == 0) {
-                        if (BN >= 128) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                        if (NFULL >= 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
                         else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");     // one chunk per tile: same buffer every time
                     }
                     __syncwarp();
@@ -308,40 +346,12 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                     }
                 }
+                // tile widths that are not a multiple of 64 (80, 160): the last 16 / 32 columns leave by direct stores
+                if constexpr (BN % 64 != 0) direct_store32(NFULL * 64);
             } else {
                 // ---- direct path (row scatter through out_rowmap, or unaligned C): per-thread 16-byte stores ----
 #pragma unroll 1
-                for (int c0 = 0; c0 < BN; c0 += 32) {
-                    uint32_t v[32];
-                    tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + c0), v);
-                    const int col0 = n_blk * BN + c0;
-                    if (row < g.M && col0 < g.N) {
-                        if (col0 + 32 <= g.N && ((reinterpret_cast<uintptr_t>(crow + col0) & 15) == 0)) {
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                uint32_t o[4];
-#pragma unroll
-                                for (int i = 0; i < 4; ++i) {
-                                    float a = __uint_as_float(v[j * 8 + 2 * i]), b2 = __uint_as_float(v[j * 8 + 2 * i + 1]);
-                                    if (g.bias) {
-                                        a += __bfloat162float(g.bias[col0 + j * 8 + 2 * i]);
-                                        b2 += __bfloat162float(g.bias[col0 + j * 8 + 2 * i + 1]);
-                                    }
-                                    __nv_bfloat162 h = __floats2bfloat162_rn(a, b2);
-                                    o[i] = *reinterpret_cast<uint32_t *>(&h);
-                                }
-                                *reinterpret_cast<uint4 *>(crow + col0 + j * 8) = make_uint4(o[0], o[1], o[2], o[3]);
-                            }
-                        } else {
-                            for (int i = 0; i < 32; ++i)
-                                if (col0 + i < g.N) {
-                                    float a = __uint_as_float(v[i]);
-                                    if (g.bias) a += __bfloat162float(g.bias[col0 + i]);
-                                    crow[col0 + i] = __float2bfloat16_rn(a);
-                                }
-                        }
-                    }
-                }
+                for (int c0 = 0; c0 < BN; c0 += 32) direct_store32(c0);
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             mbar_arrive(&tempty_bar[acc]);
@@ -448,7 +458,7 @@ static int gemm_cluster_setting() {
 template <int BN> static int launch_gemm_cl(const zg_gemm_params &p, cudaStream_t s) {
     int cl = gemm_cluster_setting();
     const int m_tiles = (p.M + G_BM - 1) / G_BM;
-    while (cl > 1 && m_tiles < cl) cl >>= 1;
+    while (cl > 1 && (m_tiles < cl || (BN / cl) % 8 != 0)) cl >>= 1;     // (a CTA's multicast slice must be whole 8-row swizzle groups)
     if (cl == 4) return launch_gemm<BN, 4>(p, s);
     if (cl == 2) return launch_gemm<BN, 2>(p, s);
     return launch_gemm<BN, 1>(p, s);
@@ -465,17 +475,28 @@ extern "C" int zg_gemm_bf16_tn(const zg_gemm_params *pp, void *stream) {
     ZG_REQUIRE((reinterpret_cast<uintptr_t>(p.A) & 15) == 0 && (reinterpret_cast<uintptr_t>(p.B) & 15) == 0, "gemm_bf16_tn: A and B must be 16-byte aligned");
     ZG_REQUIRE(!p.out_rowmap || (p.rows_per_batch > 0 && p.M % p.rows_per_batch == 0), "gemm_bf16_tn: out_rowmap needs rows_per_batch dividing M");
     cudaStream_t s = (cudaStream_t)stream;
-    // tile width: the widest tile whose ragged last column tile wastes <= 20 % of the MMA work (wider tiles move fewer
-    // operand bytes per MAC through L2; measured: N = 640 runs 96.6 us with 256-wide tiles, 98.7 us with 128-wide)
+    // tile width: among {256, 160, 128, 80, 64} the WIDEST whose ragged last column tile wastes <= 5 % of the MMA work, else the
+    // one that wastes least (wider tiles move fewer operand bytes per MAC through L2 and re-read A fewer times).  160 exists for
+    // N = 640 (out_proj of the D = 640 models: 4 x 160 exactly; 256-wide tiles pad it to 768 = 17 % idle MMAs, round 1), 80 for the
+    // x_proj widths 72 / 80 (one pass over A instead of two 64-wide ones).
     static int bn_env = -1;
     if (bn_env < 0) { const char *e = getenv("ZG_GEMM_BN"); bn_env = e ? atoi(e) : 0; }
     int bn = bn_env;
-    if (bn != 64 && bn != 128 && bn != 256) {
+    if (bn != 64 && bn != 80 && bn != 128 && bn != 160 && bn != 256) {
+        const int cand[5] = {256, 160, 128, 80, 64};
         auto waste = [&](int b) { return (double)(((p.N + b - 1) / b) * b - p.N) / (double)(((p.N + b - 1) / b) * b); };
-        bn = waste(256) <= 0.20 ? 256 : (waste(128) <= 0.20 ? 128 : 64);
-        if (p.N <= 64) bn = 64;
+        bn = 0;
+        for (int i = 0; i < 5 && !bn; ++i)
+            if (waste(cand[i]) <= 0.05) bn = cand[i];
+        if (!bn) {
+            bn = 64;
+            for (int i = 0; i < 5; ++i)
+                if (waste(cand[i]) < waste(bn) - 1e-9) bn = cand[i];
+        }
     }
     if (bn == 256) return zg::launch_gemm_cl<256>(p, s);
+    if (bn == 160) return zg::launch_gemm_cl<160>(p, s);
     if (bn == 128) return zg::launch_gemm_cl<128>(p, s);
+    if (bn == 80) return zg::launch_gemm_cl<80>(p, s);
     return zg::launch_gemm_cl<64>(p, s);
 }
