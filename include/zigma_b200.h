@@ -41,7 +41,14 @@ enum { ZG_F32 = 0, ZG_F16 = 1, ZG_BF16 = 2 };
 enum {
     ZG_SCAN_DELTA_SOFTPLUS = 1,  /* delta' = softplus(delta + bias), identity above 20 */
     ZG_SCAN_VARIABLE_B = 2,      /* B is (batch, groups, dstate, seqlen) in act dtype; else (dim, dstate) fp32 */
-    ZG_SCAN_VARIABLE_C = 4
+    ZG_SCAN_VARIABLE_C = 4,
+    /* output placement of the hot-path kernel (dim-contiguous 16-bit activations, dstate 16, seqlen % 8 == 0, dim % 64 == 0;
+     * other calls return an error): the two sweeps of scan_type "v2" (mamba_simple.py:304-339: y = y_fwd + y_bwd.flip(-1))
+     * without materialising the flipped tensor or a separate add --
+     *   OUT_REVERSE     step l is written to sequence position seqlen - 1 - l;
+     *   OUT_ACCUMULATE  out = round(out + round(y)) in the I/O dtype, i.e. the eager `a + b` of two 16-bit tensors. */
+    ZG_SCAN_OUT_REVERSE = 8,
+    ZG_SCAN_OUT_ACCUMULATE = 16
 };
 
 int zg_abi_version(void);
@@ -93,7 +100,12 @@ typedef struct {
     int32_t dtype, flags, ckpt_every;
     const void *dt_w, *dt_x;          /* fused dt_proj prologue: weight (dim, dt_rank), input rows (batch, seqlen, >= dt_rank) */
     int64_t dt_w_ld, dt_x_sb, dt_x_sl;
-    int32_t dt_rank, reserved0;
+    int32_t dt_rank;
+    /* two-level batch for z (hot-path kernel with z_rowmap only): z_batch_inner = K > 0 addresses batch element b of the call
+     * at  z + (b / K) z_sb + (b % K) z_sbi  -- the (b k) t sequences of the temporal video scan read their gate rows out of the
+     * (b, t k) token-major xz tensor (z_sl = K rows) without a permuted copy. */
+    int32_t z_batch_inner;
+    int64_t z_sbi;
 } zg_scan_params;
 
 int zg_selective_scan_fwd(const zg_scan_params *p, void *stream);
@@ -133,6 +145,11 @@ typedef struct {
     int64_t out_sb, out_sd, out_sl;
     int32_t batch, dim, seqlen, width;
     int32_t dtype, wdtype, silu;
+    /* seg_len > 0 (forward, 16-bit dim-contiguous fast path only; a multiple of 8 dividing seqlen): the sequence is a
+     * concatenation of independent segments of that length -- the taps never reach across a segment start.  With x_rowmap
+     * this convolves the (b k) t sequences of the factorised temporal video scan (mamba_simple.py:416-442) straight out of
+     * the (b, t k) token-major activations: x_rowmap[k T + t] = perm[t] K + k, seg_len = T. */
+    int32_t seg_len;
 } zg_conv_params;
 
 int zg_causal_conv1d_fwd(const zg_conv_params *p, void *stream);

@@ -82,6 +82,18 @@ def test_zigma_forward_bf16():
     check_close(out, g32["out"], "ZigMa.forward tiny bf16 vs reference fp32", rtol=5e-2, atol=5e-2, scale_atol=False, max_strict_viol=1.0)
 
 
+def test_zigma_forward_sweep2_bf16_fused_flip_add():
+    """scan_type v2 in bf16: the engine folds `y_fwd + y_bwd.flip(1)` into the second scan kernel (OUT_REVERSE | OUT_ACCUMULATE);
+    result vs the reference's fp32 output of the same (bf16-rounded) weights at the whole-model bf16 tolerance."""
+    g, cfg, shapes = model_case("tiny_sweep2")
+    m, sd = _build(cfg, shapes, torch.bfloat16)
+    x, tt, y = model_io(cfg, g["out"].shape[0])
+    with torch.no_grad():
+        out = m(x.to(DEV).bfloat16(), tt.to(DEV).bfloat16())
+    want = zo.zigma_forward({k: v.float() for k, v in sd.items()}, dict(cfg, norm_epsilon=1e-5), x.bfloat16().float(), tt.bfloat16().float())
+    check_close(out, want, "ZigMa.forward tiny v2 bf16 (fused flip-add) vs fp32 oracle", rtol=5e-2, atol=5e-2, scale_atol=False, max_strict_viol=1.0)
+
+
 def test_zigma_forward_batch_consistency_bf16_full():
     """Full-size bf16 model at bs=4: each sample equals the bs=1 run of that sample (samples are
     independent -> the multi-GPU batch sharding cannot change results), output finite."""

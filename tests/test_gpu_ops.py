@@ -169,6 +169,31 @@ def test_selective_scan_tma_pipeline_kernel(dtype, rtol, shape):
     check_close(out2, ref2, f"scan tma {dtype} {shape} plain", rtol=rtol, atol=1e-5, max_strict_viol=1.0)
 
 
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+def test_selective_scan_out_reverse_accumulate(dtype):
+    """ZG_SCAN_OUT_REVERSE | ZG_SCAN_OUT_ACCUMULATE: the kernel writes step l to position L-1-l and adds into `out` with the
+    rounding of an eager 16-bit `a + b` -- exactly `P + y.flip(-1)` of mamba_simple.py:337, bit for bit."""
+    from zigma_b200.selective_scan_interface import _scan_fwd
+    Bt, E, L, N = 2, 128, 72, 16
+    d, _ = _tok_inputs(Bt, E, L, N, 31, dtype)
+    y, _, _, _ = _scan_fwd(d["u"], d["delta"], d["A"], d["B"], d["C"], d["D"], d["z"], d["delta_bias"], True, want_last_state=False)
+    P = torch.randn(Bt, L, E, device=DEV).to(dtype)
+    buf = P.clone()
+    out, _, _, _ = _scan_fwd(d["u"], d["delta"], d["A"], d["B"], d["C"], d["D"], d["z"], d["delta_bias"], True, want_last_state=False,
+                             out=buf.transpose(1, 2), out_reverse=True, out_accumulate=True)
+    assert out.data_ptr() == buf.data_ptr()
+    want = P + y.transpose(1, 2).flip(1)                     # eager 16-bit add of the flipped result
+    assert torch.equal(buf, want)
+    rev = torch.empty_like(buf)
+    _scan_fwd(d["u"], d["delta"], d["A"], d["B"], d["C"], d["D"], d["z"], d["delta_bias"], True, want_last_state=False,
+              out=rev.transpose(1, 2), out_reverse=True)
+    assert torch.equal(rev, y.transpose(1, 2).flip(1))
+    with pytest.raises(RuntimeError):                        # fp32 / other shapes: an error, never a silently ignored flag
+        f = {k: (v.float() if v.dtype == dtype else v) for k, v in d.items()}
+        _scan_fwd(f["u"], f["delta"], f["A"], f["B"], f["C"], f["D"], f["z"], f["delta_bias"], True, want_last_state=False,
+                  out=torch.zeros(Bt, L, E, device=DEV).transpose(1, 2), out_reverse=True, out_accumulate=True)
+
+
 @pytest.mark.parametrize("dtype,rtol", [(torch.bfloat16, 1.6e-2), (torch.float16, 2e-3)])
 @pytest.mark.parametrize("R,E", [(40, 128), (48, 192)])
 def test_selective_scan_fused_dt_proj(dtype, rtol, R, E):
@@ -307,6 +332,46 @@ def test_causal_conv1d_rowmap_fuses_permutation():
     # fp32 math on the bf16 inputs, one rounding at the end (what causal_conv1d_fwd.cu:103-118 does)
     ref = zo.causal_conv1d(xz[:, :, :E].transpose(1, 2)[:, :, perm.to(DEV)].cpu(), w.cpu().float(), b.cpu().float(), "silu")
     check_close(out, ref, "conv x_rowmap (bf16)", rtol=8e-3, atol=1e-5, max_strict_viol=1.0)
+
+
+def test_conv_segments_and_scan_two_level_z_batch_temporal_layout():
+    """The two kernel features behind the copy-free temporal video layers (engine._core_temporal; mamba_simple.py:416-442):
+    (a) causal_conv1d with x_rowmap + seg_len: a (b, t k) token-major tensor convolved as (b k) sequences of T positions, taps
+        never crossing a segment start -- against the oracle conv on the explicitly permuted (b k, E, T) tensor;
+    (b) selective_scan with z_btk: sequence b K + k gates with z[b, perm[t], k, :] -- against the oracle scan on the explicitly
+        gathered z."""
+    from zigma_b200.causal_conv1d_interface import _conv_fwd
+    from zigma_b200.selective_scan_interface import _scan_fwd
+    dtype = torch.bfloat16
+    Bt, T, K, E, N = 2, 16, 8, 128, 16
+    L = T * K
+    gen = torch.Generator(device=DEV).manual_seed(9)
+    xz = torch.randn(Bt, L, 2 * E, device=DEV, generator=gen).to(dtype)               # (b, t k) token-major, x | z halves
+    w = (0.5 * torch.randn(E, 4, device=DEV, generator=gen)).to(dtype)
+    bias = (0.1 * torch.randn(E, device=DEV, generator=gen)).to(dtype)
+    perm = torch.randperm(T, device=DEV, generator=gen)
+    k_idx = torch.arange(K, device=DEV)
+    comp_in = (perm.view(1, T) * K + k_idx.view(K, 1)).reshape(-1).to(torch.int32)    # [k T + t] -> perm[t] K + k
+    xc = _conv_fwd(xz[:, :, :E].transpose(1, 2), w, bias, True, x_rowmap=comp_in, seg_len=T)     # (Bt, E, L) logical, (k, t) order
+    x_perm = xz[:, :, :E].view(Bt, T, K, E)[:, perm].permute(0, 2, 3, 1).reshape(Bt * K, E, T)   # explicit (b k, E, t) gather
+    want = zo.causal_conv1d(x_perm.float().cpu(), w.float().cpu(), bias.float().cpu(), "silu")
+    got = xc.transpose(1, 2).reshape(Bt, K, T, E).permute(0, 1, 3, 2).reshape(Bt * K, E, T)
+    check_close(got, want, "conv seg_len + composite rowmap", rtol=1.6e-2, atol=1e-5, max_strict_viol=1.0)
+    # (b) scan over the (b k) sequences, z through the two-level batch
+    inp = synth.synth_scan_inputs(Bt * K, E, T, N, 1, seed=33)
+    lo = {kk: (v.to(dtype) if kk in ("u", "delta", "B", "C") else v) for kk, v in inp.items()}
+    d = {kk: v.to(DEV) for kk, v in lo.items()}
+    tm = lambda x: x.transpose(1, 2).contiguous().transpose(1, 2)
+    Bv, Cv = d["B"].transpose(2, 3).contiguous().transpose(2, 3), d["C"].transpose(2, 3).contiguous().transpose(2, 3)
+    z_btk = xz.view(Bt, T, K, 2 * E)[:, :, :, E:]
+    out, _, _, _ = _scan_fwd(tm(d["u"]), tm(d["delta"]), d["A"], Bv, Cv, d["D"], None, d["delta_bias"], True,
+                             z_rowmap=perm.to(torch.int32), want_last_state=False, z_btk=z_btk)
+    z_perm = z_btk[:, perm].permute(0, 2, 3, 1).reshape(Bt * K, E, T)                  # z[b, perm[t], k, :] as (b k, E, t)
+    f = lambda v: v.float().cpu().numpy()
+    ref, _ = c_oracle.scan_fwd(f(lo["u"]), f(lo["delta"]), f(lo["A"]), f(lo["B"]), f(lo["C"]), f(lo["D"]), f(z_perm), f(lo["delta_bias"]), True)
+    check_close(out, ref, "scan z_btk (two-level z batch)", rtol=1.6e-2, atol=1e-5, max_strict_viol=1.0)
+    with pytest.raises(RuntimeError):        # seg_len outside the fast path is an error, not silently ignored
+        _conv_fwd(xz[:, :, :E].transpose(1, 2).float(), w.float(), bias.float(), True, x_rowmap=comp_in, seg_len=T)
 
 
 def test_causal_conv1d_backward_golden():

@@ -142,3 +142,31 @@ def test_reference_checkpoint_roundtrip(tmp_path):
     assert torch.equal(b.state_dict()["blocks.0.mixer.A_log"], ema.state_dict()["blocks.0.mixer.A_log"])
     with pytest.raises(RuntimeError):
         load_reference_checkpoint(b, {"ema": {"module.nope": torch.zeros(1)}})
+
+
+def test_vae_decode_handoff_matches_the_reference_driver_lines():
+    """zigma_b200.handoff against sample_acc.py:318-320,362-386 written out longhand with a stand-in VAE (the real one is a
+    third-party diffusers model): latents / 0.18215 -> decode(...).sample -> clamp(127.5 x + 128, 0, 255) -> uint8; videos decode
+    latents[i] for every index of the first axis and stack along dim 1; ground-truth latents are not rescaled."""
+    import types
+    import torch
+    from zigma_b200 import decode_latents, to_uint8_pixels
+    torch.manual_seed(0)
+    up = torch.nn.ConvTranspose2d(4, 3, kernel_size=8, stride=8)
+
+    class FakeVAE:
+        def decode(self, z):
+            return types.SimpleNamespace(sample=up(z))
+    vae = FakeVAE()
+    z = torch.randn(3, 4, 4, 4)
+    with torch.no_grad():
+        want = vae.decode(z / 0.18215).sample
+        got = decode_latents(z, vae)
+        assert torch.equal(got, want) and got.shape == (3, 3, 32, 32)
+        assert torch.equal(decode_latents(z, vae, from_flow=False), vae.decode(z).sample)
+        px = to_uint8_pixels(got)
+        assert px.dtype == torch.uint8 and torch.equal(px, torch.clamp(127.5 * want + 128.0, 0, 255).to(torch.uint8))
+        zv = torch.randn(2, 5, 4, 4, 4)                     # (batch, frames, C, h, w)
+        gv = decode_latents(zv, vae, video=True)
+        wv = torch.stack([vae.decode(zv[i] / 0.18215).sample for i in range(len(zv))], dim=1)
+        assert torch.equal(gv, wv) and gv.shape == (5, 2, 3, 32, 32)

@@ -5,7 +5,8 @@ Public surface mirrors the reference (CompVis/zigma):
     causal_conv1d_fn, rms_norm_fn, layer_norm_fn, RMSNorm, zigzag_path, hilbert_path,
     reverse_permut_np, create_transport, Sampler
 plus what sits around the path on a B200 node: train_step / FlatParams / GradSync / FusedAdamWEMA (zigma_b200.train),
-load_reference_checkpoint / save_reference_checkpoint (zigma_b200.checkpoint).
+load_reference_checkpoint / save_reference_checkpoint (zigma_b200.checkpoint), decode_latents / to_uint8_pixels (zigma_b200.handoff:
+the VAE-decode hand-off after sampling).
 All arithmetic on the path runs in libzigma_b200.so (include/zigma_b200.h); there is no CPU fallback.
 """
 from .utils_zigzag import zigzag_path, hilbert_path, reverse_permut_np  # noqa: F401  (pure numpy, always importable)
@@ -23,6 +24,7 @@ def __getattr__(name):
         "mamba_inner_tok_fn": "selective_scan_interface", "block_tail_fn": "block_ops",
         "FlatParams": "train", "GradSync": "train", "FusedAdamWEMA": "train", "train_step": "train",
         "load_reference_checkpoint": "checkpoint", "save_reference_checkpoint": "checkpoint",
+        "decode_latents": "handoff", "to_uint8_pixels": "handoff", "sample_and_decode": "handoff",
     }
     if name in table:
         return getattr(importlib.import_module("." + table[name], __name__), name)

@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("ZIGMA_B200_LIB") or os.path.join(_HERE, "lib", "libzigma_b200.so")   # (override: kernel timing experiments)
 
 ZG_F32, ZG_F16, ZG_BF16 = 0, 1, 2
-SCAN_DELTA_SOFTPLUS, SCAN_VARIABLE_B, SCAN_VARIABLE_C = 1, 2, 4
+SCAN_DELTA_SOFTPLUS, SCAN_VARIABLE_B, SCAN_VARIABLE_C, SCAN_OUT_REVERSE, SCAN_OUT_ACCUMULATE = 1, 2, 4, 8, 16
 _DT = {torch.float32: ZG_F32, torch.float16: ZG_F16, torch.bfloat16: ZG_BF16}
 
 vp, i64, i32, f32 = C.c_void_p, C.c_int64, C.c_int32, C.c_float
@@ -25,7 +25,8 @@ class ScanParams(C.Structure):
                 + [(n, i32) for n in ("batch", "dim", "seqlen", "dstate", "ngroups", "dtype", "flags", "ckpt_every")]
                 + [(n, vp) for n in ("dt_w", "dt_x")]
                 + [(n, i64) for n in ("dt_w_ld", "dt_x_sb", "dt_x_sl")]
-                + [(n, i32) for n in ("dt_rank", "reserved0")])
+                + [(n, i32) for n in ("dt_rank", "z_batch_inner")]
+                + [("z_sbi", i64)])
 
 
 class ScanBwdParams(C.Structure):
@@ -39,7 +40,7 @@ class ScanBwdParams(C.Structure):
 class ConvParams(C.Structure):
     _fields_ = ([(n, vp) for n in ("x", "weight", "bias", "x_rowmap", "out")]
                 + [(n, i64) for n in ("x_sb", "x_sd", "x_sl", "out_sb", "out_sd", "out_sl")]
-                + [(n, i32) for n in ("batch", "dim", "seqlen", "width", "dtype", "wdtype", "silu")])
+                + [(n, i32) for n in ("batch", "dim", "seqlen", "width", "dtype", "wdtype", "silu", "seg_len")])
 
 
 class ConvBwdParams(C.Structure):

@@ -7,7 +7,7 @@ import torch
 from . import _lib
 
 
-def _conv_fwd(x, weight, bias, silu, x_rowmap=None, out=None):
+def _conv_fwd(x, weight, bias, silu, x_rowmap=None, out=None, seg_len=0):
     """causal_conv1d_cuda.causal_conv1d_fwd (causal_conv1d.cpp:130-189).  x: logical
     (batch, dim, seqlen) with stride(2) == 1 (channel first) or stride(1) == 1 (channel last)."""
     _lib.require_cuda(x, weight, bias)
@@ -40,6 +40,7 @@ def _conv_fwd(x, weight, bias, silu, x_rowmap=None, out=None):
         p.x_sl = p.out_sl = 1
     p.batch, p.dim, p.seqlen, p.width = batch, dim, seqlen, width
     p.dtype, p.wdtype, p.silu = _lib.dt(x), _lib.dt(weight), int(bool(silu))
+    p.seg_len = int(seg_len)       # independent segments of this length inside the sequence (temporal video scan), 0 = one sequence
     _lib.call("zg_causal_conv1d_fwd", p)
     return out
 

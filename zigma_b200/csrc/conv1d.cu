@@ -169,14 +169,20 @@ __global__ void __launch_bounds__(128, 6) conv_fwd_tok4_kernel(const zg_conv_par
         }
     };
     zg_f2 x1[2], x2[2], x3[2];
+    const int seg = p.seg_len;      // 0, or a multiple of CONV_RB: independent segments (no taps across a segment start)
     {
         const uint2 zero = make_uint2(0u, 0u);
-        unpack(l0 >= 1 ? *row_ptr(l0 - 1) : zero, x1);
-        unpack(l0 >= 2 ? *row_ptr(l0 - 2) : zero, x2);
-        unpack(l0 >= 3 ? *row_ptr(l0 - 3) : zero, x3);
+        const int hist = seg > 0 ? (l0 % seg) : l0;      // positions of this segment before l0
+        unpack(hist >= 1 ? *row_ptr(l0 - 1) : zero, x1);
+        unpack(hist >= 2 ? *row_ptr(l0 - 2) : zero, x2);
+        unpack(hist >= 3 ? *row_ptr(l0 - 3) : zero, x3);
     }
 #pragma unroll 1
     for (int lb = 0; lb < CONV_LCH; lb += CONV_RB) {
+        if (seg > 0 && lb > 0 && ((l0 + lb) % seg) == 0) {      // a new segment starts with this batch of rows: zero history
+#pragma unroll
+            for (int h = 0; h < 2; ++h) x1[h] = x2[h] = x3[h] = make_float2(0.f, 0.f);
+        }
         uint2 raw[CONV_RB];
 #pragma unroll
         for (int j = 0; j < CONV_RB; ++j) raw[j] = *row_ptr(l0 + lb + j);
@@ -701,7 +707,7 @@ template <typename T> static int conv_fwd_t(const zg_conv_params &p, bool seq, c
             }
         }
         if constexpr (sizeof(T) == 2) {
-            const bool fast = (dv_env == 0) && (p.dim % 4 == 0) && (align_bits % 8 == 0) && (p.x_sb % 4 == 0) && (p.x_sl % 4 == 0) &&
+            const bool fast = (dv_env == 0 || p.seg_len > 0) && (p.seg_len % CONV_RB == 0) && (p.seg_len == 0 || p.seqlen % p.seg_len == 0) && (p.dim % 4 == 0) && (align_bits % 8 == 0) && (p.x_sb % 4 == 0) && (p.x_sl % 4 == 0) &&
                               (p.out_sb % 4 == 0) && (p.out_sl % 4 == 0) && (p.seqlen % CONV_LCH == 0) &&
                               ((int64_t)p.seqlen * p.x_sl < 0x7fffffffLL) && ((int64_t)p.seqlen * p.out_sl < 0x7fffffffLL);
             if (fast) {
@@ -711,6 +717,8 @@ template <typename T> static int conv_fwd_t(const zg_conv_params &p, bool seq, c
                 return zg_check_launch("causal_conv1d_fwd");
             }
         }
+        if (p.seg_len > 0)
+            return zg_set_error("causal_conv1d_fwd: seg_len needs the 16-bit fast path (seg_len %% 8 == 0 dividing seqlen, seqlen %% 32 == 0, dim %% 4 == 0, 8-byte aligned rows)");
         constexpr int DV = 4;
         constexpr int DB = DV * (int)sizeof(T);
         const bool vec_ok = (p.dim % DV == 0) && (align_bits % DB == 0) && (p.x_sb % DV == 0) && (p.x_sl % DV == 0) &&
@@ -747,6 +755,7 @@ extern "C" int zg_causal_conv1d_fwd(const zg_conv_params *pp, void *stream) {
     if (int rc = conv_validate(p, "causal_conv1d_fwd")) return rc;
     const bool seq = (p.x_sl == 1 && p.out_sl == 1);
     ZG_REQUIRE(!(seq && p.x_rowmap), "causal_conv1d_fwd: x_rowmap needs the dim-contiguous layout");
+    ZG_REQUIRE(p.seg_len >= 0 && !(seq && p.seg_len > 0), "causal_conv1d_fwd: seg_len needs the dim-contiguous layout");
     if (p.batch == 0 || p.seqlen == 0) return 0;
     cudaStream_t s = (cudaStream_t)stream;
     switch (p.dtype) {
@@ -761,6 +770,7 @@ extern "C" int zg_causal_conv1d_bwd(const zg_conv_bwd_params *qq, void *stream) 
     const zg_conv_bwd_params &q = *qq;
     if (int rc = conv_validate(q.fwd, "causal_conv1d_bwd")) return rc;
     ZG_REQUIRE(q.dout && q.dx && q.dweight, "causal_conv1d_bwd: null tensor pointer");
+    ZG_REQUIRE(q.fwd.seg_len == 0, "causal_conv1d_bwd: seg_len is a forward (sampling) feature");
     if (q.fwd.batch == 0 || q.fwd.seqlen == 0) return 0;
     cudaStream_t s = (cudaStream_t)stream;
     const zg_conv_params &p = q.fwd;

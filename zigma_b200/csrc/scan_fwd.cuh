@@ -469,11 +469,16 @@ template <typename T> int dispatch_scan_fwd(const zg_scan_params &p, bool seq, b
         if (!seq && !constbc) {     // hot-path specialisations, when the call fits them: round 2 (bulk-async pipeline), round 1
             int rc = try_launch_scan_fwd_tma<T>(p, stream);
             if (rc >= 0) return rc;
+            if (p.dt_w || p.z_batch_inner > 0 || (p.flags & (ZG_SCAN_OUT_REVERSE | ZG_SCAN_OUT_ACCUMULATE))) goto unsupported;   // only that kernel implements them
             rc = try_launch_scan_fwd_tpc2<T>(p, stream);
             if (rc >= 0) return rc;
         }
     }
+unsupported:
     if (p.dt_w) return zg_set_error("selective_scan_fwd: the fused dt_proj prologue needs 16-bit dim-contiguous activations with input-dependent B/C");
+    if (p.z_batch_inner > 0) return zg_set_error("selective_scan_fwd: z_batch_inner is implemented by the hot-path kernel only (16-bit dim-contiguous, dstate 16, seqlen %% 8 == 0, dim %% 64 == 0, z_rowmap given)");
+    if (p.flags & (ZG_SCAN_OUT_REVERSE | ZG_SCAN_OUT_ACCUMULATE))
+        return zg_set_error("selective_scan_fwd: OUT_REVERSE / OUT_ACCUMULATE are implemented by the hot-path kernel only (16-bit dim-contiguous, dstate 16, seqlen %% 8 == 0, dim %% 64 == 0)");
 #define ZG_SCAN_CASE(NSV)                                                                   \
     if (N <= NSV) {                                                                         \
         if (seq) return launch_scan_fwd_npoly<T, NSV, true>(p, stream);                     \

@@ -285,7 +285,9 @@ __global__ void __launch_bounds__(PT_THREADS, 9) scan_fwd_tma_kernel(const zg_sc
     // ---- producer: thread 0 issues the tensor tiles; threads 64..127 gather one z chunk each, 64..95 a B|C chunk ----
     const uint32_t tx_bytes = TILE + (FUSE ? TL * LY::XBYTES : TILE) + ((has_z && !z_gather) ? TILE : 0);
     const int zr = (tid >> 3) & 7, zj = tid & 7;          // threads 64..127: z row / 16-byte column of the stage
-    const unsigned char *zsrc = (z_gather && tid >= 64) ? reinterpret_cast<const unsigned char *>(reinterpret_cast<const T *>(p.z) + (int64_t)b * p.z_sb + e0 + zj * 8) : nullptr;
+    // batch element b of z: plain batch stride, or two-level (b / K, b % K) for the temporal video scan (zg_scan_params.z_batch_inner)
+    const int64_t z_boff = p.z_batch_inner > 0 ? (int64_t)(b / p.z_batch_inner) * p.z_sb + (int64_t)(b % p.z_batch_inner) * p.z_sbi : (int64_t)b * p.z_sb;
+    const unsigned char *zsrc = (z_gather && tid >= 64) ? reinterpret_cast<const unsigned char *>(reinterpret_cast<const T *>(p.z) + z_boff + e0 + zj * 8) : nullptr;
     const uint32_t z_sl2 = (uint32_t)p.z_sl * 2u;            // byte offsets inside a batch element fit 32 bits (host check)
     int zrow_next = (zsrc != nullptr) ? p.z_rowmap[zr] : 0;   // (permuted) source row of the NEXT stage to issue
     auto issue_stage = [&](int s, int slot) {             // all threads
@@ -384,10 +386,14 @@ __global__ void __launch_bounds__(PT_THREADS, 9) scan_fwd_tma_kernel(const zg_sc
         dst[0] = make_float2(dl.x, du.x);
         dst[1] = make_float2(dl.y, du.y);
     };
-    const int64_t out_step = FUSE ? 8 : 4 * p.out_sl;     // element distance between the thread's two output pairs
-    T *gout = reinterpret_cast<T *>(p.out) + (int64_t)b * p.out_sb + (int64_t)(FUSE ? (lane >> 2) : warp) * p.out_sl + e0 +
+    // output rows: step l -> sequence position l, or seqlen - 1 - l (ZG_SCAN_OUT_REVERSE: the backward sweep of scan_type v2)
+    const bool out_rev = (p.flags & ZG_SCAN_OUT_REVERSE) != 0, out_acc = (p.flags & ZG_SCAN_OUT_ACCUMULATE) != 0;
+    const int64_t out_row = out_rev ? -p.out_sl : p.out_sl;
+    const int r0 = FUSE ? (lane >> 2) : warp;               // the thread's first row of a stage
+    const int64_t out_step = FUSE ? 8 : 4 * out_row;      // element distance between the thread's two output pairs
+    T *gout = reinterpret_cast<T *>(p.out) + (int64_t)b * p.out_sb + (int64_t)(out_rev ? L - 1 - r0 : r0) * p.out_sl + e0 +
               (FUSE ? 16 * warp + 2 * (lane & 3) : 2 * lane);
-    const int64_t out_stage = (int64_t)TL * p.out_sl;
+    const int64_t out_stage = (int64_t)TL * out_row;
     auto post_item = [&](int k, const unsigned char *sw) {               // y = y_lo + y_hi + D u, SiLU(z) gate, store
         const float4 yy = *reinterpret_cast<const float4 *>(ddu + it_ddu[k]);   // (lo, hi) halves of 2 channels
         const float2 u2 = pt_unpack2<T>(*reinterpret_cast<const uint32_t *>(sw + it_swz[k]));
@@ -397,7 +403,12 @@ __global__ void __launch_bounds__(PT_THREADS, 9) scan_fwd_tma_kernel(const zg_sc
 #else
         if (has_z) y = zg_mul2(y, pt_silu2(pt_unpack2<T>(*reinterpret_cast<const uint32_t *>(sw + TILE + it_swz[k]))));
 #endif
-        *reinterpret_cast<uint32_t *>(gout + (k ? out_step : 0)) = pt_pack2<T>(y.x, y.y);
+        uint32_t *dst = reinterpret_cast<uint32_t *>(gout + (k ? out_step : 0));
+        if (out_acc) {      // out = round(out + round(y)): the eager sum of two I/O-dtype tensors (mamba_simple.py:337)
+            const float2 prev = pt_unpack2<T>(*dst), yr = pt_unpack2<T>(pt_pack2<T>(y.x, y.y));
+            y = zg_add2(prev, yr);
+        }
+        *dst = pt_pack2<T>(y.x, y.y);
     };
 
     // ---- the pipeline ------------------------------------------------------------------------------------------------
@@ -554,6 +565,7 @@ template <typename T> int try_launch_scan_fwd_tma(const zg_scan_params &p, cudaS
     if ((int64_t)p.seqlen * p.u_sl * 2 > lim || (!fuse && (int64_t)p.seqlen * p.delta_sl * 2 > lim) || (p.z && (int64_t)p.seqlen * p.z_sl * 2 > lim))
         return decline("batch element too large for 32-bit offsets");
     if ((long long)(p.dim / PT_CH) * p.batch > 0x7fffffffLL) return decline("grid too large");
+    if (p.z_batch_inner > 0 && (!p.z || !p.z_rowmap || p.z_sbi % 8 != 0)) return decline("z_batch_inner needs z with a z_rowmap and 16-byte aligned rows");
     if (!fuse) return pt_launch_variant<T, 0>(p, stream);
     // fused prologue: B and C must be the tail of the dt_x rows (the x_dbl rows of x_proj)
     const T *x = reinterpret_cast<const T *>(p.dt_x);

@@ -161,8 +161,9 @@ class ZigMaEngine:
         return self._rev_cache[L]
 
     # ---- one directional pass of the mixer core, token major ------------------------------------------
-    def _core(self, xz, Bt, L, lay, w, rowmap):
-        """xz: (Bt*L, 2E) token-major.  Returns y (Bt, L, E) = scan(...) * silu(z), in scan order."""
+    def _core(self, xz, Bt, L, lay, w, rowmap, acc_into=None):
+        """xz: (Bt*L, 2E) token-major.  Returns y (Bt, L, E) = scan(...) * silu(z), in scan order.  acc_into: (Bt, L, E) result of
+        the forward sweep -- this (backward) sweep is written flipped and added into it by the scan kernel itself."""
         E, R, N = lay["E"], lay["R"], lay["N"]
         xz3 = xz.view(Bt, L, 2 * E)
         x_log = xz3[:, :, :E].transpose(1, 2)          # logical (Bt, E, L), dim-contiguous
@@ -173,16 +174,55 @@ class ZigMaEngine:
         xd3 = x_dbl.view(Bt, L, R + 2 * N)
         B_log = xd3[:, :, R:R + N].permute(0, 2, 1).unsqueeze(1)                           # (Bt, 1, N, L) view
         C_log = xd3[:, :, R + N:].permute(0, 2, 1).unsqueeze(1)
+        extra = {} if acc_into is None else dict(out=acc_into.transpose(1, 2), out_reverse=True, out_accumulate=True)
         if self.fuse_dt and fused_dt_ok(xz.dtype, E, L, N, R, w["dt_proj"]):
             # dt_proj inside the scan kernel (tensor-core prologue): no delta tensor, no dt_proj GEMM launch
             y, _, _, _ = _scan_fwd(xc, None, w["A"], B_log, C_log, w["D"], z_log, w["dt_bias"], True,
-                                   z_rowmap=rowmap, want_last_state=False, want_ckpt=False, dt_proj=(w["dt_proj"], xd3))
+                                   z_rowmap=rowmap, want_last_state=False, want_ckpt=False, dt_proj=(w["dt_proj"], xd3), **extra)
         else:
             delta = _linear(x_dbl[:, :R], w["dt_proj"])                                    # (Bt*L, E)
             d_log = delta.view(Bt, L, E).transpose(1, 2)
             y, _, _, _ = _scan_fwd(xc, d_log, w["A"], B_log, C_log, w["D"], z_log, w["dt_bias"], True,
-                                   z_rowmap=rowmap, want_last_state=False, want_ckpt=False)
+                                   z_rowmap=rowmap, want_last_state=False, want_ckpt=False, **extra)
         return y.transpose(1, 2)                                                            # (Bt, L, E) contiguous
+
+    def _temporal_fused_ok(self, dtype, lay, T, K):
+        E, N = lay["E"], lay["N"]
+        return (dtype in (torch.bfloat16, torch.float16) and N == 16 and T % 8 == 0 and (T * K) % 32 == 0 and E % 64 == 0
+                and os.environ.get("ZG_SCAN_TMA", "1") != "0" and os.environ.get("ZIGMA_TEMPORAL_FUSED", "1") != "0" and not self.fuse_dt)
+
+    def _temporal_tables(self, lay, T, K, dev):
+        """Composite row tables of a temporal layer (int32, length T K): position p = k T + t of the (k, t)-ordered working layout
+        <-> token (perm[t], k) of the (t, k)-ordered model layout."""
+        key = ("temporal", id(lay), T, K)
+        if key not in self._rev_cache:
+            perm, rev = lay["perm64"], lay["perm_rev64"]
+            k = torch.arange(K, device=dev)
+            comp_in = (perm.view(1, T) * K + k.view(K, 1)).reshape(-1)                    # [k T + t] -> perm[t] K + k
+            comp_out = (k.view(1, K) * T + rev.view(T, 1)).reshape(-1)                    # [t K + k] -> k T + perm_rev[t]
+            self._rev_cache[key] = {"in": comp_in.to(torch.int32).contiguous(), "out": comp_out.to(torch.int32).contiguous()}
+        return self._rev_cache[key]
+
+    def _core_temporal(self, xz, B, T, K, lay, w, tb):
+        """Temporal layer of a factorised video scan (mamba_simple.py:416-442) on the (B T K, 2E) token-major xz, no permuted
+        copies.  Returns y (B K T, E) in (b, k, t) order."""
+        E, R, N = lay["E"], lay["R"], lay["N"]
+        L = T * K
+        xz3 = xz.view(B, L, 2 * E)
+        x_log = xz3[:, :, :E].transpose(1, 2)                                              # logical (B, E, L), dim-contiguous
+        xc = _conv_fwd(x_log, w["conv_w"], w["conv_b"], True, x_rowmap=tb["in"], seg_len=T)   # (B, L, E) memory, (k, t) order
+        xc_flat = xc.transpose(1, 2).reshape(B * L, E)
+        x_dbl = _linear(xc_flat, w["x_proj"])
+        delta = _linear(x_dbl[:, :R], w["dt_proj"])
+        u_log = xc_flat.view(B * K, T, E).transpose(1, 2)
+        d_log = delta.view(B * K, T, E).transpose(1, 2)
+        xd3 = x_dbl.view(B * K, T, R + 2 * N)
+        B_log = xd3[:, :, R:R + N].permute(0, 2, 1).unsqueeze(1)
+        C_log = xd3[:, :, R + N:].permute(0, 2, 1).unsqueeze(1)
+        z_btk = xz.view(B, T, K, 2 * E)[:, :, :, E:]                                       # (B, T, K, E) strided view of the z half
+        y, _, _, _ = _scan_fwd(u_log, d_log, w["A"], B_log, C_log, w["D"], None, w["dt_bias"], True, z_rowmap=lay["perm"],
+                               want_last_state=False, want_ckpt=False, z_btk=z_btk)
+        return y.transpose(1, 2)
 
     def _mixer(self, modded, lay):
         """modded: (B, L, D) -> (mix (Bt', L', D) token-major in SCAN order, tail rowmap, fold info)."""
@@ -195,8 +235,12 @@ class ZigMaEngine:
             rowmap = None
         elif st == "v2":
             yf = self._core(xz, B, L, lay, lay["fwd"], None)
-            yb = self._core(xz, B, L, lay, lay["bwd"], self._flip_map(L, xz.device))
-            y = yf + yb.flip(1)
+            if xz.dtype in (torch.bfloat16, torch.float16) and lay["N"] == 16 and L % 8 == 0 and E % 64 == 0 and os.environ.get("ZG_SCAN_TMA", "1") != "0":
+                # y = yf + yb.flip(1) inside the second scan (ZG_SCAN_OUT_REVERSE | ZG_SCAN_OUT_ACCUMULATE): no flipped copy, no add kernel
+                y = self._core(xz, B, L, lay, lay["bwd"], self._flip_map(L, xz.device), acc_into=yf)
+            else:
+                yb = self._core(xz, B, L, lay, lay["bwd"], self._flip_map(L, xz.device))
+                y = yf + yb.flip(1)
             rowmap = None
         elif "s_or_t" not in lay:
             y = self._core(xz, B, L, lay, lay["fwd"], lay["perm"])
@@ -208,7 +252,14 @@ class ZigMaEngine:
                 y = self._core(xz, B * T, K, lay, lay["fwd"], lay["perm"])
                 mix = _linear(y.reshape(B * T * K, E), lay["out_proj"], lay["out_bias"]).view(B * T, K, D)
                 return mix, lay["perm_rev"], T
-            # (b k) sequences of T tokens: strided in token-major memory -> explicit transposes
+            # (b k) sequences of T tokens: strided in the (b, t k) token-major memory
+            if self._temporal_fused_ok(xz.dtype, lay, T, K):
+                # no copies: the conv gathers its input rows through a composite table (segments of T positions), the scan
+                # reads z through a two-level batch, and the block tail un-permutes with the inverse composite table
+                tb = self._temporal_tables(lay, T, K, xz.device)
+                y = self._core_temporal(xz, B, T, K, lay, lay["fwd"], tb)
+                mix = _linear(y.reshape(B * L, E), lay["out_proj"], lay["out_bias"]).view(B, L, D)        # rows in (b, k, t) order
+                return mix, tb["out"], 1
             xz_t = xz.view(B, T, K, 2 * E).permute(0, 2, 1, 3).reshape(B * K * T, 2 * E)
             y = self._core(xz_t, B * K, T, lay, lay["fwd"], lay["perm"])
             mix = _linear(y.reshape(B * K * T, E), lay["out_proj"], lay["out_bias"]).view(B * K, T, D)

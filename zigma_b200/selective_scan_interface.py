@@ -27,14 +27,20 @@ def _strides3(t):
 
 
 def _scan_fwd(u, delta, A, B, C, D=None, z=None, delta_bias=None, delta_softplus=False,
-              z_rowmap=None, want_last_state=True, want_ckpt=False, out=None, dt_proj=None):
+              z_rowmap=None, want_last_state=True, want_ckpt=False, out=None, dt_proj=None, out_reverse=False, out_accumulate=False, z_btk=None):
     """Raw forward.  u, delta, z: logical (batch, dim, seqlen) tensors (either memory layout, see
     include/zigma_b200.h); B, C: (batch, groups, dstate, seqlen) variable or (dim, dstate) fp32.
     Returns (out, last_state | None, ckpt | None).  Mirrors the checks of selective_scan.cpp:238-300.
 
     dt_proj = (dt_weight (dim, R), x_dbl (batch, seqlen, >= R + 2 dstate)) with delta=None: the fused dt_proj prologue --
     delta = dt_weight @ x_dbl[..., :R] is formed inside the kernel (tensor cores), B and C must be the views
-    x_dbl[..., R:R+N] / x_dbl[..., R+N:R+2N] of the same rows (selective_scan_interface.py:323 of the reference)."""
+    x_dbl[..., R:R+N] / x_dbl[..., R+N:R+2N] of the same rows (selective_scan_interface.py:323 of the reference).
+
+    z_btk (instead of z, hot-path kernel only, needs z_rowmap): a (B, T, K, dim) strided view; sequence b' = b K + k of the call
+    gates with z_btk[b, :, k, :] -- the factorised temporal scan reading the (b, t k) token-major xz tensor in place.
+
+    out_reverse / out_accumulate (hot-path kernel only, needs ``out``): write step l to position seqlen-1-l / add into ``out``
+    with the rounding of an eager 16-bit ``a + b`` -- the second sweep of scan_type "v2" (mamba_simple.py:304-339)."""
     _lib.require_cuda(u, delta, A, B, C, D, z, delta_bias)
     if u.dim() != 3:
         raise RuntimeError("selective_scan: u must be (batch, dim, seqlen)")
@@ -58,6 +64,9 @@ def _scan_fwd(u, delta, A, B, C, D=None, z=None, delta_bias=None, delta_softplus
     A = A.contiguous()
     var_b, var_c = B.dim() >= 3, C.dim() >= 3
     flags = (_lib.SCAN_DELTA_SOFTPLUS if delta_softplus else 0) | (_lib.SCAN_VARIABLE_B if var_b else 0) | (_lib.SCAN_VARIABLE_C if var_c else 0)
+    flags |= (_lib.SCAN_OUT_REVERSE if out_reverse else 0) | (_lib.SCAN_OUT_ACCUMULATE if out_accumulate else 0)
+    if out_accumulate and out is None:
+        raise RuntimeError("selective_scan: out_accumulate needs an existing `out`")
     ngroups = 1
     for name, M, var in (("B", B, var_b), ("C", C, var_c)):
         if var:
@@ -77,6 +86,12 @@ def _scan_fwd(u, delta, A, B, C, D=None, z=None, delta_bias=None, delta_softplus
             raise RuntimeError(f"selective_scan: {name} must be fp32 (dim,)")
     if z is not None and (z.shape != u.shape or z.dtype != u.dtype):
         raise RuntimeError("selective_scan: z must match u in shape and dtype")
+    if z_btk is not None:
+        if z is not None or z_rowmap is None:
+            raise RuntimeError("selective_scan: z_btk replaces z and needs a z_rowmap")
+        Bz, Tz, Kz, Ez = z_btk.shape
+        if Bz * Kz != batch or Tz != seqlen or Ez != dim or z_btk.dtype != u.dtype or z_btk.stride(3) != 1:
+            raise RuntimeError("selective_scan: z_btk must be (B, seqlen, K, dim) with B * K == batch, dim contiguous")
 
     seq_layout = u.stride(2) == 1 or seqlen == 1
     if not seq_layout and not (u.stride(1) == 1 or dim == 1):
@@ -130,6 +145,10 @@ def _scan_fwd(u, delta, A, B, C, D=None, z=None, delta_bias=None, delta_softplus
     else:
         p.dt_w, p.dt_x = _lib.ptr(dt_w), _lib.ptr(dt_x)
         p.dt_w_ld, p.dt_x_sb, p.dt_x_sl, p.dt_rank = dt_w.stride(0), dt_x.stride(0), dt_x.stride(1), dt_w.shape[1]
+    if z_btk is not None:
+        p.z = _lib.ptr(z_btk)
+        p.z_sb, p.z_sl, p.z_sbi, p.z_sd = z_btk.stride(0), z_btk.stride(1), z_btk.stride(2), 1
+        p.z_batch_inner = z_btk.shape[2]
     if z is not None:
         p.z_sb, p.z_sd, p.z_sl = _strides3(z)
     p.out_sb, p.out_sd, p.out_sl = _strides3(out)
@@ -185,11 +204,7 @@ def _scan_bwd(saved, ckpt, dout, delta_softplus, dz_out=None, z_rowmap=None):
     p.ckpt = _lib.ptr(ckpt)
     p.z_rowmap = _lib.ptr(z_rowmap)     # z read / dz written in token order (dstate == 16 kernel only)
     p.u_sb, p.u_sd, p.u_sl = _strides3(u)
-    if delta is not None:
-        p.delta_sb, p.delta_sd, p.delta_sl = _strides3(delta)
-    else:
-        p.dt_w, p.dt_x = _lib.ptr(dt_w), _lib.ptr(dt_x)
-        p.dt_w_ld, p.dt_x_sb, p.dt_x_sl, p.dt_rank = dt_w.stride(0), dt_x.stride(0), dt_x.stride(1), dt_w.shape[1]
+    p.delta_sb, p.delta_sd, p.delta_sl = _strides3(delta)
     if z is not None:
         p.z_sb, p.z_sd, p.z_sl = _strides3(z)
     p.B_sb, p.B_sg, p.B_sn, p.B_sl = B.stride()
