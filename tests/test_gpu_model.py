@@ -83,15 +83,20 @@ def test_zigma_forward_bf16():
 
 
 def test_zigma_forward_sweep2_bf16_fused_flip_add():
-    """scan_type v2 in bf16: the engine folds `y_fwd + y_bwd.flip(1)` into the second scan kernel (OUT_REVERSE | OUT_ACCUMULATE);
-    result vs the reference's fp32 output of the same (bf16-rounded) weights at the whole-model bf16 tolerance."""
-    g, cfg, shapes = model_case("tiny_sweep2")
-    m, sd = _build(cfg, shapes, torch.bfloat16)
-    x, tt, y = model_io(cfg, g["out"].shape[0])
-    with torch.no_grad():
-        out = m(x.to(DEV).bfloat16(), tt.to(DEV).bfloat16())
-    want = zo.zigma_forward({k: v.float() for k, v in sd.items()}, dict(cfg, norm_epsilon=1e-5), x.bfloat16().float(), tt.bfloat16().float())
-    check_close(out, want, "ZigMa.forward tiny v2 bf16 (fused flip-add) vs fp32 oracle", rtol=5e-2, atol=5e-2, scale_atol=False, max_strict_viol=1.0)
+    """scan_type v2 in bf16: the engine folds `y_fwd + y_bwd.flip(1)` into the second scan kernel (OUT_REVERSE | OUT_ACCUMULATE)
+    when the layer fits the hot-path kernel (D = 128 here: dt_rank 8, 16-byte aligned B / C columns); result vs the fp32 oracle
+    on the same (bf16-rounded) weights at the whole-model bf16 tolerance.  D = 32 (dt_rank 2) takes the eager flip + add."""
+    from zigma_b200 import ZigMa
+    for D in (128, 32):
+        cfg = dict(in_channels=4, embed_dim=D, depth=2, img_dim=8, patch_size=1, scan_type="v2", use_pe=2)
+        m = ZigMa(device=DEV, dtype=torch.bfloat16, **cfg).eval()
+        sd = synth.synth_state_dict({k: tuple(v.shape) for k, v in m.state_dict().items()}, seed=0, dtype=torch.bfloat16)
+        m.load_state_dict(sd)
+        x, tt, y = model_io(cfg, 2)
+        with torch.no_grad():
+            out = m(x.to(DEV).bfloat16(), tt.to(DEV).bfloat16())
+        want = zo.zigma_forward({k: v.float() for k, v in sd.items()}, dict(cfg, norm_epsilon=1e-5), x.bfloat16().float(), tt.bfloat16().float())
+        check_close(out, want, f"ZigMa.forward tiny v2 bf16 D={D} vs fp32 oracle", rtol=5e-2, atol=5e-2, scale_atol=False, max_strict_viol=1.0)
 
 
 def test_zigma_forward_batch_consistency_bf16_full():

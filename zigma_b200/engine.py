@@ -47,6 +47,13 @@ def fused_dt_ok(dtype, E, L, N, R, dt_w):
             and dt_w.dtype == dtype and dt_w.stride(1) == 1 and dt_w.stride(0) % 8 == 0 and (R + 2 * N) % 8 == 0)
 
 
+def scan_hot_path_ok(dtype, E, L, N, R):
+    """Shape class of zg::scan_fwd_tma_kernel as the engine calls it (B / C read in place from the x_dbl rows): the features only
+    that kernel implements (OUT_REVERSE / OUT_ACCUMULATE, z_batch_inner) may be requested."""
+    return (dtype in (torch.bfloat16, torch.float16) and N == 16 and L % 8 == 0 and L > 0 and E % 64 == 0 and R % 8 == 0
+            and (R + 2 * N) % 8 == 0 and os.environ.get("ZG_SCAN_TMA", "1") != "0")
+
+
 def block_tail(x, mix, gate, shift, scale, norm_w, residual, rowmap, eps, final=False, mod_div=1, want_modded=True, want_rstd=False):
     """zg_block_tail_fwd wrapper.  x: (Bt, L, D) contiguous; gate/shift/scale: (Bt // mod_div, D)
     views with a common row stride.  Returns residual_out (fp32), normed, modded."""
@@ -188,8 +195,8 @@ class ZigMaEngine:
 
     def _temporal_fused_ok(self, dtype, lay, T, K):
         E, N = lay["E"], lay["N"]
-        return (dtype in (torch.bfloat16, torch.float16) and N == 16 and T % 8 == 0 and (T * K) % 32 == 0 and E % 64 == 0
-                and os.environ.get("ZG_SCAN_TMA", "1") != "0" and os.environ.get("ZIGMA_TEMPORAL_FUSED", "1") != "0" and not self.fuse_dt)
+        return (scan_hot_path_ok(dtype, E, T, N, lay["R"]) and (T * K) % 32 == 0
+                and os.environ.get("ZIGMA_TEMPORAL_FUSED", "1") != "0" and not self.fuse_dt)
 
     def _temporal_tables(self, lay, T, K, dev):
         """Composite row tables of a temporal layer (int32, length T K): position p = k T + t of the (k, t)-ordered working layout
@@ -235,7 +242,7 @@ class ZigMaEngine:
             rowmap = None
         elif st == "v2":
             yf = self._core(xz, B, L, lay, lay["fwd"], None)
-            if xz.dtype in (torch.bfloat16, torch.float16) and lay["N"] == 16 and L % 8 == 0 and E % 64 == 0 and os.environ.get("ZG_SCAN_TMA", "1") != "0":
+            if scan_hot_path_ok(xz.dtype, E, L, lay["N"], lay["R"]):
                 # y = yf + yb.flip(1) inside the second scan (ZG_SCAN_OUT_REVERSE | ZG_SCAN_OUT_ACCUMULATE): no flipped copy, no add kernel
                 y = self._core(xz, B, L, lay, lay["bwd"], self._flip_map(L, xz.device), acc_into=yf)
             else:
