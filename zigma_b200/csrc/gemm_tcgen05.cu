@@ -33,10 +33,13 @@
 
 namespace zg {
 
+#ifndef ZG_GEMM_2CTA_DEFAULT
+#define ZG_GEMM_2CTA_DEFAULT 1
+#endif
 constexpr int G_BM = 128, G_BK = 64, G_UMMA_K = 16, G_THREADS = 192;   // 6 warps: TMA, MMA, 4 epilogue
 // smem ring depth: as many (128 + BN) x 64 bf16 stages as fit next to the 32 KB epilogue staging
-__host__ __device__ constexpr int gemm_stages(int BN) {
-    const int stage = (G_BM + BN) * G_BK * 2, avail = 227 * 1024 - 4 * 2 * 32 * 128 - 2048;
+__host__ __device__ constexpr int gemm_stages(int BN, bool pair = false) {      // pair: each CTA stages half of the B tile
+    const int stage = (G_BM + (pair ? BN / 2 : BN)) * G_BK * 2, avail = 227 * 1024 - 4 * 2 * 32 * 128 - 2048;
     return avail / stage > 8 ? 8 : avail / stage;
 }
 
@@ -82,6 +85,35 @@ __device__ __forceinline__ void mbar_arrive_remote(uint64_t *bar, uint32_t cta) 
     uint32_t ra;
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(smem_u32(bar)), "r"(cta));
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(ra) : "memory");
+}
+// ---- cta_group::2 (CTA pair) variants: one MMA of M = 256 over the two CTAs of a cluster; PTX forms as in the vendored
+// CUTLASS headers (cute/arch/mma_sm100_umma.hpp SM100_MMA_F16BF16_2x1SM_SS, cutlass/arch/barrier.h umma_arrive_multicast_2x1SM,
+// cute/arch/copy_sm100_tma.hpp SM100_TMA_2SM_LOAD_2D, cute/arch/tmem_allocator_sm100.hpp Allocator2Sm) ----
+__device__ __forceinline__ uint32_t leader_addr(const void *p) {      // the same shared-memory offset in CTA 0 of the cluster
+    uint32_t ra;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(smem_u32(p)), "r"(0u));
+    return ra;
+}
+__device__ __forceinline__ void tma_load_2d_pair(void *dst, const CUtensorMap *map, uint32_t leader_bar, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(dst)),
+                 "l"(map), "r"(leader_bar), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void umma_f16_pair(uint32_t tmem_c, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    const uint32_t z = 0u;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n\t"
+        "}\n" ::"r"(tmem_c), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(z) : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair_mc(uint64_t *bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)), "h"(mask)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster_addr(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
@@ -153,12 +185,16 @@ struct GemmArgs {
     int tma_store;      // 1: epilogue goes through smem + TMA store (needs 16-byte aligned C rows)
 };
 
-template <int BN, int CL>
+// TWO (needs CL == 2): the two CTAs of the cluster form a CTA PAIR -- one tcgen05.mma.cta_group::2 of M = 256 per k-step, issued by
+// CTA 0, reading each CTA's own 128 x 64 A tile and its HALF (BN / 2 rows) of the B tile: half the B bytes per SM and twice the
+// math per pipeline stage compared with two independent M = 128 MMAs on a multicast B tile.
+template <int BN, int CL, bool TWO = false>
 __global__ void __launch_bounds__(G_THREADS, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmC, const GemmArgs g) {
-    constexpr int BM = G_BM, BK = G_BK, STAGES = gemm_stages(BN);
-    constexpr uint32_t A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
+    static_assert(!TWO || CL == 2, "a CTA pair is a cluster of two");
+    constexpr int BM = G_BM, BK = G_BK, STAGES = gemm_stages(BN, TWO);
+    constexpr uint32_t A_BYTES = BM * BK * 2, B_BYTES = (TWO ? BN / 2 : BN) * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
     constexpr uint32_t TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
     extern __shared__ __align__(1024) unsigned char gsm[];
     unsigned char *tiles = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(gsm) + 1023) & ~(uintptr_t)1023);
@@ -184,12 +220,17 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
         for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); mbar_init(&free_bar[i], CL); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 128); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], TWO ? 256 : 128); }   // pair: both CTAs' epilogue threads
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_slot)), "r"(TMEM_COLS) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if constexpr (TWO) {      // (the same warp of both CTAs, the same destination offset: cute Allocator2Sm)
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_slot)), "r"(TMEM_COLS) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_slot)), "r"(TMEM_COLS) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -206,9 +247,18 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 for (int kb = 0; kb < k_blocks; ++kb, ++it) {
                     const int st = it % STAGES;
                     const uint32_t ph = (it / STAGES) & 1;
-                    mbar_wait(CL > 1 ? &free_bar[st] : &empty_bar[st], ph ^ 1);
-                    mbar_expect_tx(&full_bar[st], STAGE_BYTES);
+                    mbar_wait((CL > 1 && !TWO) ? &free_bar[st] : &empty_bar[st], ph ^ 1);
                     unsigned char *sa = tiles + st * STAGE_BYTES;
+                    if constexpr (TWO) {
+                        // both CTAs load their own A rows and their half of the B rows; every byte is counted on CTA 0's barrier,
+                        // which CTA 0 arms for the pair
+                        if (rank == 0) mbar_expect_tx(&full_bar[st], 2 * STAGE_BYTES);
+                        const uint32_t lbar = leader_addr(&full_bar[st]);
+                        tma_load_2d_pair(sa, &tmA, lbar, kb * BK, m_blk * BM);
+                        tma_load_2d_pair(sa + A_BYTES, &tmB, lbar, kb * BK, n_blk * BN + (int)rank * (BN / 2));
+                        continue;
+                    }
+                    mbar_expect_tx(&full_bar[st], STAGE_BYTES);
                     tma_load_2d(sa, &tmA, &full_bar[st], kb * BK, m_blk * BM);
                     if (CL > 1) {   // my 1/CL slice of the weight tile, multicast to the whole cluster
                         constexpr int SL = BN / CL;
@@ -221,9 +271,9 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             }
         }
     } else if (warp == 1) {
-        // ===== MMA issuer =====
-        if (elect_one()) {
-            constexpr uint32_t idesc = make_idesc(BM, BN);
+        // ===== MMA issuer (pair: CTA 0 only) =====
+        if ((!TWO || rank == 0) && elect_one()) {
+            constexpr uint32_t idesc = make_idesc(TWO ? 2 * BM : BM, BN);
             uint32_t it = 0, tcount = 0;
             for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++tcount) {
                 const int acc = tcount & 1;
@@ -239,13 +289,17 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     const uint32_t sa = smem_u32(tiles + st * STAGE_BYTES);
                     const uint64_t adesc = make_smem_desc(sa), bdesc = make_smem_desc(sa + A_BYTES);
 #pragma unroll
-                    for (int k = 0; k < BK / G_UMMA_K; ++k)      // +32 B per K=16 step inside the 128-byte swizzle atom
-                        umma_f16(tmem_c, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
+                    for (int k = 0; k < BK / G_UMMA_K; ++k) {    // +32 B per K=16 step inside the 128-byte swizzle atom
+                        if constexpr (TWO) umma_f16_pair(tmem_c, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
+                        else umma_f16(tmem_c, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
+                    }
                     // smem stage free once these MMAs retire; with clusters every CTA of the cluster is told
-                    if (CL > 1) umma_commit_mc(&free_bar[st], (uint16_t)((1u << CL) - 1));
+                    if constexpr (TWO) umma_commit_pair_mc(&empty_bar[st], (uint16_t)3);
+                    else if (CL > 1) umma_commit_mc(&free_bar[st], (uint16_t)((1u << CL) - 1));
                     else umma_commit(&empty_bar[st]);
                 }
-                umma_commit(&tfull_bar[acc]);                    // accumulator complete
+                if constexpr (TWO) umma_commit_pair_mc(&tfull_bar[acc], (uint16_t)3);      // accumulator complete, in both CTAs
+                else umma_commit(&tfull_bar[acc]);
             }
         }
     } else if (warp < 6) {
@@ -354,7 +408,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 for (int c0 = 0; c0 < BN; c0 += 32) direct_store32(c0);
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            mbar_arrive(&tempty_bar[acc]);
+            if constexpr (TWO) mbar_arrive_cluster_addr(leader_addr(&tempty_bar[acc]));     // the pair's MMA issuer lives in CTA 0
+            else mbar_arrive(&tempty_bar[acc]);
         }
     }
     if (warp >= 2 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // my TMA stores have landed
@@ -362,7 +417,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     __syncthreads();
     if (CL > 1) cluster_sync_all();          // no CTA leaves while a peer may still multicast into it / arrive on its barriers
     if (warp == 1) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+        if constexpr (TWO) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
     }
 }
 
@@ -396,7 +452,7 @@ static int make_map(CUtensorMap *m, const void *base, int64_t rows, int64_t cols
     return 0;
 }
 
-template <int BN, int CL> static int launch_gemm(const zg_gemm_params &p, cudaStream_t s) {
+template <int BN, int CL, bool TWO = false> static int launch_gemm(const zg_gemm_params &p, cudaStream_t s) {
     CUtensorMap tmA, tmB, tmC;
     if (int rc = make_map(&tmA, p.A, p.M, p.K, p.lda, G_BM)) return rc;
     if (int rc = make_map(&tmB, p.B, p.N, p.K, p.ldb, BN / CL)) return rc;
@@ -408,8 +464,8 @@ template <int BN, int CL> static int launch_gemm(const zg_gemm_params &p, cudaSt
     }
     GemmArgs g{reinterpret_cast<__nv_bfloat16 *>(p.C), reinterpret_cast<const __nv_bfloat16 *>(p.bias), p.out_rowmap, p.ldc, p.M, p.N, p.K,
                p.rows_per_batch > 0 ? p.rows_per_batch : p.M, tma_store_ok ? 1 : 0};
-    const int smem = gemm_stages(BN) * (G_BM * G_BK * 2 + BN * G_BK * 2) + 4 * 2 * 32 * 128 + 1024 + 512;
-    auto kern = gemm_bf16_tn_kernel<BN, CL>;
+    const int smem = gemm_stages(BN, TWO) * (G_BM * G_BK * 2 + (TWO ? BN / 2 : BN) * G_BK * 2) + 4 * 2 * 32 * 128 + 1024 + 512;
+    auto kern = gemm_bf16_tn_kernel<BN, CL, TWO>;
     static bool attr = false;
     if (!attr) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -459,8 +515,15 @@ template <int BN> static int launch_gemm_cl(const zg_gemm_params &p, cudaStream_
     int cl = gemm_cluster_setting();
     const int m_tiles = (p.M + G_BM - 1) / G_BM;
     while (cl > 1 && (m_tiles < cl || (BN / cl) % 8 != 0)) cl >>= 1;     // (a CTA's multicast slice must be whole 8-row swizzle groups)
+    static int pair = -1;        // ZG_GEMM_2CTA = 1: the cluster of two runs as a CTA pair (one M = 256 MMA, cta_group::2)
+    if (pair < 0) { const char *e = getenv("ZG_GEMM_2CTA"); pair = e ? atoi(e) : ZG_GEMM_2CTA_DEFAULT; }
     if (cl == 4) return launch_gemm<BN, 4>(p, s);
-    if (cl == 2) return launch_gemm<BN, 2>(p, s);
+    if (cl == 2) {
+        // (each CTA's half of the B tile must be whole 8-row swizzle groups, N % 16 == 0.  Short-K products are memory-bound and
+        // lose from the coupling of the pair: dt_proj, K = 40, 60.2 us as a pair vs 41.5 us -- pairs from 4 k-blocks on.)
+        if constexpr (BN % 32 == 0) { if (pair && p.K >= 4 * G_BK) return launch_gemm<BN, 2, true>(p, s); }
+        return launch_gemm<BN, 2>(p, s);
+    }
     return launch_gemm<BN, 1>(p, s);
 }
 
