@@ -169,6 +169,17 @@ def test_selective_scan_tma_pipeline_kernel(dtype, rtol, shape):
     check_close(out2, ref2, f"scan tma {dtype} {shape} plain", rtol=rtol, atol=1e-5, max_strict_viol=1.0)
 
 
+def test_selective_scan_hot_path_four_threads_per_channel_variant():
+    """ZG_SCAN_TPC=4 (four threads per channel, an opt-in variant of the hot-path kernel; the choice is read once per process):
+    the same small-shape tests in a child process."""
+    import os, subprocess, sys
+    from util import ROOT
+    env = dict(os.environ, ZG_SCAN_TPC="4")
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_gpu_ops.py"), "-m", "gpu", "-q", "-x", "-p", "no:cacheprovider",
+                        "-k", "tma_pipeline or out_reverse or temporal_layout or z_rowmap"], capture_output=True, text=True, cwd=ROOT, env=env, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-1000:]
+
+
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
 def test_selective_scan_out_reverse_accumulate(dtype):
     """ZG_SCAN_OUT_REVERSE | ZG_SCAN_OUT_ACCUMULATE: the kernel writes step l to position L-1-l and adds into `out` with the

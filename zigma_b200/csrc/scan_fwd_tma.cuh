@@ -49,12 +49,11 @@ namespace zg {
 
 constexpr int PT_TL = 8;              // steps per stage
 constexpr int PT_CH = 64;             // channels per CTA
-constexpr int PT_THREADS = 128;
 constexpr int PT_F32ROW = 576;        // pitch of one step of the fp32 pair tile (64 channels x 8 B + 64: bank shift of 16 words)
 
 __host__ __device__ constexpr int pt_pitch16(int bytes) { return ((bytes / 16) | 1) * 16; }   // odd number of 16-byte units
 
-template <int R> struct PtLayout {           // R = dt_rank of the fused prologue, 0 = delta comes from HBM
+template <int R, int TPC = 2> struct PtLayout {           // R = dt_rank of the fused prologue, 0 = delta comes from HBM; TPC = threads per channel
     static constexpr bool FUSE = R > 0;
     static constexpr int NSTAGE = 3;
     static constexpr int NSWZ = FUSE ? 2 : 3;                         // swizzled 8 x 128 B tiles per stage: u, z (, delta)
@@ -67,7 +66,9 @@ template <int R> struct PtLayout {           // R = dt_rank of the fused prologu
     static constexpr int XSTAGE = FUSE ? ((PT_TL * XBYTES + 127) / 128) * 128 : PT_TL * 64;
     static constexpr int DDU_OFF = X_OFF + NSTAGE * XSTAGE;           // (delta', delta' u) fp32 pairs; the partial y overwrite them
     static constexpr int BCF_OFF = DDU_OFF + PT_TL * PT_F32ROW;       // fp32 [step][B0..15 C0..15]
-    static constexpr int W_OFF = BCF_OFF + PT_TL * 32 * 4;
+    static constexpr int YROW = 64 * 4 * TPC + 64;                    // TPC > 2: separate partial-y tile, TPC floats per channel and step
+    static constexpr int Y_OFF = BCF_OFF + PT_TL * 32 * 4;
+    static constexpr int W_OFF = Y_OFF + (TPC > 2 ? PT_TL * YROW : 0);
     static constexpr int BAR_OFF = W_OFF + (FUSE ? PT_CH * WROW : 0);
     static constexpr int TOTAL = BAR_OFF + NSTAGE * 8;
 };
@@ -165,21 +166,28 @@ template <typename T> __device__ __forceinline__ void pt_mma_k8(float &d0, float
     }
 }
 
-// one stage (8 steps) of the recurrence for this thread's 8 states; NP of its 4 state pairs use the FMA-pipe exp2.
-// ddu_c: this channel's (delta', delta' u) pairs, one per step; the partial y of the step overwrites the pair (lo half | hi half).
-template <int NP>
-__device__ __forceinline__ void pt_main_stage(unsigned char *ddu_c, const float *bcf_h, int hf, zg_f2 (&h2)[4], const zg_f2 (&Al2p)[4], bool store = true) {
+// one stage (8 steps) of the recurrence for this thread's 16 / TPC states (NPAIR fp32x2 pairs); NP of the pairs use the FMA-pipe exp2.
+// ddu_c: this channel's (delta', delta' u) pairs, one per step.  ypart: where this thread's partial y of step t goes (+ t * ypitch):
+// with two threads per channel the two halves overwrite the pair they were computed from, else a separate tile.
+template <int NP, int TPC>
+__device__ __forceinline__ void pt_main_stage(const unsigned char *ddu_c, const float *bcf_p, unsigned char *ypart, int ypitch,
+                                              zg_f2 (&h2)[8 / TPC], const zg_f2 (&Al2p)[8 / TPC], bool store = true) {
+    constexpr int NPAIR = 8 / TPC, NQ = 4 / TPC;           // state pairs per thread; float4 loads of B (and of C) per step
 #pragma unroll
     for (int t = 0; t < PT_TL; ++t) {
-        const float2 dd = *reinterpret_cast<const float2 *>(ddu_c + t * PT_F32ROW);       // (delta', delta' * u)
-        const float4 *bc = reinterpret_cast<const float4 *>(bcf_h + t * 32);
-        const float4 B0 = bc[0], B1 = bc[1], C0 = bc[4], C1 = bc[5];
-        const zg_f2 Bp[4] = {make_float2(B0.x, B0.y), make_float2(B0.z, B0.w), make_float2(B1.x, B1.y), make_float2(B1.z, B1.w)};
-        const zg_f2 Cp[4] = {make_float2(C0.x, C0.y), make_float2(C0.z, C0.w), make_float2(C1.x, C1.y), make_float2(C1.z, C1.w)};
+        const float2 dd = *reinterpret_cast<const float2 *>(ddu_c + t * PT_F32ROW);      // (delta', delta' * u)
+        const float4 *bc = reinterpret_cast<const float4 *>(bcf_p + t * 32);
+        zg_f2 Bp[NPAIR], Cp[NPAIR];
+#pragma unroll
+        for (int k = 0; k < NQ; ++k) {
+            const float4 Bk = bc[k], Ck = bc[4 + k];
+            Bp[2 * k] = make_float2(Bk.x, Bk.y); Bp[2 * k + 1] = make_float2(Bk.z, Bk.w);
+            Cp[2 * k] = make_float2(Ck.x, Ck.y); Cp[2 * k + 1] = make_float2(Ck.z, Ck.w);
+        }
         const zg_f2 dl = zg_splat2(dd.x), du = zg_splat2(dd.y);
         zg_f2 y2 = zg_splat2(0.f);
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
+        for (int q = 0; q < NPAIR; ++q) {
             const zg_f2 x = zg_mul2(dl, Al2p[q]);
 #if ZG_SCAN_EXP == 5
             const zg_f2 a = zg_add2(x, zg_splat2(1.f));      // experiment: everything but the exponentials
@@ -189,11 +197,11 @@ __device__ __forceinline__ void pt_main_stage(unsigned char *ddu_c, const float 
             h2[q] = zg_fma2(a, h2[q], zg_mul2(du, Bp[q]));
             y2 = zg_fma2(Cp[q], h2[q], y2);
         }
-        // both threads of the channel have read the pair (one converged LDS) before either overwrites its half
+        // (TPC == 2: both threads of the channel have read the pair -- one converged LDS -- before either overwrites its half)
 #if ZG_SCAN_EXP == 3
-        if (store) reinterpret_cast<float *>(ddu_c + t * PT_F32ROW)[hf] = y2.x + y2.y;
+        if (store) *reinterpret_cast<float *>(ypart + t * ypitch) = y2.x + y2.y;
 #else
-        reinterpret_cast<float *>(ddu_c + t * PT_F32ROW)[hf] = y2.x + y2.y;
+        *reinterpret_cast<float *>(ypart + t * ypitch) = y2.x + y2.y;
 #endif
     }
 }
@@ -210,10 +218,15 @@ __device__ __forceinline__ void pt_cp_async_arrive(uint64_t *bar) {
     asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(zg_smem_u32(bar)) : "memory");
 }
 
-template <typename T, int R, int NPOLY, bool CKPT>
-__global__ void __launch_bounds__(PT_THREADS, 9) scan_fwd_tma_kernel(const zg_scan_params p, const __grid_constant__ PtMaps maps) {
+// TPC threads per channel: 2 (16 / 2 = 8 states per thread, 128-thread CTAs, 9 CTAs / SM) is the product mapping; 4 (4 states per
+// thread, 256-thread CTAs: twice the warps for the same instructions per (b, e, l)) is an experiment for under-occupied shapes
+// (ZG_SCAN_TPC=4) that measured slower, see pt_launch_variant.
+template <typename T, int R, int NPOLY, bool CKPT, int TPC = 2>
+__global__ void __launch_bounds__(64 * TPC, TPC == 2 ? 9 : 6) scan_fwd_tma_kernel(const zg_scan_params p, const __grid_constant__ PtMaps maps) {
     static_assert(sizeof(T) == 2, "16-bit I/O only");
-    using LY = PtLayout<R>;
+    static_assert(TPC == 2 || (TPC == 4 && R == 0 && NPOLY == 0), "four threads per channel: unfused, MUFU-only instantiation");
+    using LY = PtLayout<R, TPC>;
+    constexpr int PT_THREADS = 64 * TPC, NPAIR = 8 / TPC, NITEM = 4 / TPC;      // (step, channel pair) items per thread in pre / post
     constexpr bool FUSE = LY::FUSE;
     constexpr int NSTAGE = LY::NSTAGE, TL = PT_TL, CH = PT_CH, TILE = LY::TILE;
     extern __shared__ __align__(1024) unsigned char smem[];
@@ -222,7 +235,7 @@ __global__ void __launch_bounds__(PT_THREADS, 9) scan_fwd_tma_kernel(const zg_sc
     uint64_t *full = reinterpret_cast<uint64_t *>(smem + LY::BAR_OFF);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int hf = tid & 1;
+    const int part = tid % TPC;                                     // which 16 / TPC states of the channel
     const int E = p.dim, L = p.seqlen;
     const int per_group = E / p.ngroups;
     const int tiles_per_group = per_group / CH;
@@ -231,18 +244,18 @@ __global__ void __launch_bounds__(PT_THREADS, 9) scan_fwd_tma_kernel(const zg_sc
     const int tile = blockIdx.x % tiles;
     const int g = tile / tiles_per_group;
     const int e0 = g * per_group + (tile % tiles_per_group) * CH;
-    const int e = e0 + (tid >> 1);                                  // main phase: this thread's channel
+    const int e = e0 + tid / TPC;                                   // main phase: this thread's channel
     const bool has_z = p.z != nullptr;
     const bool z_gather = has_z && p.z_rowmap != nullptr;           // z rows by cp.async through the table
     const bool softplus = (p.flags & ZG_SCAN_DELTA_SOFTPLUS) != 0;
     const int nstages = L / TL;
 
     // ---- per-thread constants -----------------------------------------------------------------------------------
-    zg_f2 Al2p[4], h2[4];
+    zg_f2 Al2p[NPAIR], h2[NPAIR];
     bool a_pos = false;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const float2 a = *reinterpret_cast<const float2 *>(p.A + (int64_t)e * 16 + 8 * hf + 2 * k);
+    for (int k = 0; k < NPAIR; ++k) {
+        const float2 a = *reinterpret_cast<const float2 *>(p.A + (int64_t)e * 16 + 2 * NPAIR * part + 2 * k);
         Al2p[k] = zg_mul2(a, zg_splat2(ZG_LOG2E));
         a_pos = a_pos || a.x > 0.f || a.y > 0.f;
         h2[k] = zg_splat2(0.f);
@@ -251,11 +264,11 @@ __global__ void __launch_bounds__(PT_THREADS, 9) scan_fwd_tma_kernel(const zg_sc
     // the partial y from the 16 bytes its own pre phase filled, so a thread may run pre(s + 1) right after post(s)):
     //   unfused: lane = channel pair, steps warp and warp + 4  (128-byte coalesced output rows)
     //   fused:   step lane / 4, channel pairs 16 warp + 8 k + 2 (lane % 4) -- the m16n8 accumulator layout of the delta tile
-    int it_swz[2], it_ddu[2];                              // byte offsets inside a swizzled 8 x 128 B tile / the fp32 pair tile
-    float2 Dv[2], biasv[2];
+    int it_swz[NITEM], it_ddu[NITEM];                      // byte offsets inside a swizzled 8 x 128 B tile / the fp32 pair tile
+    float2 Dv[NITEM], biasv[NITEM];
 #pragma unroll
-    for (int k = 0; k < 2; ++k) {
-        const int row = FUSE ? (lane >> 2) : warp + 4 * k;
+    for (int k = 0; k < NITEM; ++k) {
+        const int row = FUSE ? (lane >> 2) : warp + 2 * TPC * k;          // (2 TPC warps: rows warp, warp + 4 | row warp)
         const int pair = FUSE ? 8 * warp + 4 * k + (lane & 3) : lane;                  // channel pair 0..31 of the tile
         it_swz[k] = row * 128 + (((pair >> 2) ^ row) << 4) + (pair & 3) * 4;
         it_ddu[k] = row * PT_F32ROW + pair * 16;
@@ -325,6 +338,7 @@ __global__ void __launch_bounds__(PT_THREADS, 9) scan_fwd_tma_kernel(const zg_sc
     // 16 bytes of the pair tile (y read, then (delta', delta' u) written), so they are interleaved item by item: four
     // independent MUFU chains (SiLU of two items, softplus of two items) per thread instead of two after two.
     auto bc_convert = [&](const unsigned char *xt) {      // B | C rows -> fp32 [step][B0..15 C0..15]: one 16-bit pair per thread
+        if (TPC > 2 && tid >= 128) return;
         const int t = tid >> 4, j = tid & 15;
         const uint32_t raw = FUSE ? *reinterpret_cast<const uint32_t *>(xt + t * LY::XBYTES + 2 * R + j * 4)
                                   : *reinterpret_cast<const uint32_t *>(xt + t * 64 + j * 4);
@@ -332,7 +346,7 @@ __global__ void __launch_bounds__(PT_THREADS, 9) scan_fwd_tma_kernel(const zg_sc
     };
     // raw (rounded) delta of the thread's two items: from the delta tile, or (fused) from the tensor-core product
     //     x_dbl[8 steps, 0:R] . W[64 ch, 0:R]^T      (this warp: channels 16 warp .. +15; rows 8..15 of the m16 tile are zero)
-    auto delta_items = [&](const unsigned char *sw, const unsigned char *xt, float2 (&dlt)[2]) {
+    auto delta_items = [&](const unsigned char *sw, const unsigned char *xt, float2 (&dlt)[NITEM]) {
         if constexpr (FUSE) {
             const uint32_t xs = zg_smem_u32(xt), ws = zg_smem_u32(smem + LY::W_OFF);
             float d[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
@@ -371,7 +385,7 @@ __global__ void __launch_bounds__(PT_THREADS, 9) scan_fwd_tma_kernel(const zg_sc
             for (int j = 0; j < 2; ++j) dlt[j] = pt_unpack2<T>(pt_pack2<T>(d[j][0], d[j][1]));
         } else {
 #pragma unroll
-            for (int k = 0; k < 2; ++k) dlt[k] = pt_unpack2<T>(*reinterpret_cast<const uint32_t *>(sw + 2 * TILE + it_swz[k]));
+            for (int k = 0; k < NITEM; ++k) dlt[k] = pt_unpack2<T>(*reinterpret_cast<const uint32_t *>(sw + 2 * TILE + it_swz[k]));
         }
     };
     auto pre_item = [&](int k, float2 dl, const unsigned char *sw) {     // bias, softplus, * u -> (delta', delta' u) pairs
@@ -390,14 +404,22 @@ __global__ void __launch_bounds__(PT_THREADS, 9) scan_fwd_tma_kernel(const zg_sc
     const bool out_rev = (p.flags & ZG_SCAN_OUT_REVERSE) != 0, out_acc = (p.flags & ZG_SCAN_OUT_ACCUMULATE) != 0;
     const int64_t out_row = out_rev ? -p.out_sl : p.out_sl;
     const int r0 = FUSE ? (lane >> 2) : warp;               // the thread's first row of a stage
-    const int64_t out_step = FUSE ? 8 : 4 * out_row;      // element distance between the thread's two output pairs
+    const int64_t out_step = FUSE ? 8 : 4 * out_row;      // element distance between the thread's two output pairs (TPC == 2)
     T *gout = reinterpret_cast<T *>(p.out) + (int64_t)b * p.out_sb + (int64_t)(out_rev ? L - 1 - r0 : r0) * p.out_sl + e0 +
               (FUSE ? 16 * warp + 2 * (lane & 3) : 2 * lane);
     const int64_t out_stage = (int64_t)TL * out_row;
     auto post_item = [&](int k, const unsigned char *sw) {               // y = y_lo + y_hi + D u, SiLU(z) gate, store
-        const float4 yy = *reinterpret_cast<const float4 *>(ddu + it_ddu[k]);   // (lo, hi) halves of 2 channels
+        float2 ysum;
+        if constexpr (TPC == 2) {
+            const float4 yy = *reinterpret_cast<const float4 *>(ddu + it_ddu[k]);   // (lo, hi) halves of 2 channels
+            ysum = zg_add2(make_float2(yy.x, yy.z), make_float2(yy.y, yy.w));
+        } else {                                          // 4 partial sums per channel in the separate y tile
+            const float4 *yp = reinterpret_cast<const float4 *>(smem + LY::Y_OFF + (it_ddu[k] / PT_F32ROW) * LY::YROW + ((it_ddu[k] % PT_F32ROW) / 16) * 32);
+            const float4 a4 = yp[0], b4 = yp[1];
+            ysum = make_float2((a4.x + a4.y) + (a4.z + a4.w), (b4.x + b4.y) + (b4.z + b4.w));
+        }
         const float2 u2 = pt_unpack2<T>(*reinterpret_cast<const uint32_t *>(sw + it_swz[k]));
-        float2 y = zg_fma2(Dv[k], u2, zg_add2(make_float2(yy.x, yy.z), make_float2(yy.y, yy.w)));
+        float2 y = zg_fma2(Dv[k], u2, ysum);
 #if ZG_SCAN_EXP == 1
         if (has_z) y = zg_mul2(y, pt_unpack2<T>(*reinterpret_cast<const uint32_t *>(sw + TILE + it_swz[k])));
 #else
@@ -412,45 +434,47 @@ __global__ void __launch_bounds__(PT_THREADS, 9) scan_fwd_tma_kernel(const zg_sc
     };
 
     // ---- the pipeline ------------------------------------------------------------------------------------------------
-    unsigned char *ddu_c = ddu + (tid >> 1) * 8;
-    const float *bcf_h = bcf + 8 * hf;
+    const unsigned char *ddu_c = ddu + (tid / TPC) * 8;
+    const float *bcf_p = bcf + 2 * NPAIR * part;
+    unsigned char *ypart = TPC == 2 ? ddu + (tid / TPC) * 8 + part * 4 : smem + LY::Y_OFF + (tid / TPC) * 16 + part * 4;
+    constexpr int ypitch = TPC == 2 ? PT_F32ROW : LY::YROW;
     {   // stage 0: pre only
         const unsigned char *sw = smem + LY::SWZ_OFF, *xt = smem + LY::X_OFF;
         zg_mbar_wait(&full[0], 0);
-        float2 dlt[2];
+        float2 dlt[NITEM];
         delta_items(sw, xt, dlt);
-        pre_item(0, dlt[0], sw);
-        pre_item(1, dlt[1], sw);
+#pragma unroll
+        for (int k = 0; k < NITEM; ++k) pre_item(k, dlt[k], sw);
         bc_convert(xt);
     }
     __syncthreads();
     int slot = 0, nslot = 1;
     uint32_t npar = 0;                                       // phase parity of the next stage's slot
     for (int s = 0; s < nstages; ++s) {
-        if (NPOLY > 0 && use_poly) pt_main_stage<NPOLY>(ddu_c, bcf_h, hf, h2, Al2p);
-        else pt_main_stage<0>(ddu_c, bcf_h, hf, h2, Al2p, s == nstages - 1);
+        if (NPOLY > 0 && use_poly) pt_main_stage<NPOLY, TPC>(ddu_c, bcf_p, ypart, ypitch, h2, Al2p);
+        else pt_main_stage<0, TPC>(ddu_c, bcf_p, ypart, ypitch, h2, Al2p, s == nstages - 1);
         if constexpr (CKPT) {       // recompute seeds of the backward: state after every 8 steps, (batch, n_ckpt, dim, dstate)
-            float4 *dst = reinterpret_cast<float4 *>(p.ckpt + (((int64_t)b * (L >> 3) + s) * E + e) * 16 + 8 * hf);
-            dst[0] = make_float4(h2[0].x, h2[0].y, h2[1].x, h2[1].y);
-            dst[1] = make_float4(h2[2].x, h2[2].y, h2[3].x, h2[3].y);
+            float4 *dst = reinterpret_cast<float4 *>(p.ckpt + (((int64_t)b * (L >> 3) + s) * E + e) * 16 + 2 * NPAIR * part);
+#pragma unroll
+            for (int k = 0; k < NPAIR / 2; ++k) dst[k] = make_float4(h2[2 * k].x, h2[2 * k].y, h2[2 * k + 1].x, h2[2 * k + 1].y);
         }
         const unsigned char *sw = smem + LY::SWZ_OFF + slot * LY::NSWZ * TILE;
         const unsigned char *swn = smem + LY::SWZ_OFF + nslot * LY::NSWZ * TILE;
         const unsigned char *xtn = smem + LY::X_OFF + nslot * LY::XSTAGE;
 #if ZG_SCAN_EXP == 2 || ZG_SCAN_EXP == 3
-        if (s == nstages - 1) { post_item(0, sw); post_item(1, sw); }   // experiment: the recurrence alone
+        if (s == nstages - 1) { for (int k = 0; k < NITEM; ++k) post_item(k, sw); }   // experiment: the recurrence alone
 #else
         __syncthreads();            // y complete; B/C tile free
         if (s + 1 < nstages) {      // post(s) interleaved with pre(s + 1)
             zg_mbar_wait(&full[nslot], npar);
-            float2 dlt[2];
+            float2 dlt[NITEM];
             delta_items(swn, xtn, dlt);
 #pragma unroll
-            for (int k = 0; k < 2; ++k) { post_item(k, sw); pre_item(k, dlt[k], swn); }
+            for (int k = 0; k < NITEM; ++k) { post_item(k, sw); pre_item(k, dlt[k], swn); }
             bc_convert(xtn);
         } else {
-            post_item(0, sw);
-            post_item(1, sw);
+#pragma unroll
+            for (int k = 0; k < NITEM; ++k) post_item(k, sw);
         }
         gout += out_stage;
         __syncthreads();            // raw slot of stage s free; tiles of stage s + 1 complete
@@ -460,9 +484,9 @@ __global__ void __launch_bounds__(PT_THREADS, 9) scan_fwd_tma_kernel(const zg_sc
         if (++nslot == NSTAGE) { nslot = 0; npar ^= 1; }
     }
     if (p.last_state) {
-        float4 *dst = reinterpret_cast<float4 *>(p.last_state + ((int64_t)b * E + e) * 16 + 8 * hf);
-        dst[0] = make_float4(h2[0].x, h2[0].y, h2[1].x, h2[1].y);
-        dst[1] = make_float4(h2[2].x, h2[2].y, h2[3].x, h2[3].y);
+        float4 *dst = reinterpret_cast<float4 *>(p.last_state + ((int64_t)b * E + e) * 16 + 2 * NPAIR * part);
+#pragma unroll
+        for (int k = 0; k < NPAIR / 2; ++k) dst[k] = make_float4(h2[2 * k].x, h2[2 * k].y, h2[2 * k + 1].x, h2[2 * k + 1].y);
     }
 }
 
@@ -502,8 +526,8 @@ inline int pt_make_map(CUtensorMap *m, const void *base, int64_t cols, int64_t s
     return 0;
 }
 
-template <typename T, int R, int NPOLY, bool CKPT> int pt_launch(const zg_scan_params &p, cudaStream_t stream) {
-    using LY = PtLayout<R>;
+template <typename T, int R, int NPOLY, bool CKPT, int TPC = 2> int pt_launch(const zg_scan_params &p, cudaStream_t stream) {
+    using LY = PtLayout<R, TPC>;
     PtMaps maps;
     memset(&maps, 0, sizeof(maps));
     int rc = pt_make_map<T>(&maps.u, p.u, p.dim, p.seqlen, p.batch, p.u_sl, p.u_sb, PT_CH, true);
@@ -511,7 +535,7 @@ template <typename T, int R, int NPOLY, bool CKPT> int pt_launch(const zg_scan_p
                         : pt_make_map<T>(&maps.d, p.delta, p.dim, p.seqlen, p.batch, p.delta_sl, p.delta_sb, PT_CH, true);
     if (!rc && p.z && !p.z_rowmap) rc = pt_make_map<T>(&maps.z, p.z, p.dim, p.seqlen, p.batch, p.z_sl, p.z_sb, PT_CH, true);
     if (rc) return rc;
-    auto kern = scan_fwd_tma_kernel<T, R, NPOLY, CKPT>;
+    auto kern = scan_fwd_tma_kernel<T, R, NPOLY, CKPT, TPC>;
     static bool attr_set = false;       // per instantiation (the library drives one device per process)
     if (!attr_set) {
         cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, LY::TOTAL);
@@ -520,7 +544,7 @@ template <typename T, int R, int NPOLY, bool CKPT> int pt_launch(const zg_scan_p
         attr_set = true;
     }
     const long long nblk = (long long)(p.dim / PT_CH) * p.batch;
-    kern<<<(unsigned)nblk, PT_THREADS, LY::TOTAL, stream>>>(p, maps);
+    kern<<<(unsigned)nblk, 64 * TPC, LY::TOTAL, stream>>>(p, maps);
     zg_count_launch();
     return zg_check_launch("scan_fwd(tma)");
 }
@@ -528,6 +552,15 @@ template <typename T, int R, int NPOLY, bool CKPT> int pt_launch(const zg_scan_p
 template <typename T, int R> int pt_launch_variant(const zg_scan_params &p, cudaStream_t stream) {
     static int npoly = -1;
     if (npoly < 0) { npoly = pt_env_int("ZG_SCAN_TMA_NPOLY", ZG_SCAN_TMA_NPOLY_DEFAULT); if (npoly < 0 || npoly > 2) npoly = 0; }
+    if constexpr (R == 0) {
+        // ZG_SCAN_TPC=4: four threads per channel (twice the warps for the same work).  Opt-in only: measured SLOWER than two at
+        // every under-occupied shape it was meant for (bs 32, L 4096, E 1536: 1.72 vs 1.46 ms; bs 16, L 1024, E 1280: 0.249 vs
+        // 0.224 ms) -- eight warps per barrier cost more than the extra warps hide -- and a batch-size dependent choice would
+        // make results depend on the batch split (the partial sums of y associate differently).
+        static int tpc_env = -1;
+        if (tpc_env < 0) tpc_env = pt_env_int("ZG_SCAN_TPC", 2);
+        if (tpc_env == 4) return p.ckpt ? pt_launch<T, 0, 0, true, 4>(p, stream) : pt_launch<T, 0, 0, false, 4>(p, stream);
+    }
     if (p.ckpt) return pt_launch<T, R, 0, true>(p, stream);        // training forward (writes the recompute seeds)
     if (npoly == 1) return pt_launch<T, R, 1, false>(p, stream);
     if (npoly == 2) return pt_launch<T, R, 2, false>(p, stream);

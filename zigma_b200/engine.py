@@ -159,6 +159,7 @@ class ZigMaEngine:
         self.ada_w = torch.cat([b.adaLN_modulation[1].weight.detach() for b in m.blocks], dim=0).contiguous()
         self.ada_b = torch.cat([b.adaLN_modulation[1].bias.detach() for b in m.blocks], dim=0).contiguous()
         self._rev_cache = {}
+        self._pe_w = None                       # zero-padded patch-embedding weight (bf16), built on first use
         self._versions = self._param_versions()
         self._graphs = {}
 
@@ -192,6 +193,34 @@ class ZigMaEngine:
             y, _, _, _ = _scan_fwd(xc, d_log, w["A"], B_log, C_log, w["D"], z_log, w["dt_bias"], True,
                                    z_rowmap=rowmap, want_last_state=False, want_ckpt=False, **extra)
         return y.transpose(1, 2)                                                            # (Bt, L, E) contiguous
+
+    def _patch_embed(self, x):
+        """Patch embedding (model_zigma.py:608-614: a Conv2d with kernel = stride = patch, i.e. a per-patch linear map) as a GEMM
+        on the tcgen05 kernel: the K = C p^2 columns (4 at patch 1) are zero-padded to the 16-byte row pitch TMA needs.  Returns
+        (B, L, D) tokens, or None when the model is not bf16 (the module's own forward runs then)."""
+        m = self.m
+        if x.dtype != torch.bfloat16 or os.environ.get("ZIGMA_TCGEN05", "1") != "1":
+            return None
+        emb = m.x_embedder
+        p = emb.patch_size[0]
+        lead = x.shape[:-3]
+        x4 = x.reshape(-1, *x.shape[-3:])                    # video: (B T, C, H, W)
+        Bn, C, H, W = x4.shape
+        if p == 1:
+            tok = x4.flatten(2).transpose(1, 2)
+        else:
+            tok = x4.reshape(Bn, C, H // p, p, W // p, p).permute(0, 2, 4, 1, 3, 5).reshape(Bn, (H // p) * (W // p), C * p * p)
+        K = tok.shape[-1]
+        if self._pe_w is None:
+            Kp = (K + 7) // 8 * 8
+            w = torch.zeros((emb.proj.weight.shape[0], Kp), dtype=torch.bfloat16, device=x.device)
+            w[:, :K] = emb.proj.weight.detach().reshape(w.shape[0], -1)
+            self._pe_w = w
+        Kp = self._pe_w.shape[1]
+        tp = torch.zeros((tok.shape[0] * tok.shape[1], Kp), dtype=torch.bfloat16, device=x.device)
+        tp[:, :K] = tok.reshape(-1, K)
+        out = _linear(tp, self._pe_w, None if emb.proj.bias is None else emb.proj.bias.detach())
+        return out.view(*lead[:1], -1, out.shape[-1]) if len(lead) == 2 else out.view(Bn, -1, out.shape[-1])
 
     def _temporal_fused_ok(self, dtype, lay, T, K):
         E, N = lay["E"], lay["N"]
@@ -278,12 +307,12 @@ class ZigMaEngine:
     # ---- whole forward -----------------------------------------------------------------------------
     def _forward_impl(self, x, t, y):
         m = self.m
-        hs, c, text = m.embed(x, t, y)
+        hs, c, text = m.embed(x, t, y, tokens=self._patch_embed(x))
         hs = hs.contiguous()
         B, L, D = hs.shape
         depth = len(self.layers)
         nmod = 6 if m.has_text else 3          # (+ shift, scale, gate of the text cross-attention branch)
-        mods = F.linear(F.silu(c), self.ada_w, self.ada_b).view(B, depth, nmod, D)  # shift, scale, gate per block
+        mods = _linear(F.silu(c), self.ada_w, self.ada_b).view(B, depth, nmod, D)  # shift, scale, gate per block (one GEMM for all)
         eps = m.blocks[0].norm.eps
         lay0 = self.layers[0]
         residual, normed, modded = block_tail(hs, None, None, mods[:, 0, 0], mods[:, 0, 1], lay0["norm_w"], None, None, eps)
@@ -315,7 +344,7 @@ class ZigMaEngine:
                     residual, modded = residual.view(B, L, D), modded.view(B, L, D)
             else:
                 residual, normed, modded = block_tail(normed, mix, gate, shift, scale, nw, residual, rowmap, neps, final=last)
-        out = F.linear(normed, m.final_layer.linear.weight, m.final_layer.linear.bias)
+        out = _linear(normed.reshape(B * L, D), m.final_layer.linear.weight, m.final_layer.linear.bias).view(B, L, -1)   # un-embed
         if m.video_frames > 0:
             return m.unpatchify_video(out, m.video_frames)
         return m.unpatchify(out)

@@ -372,9 +372,10 @@ class ZigMa(nn.Module):
                 .reshape(x.shape[0], video_frames, c, h * p, w * p))
 
     # ---- forward ----------------------------------------------------------------------------------
-    def embed(self, hidden_states, t, y=None):
-        """Everything before the blocks (model_zigma.py:923-947): tokens (B, L, D) and conditioning c."""
-        hidden_states = self.x_embedder(hidden_states)
+    def embed(self, hidden_states, t, y=None, tokens=None):
+        """Everything before the blocks (model_zigma.py:923-947): tokens (B, L, D) and conditioning c.  ``tokens``: the
+        patch-embedding result when the caller computed it itself (the sampling engine runs that GEMM on its tcgen05 kernel)."""
+        hidden_states = self.x_embedder(hidden_states) if tokens is None else tokens
         _B = hidden_states.shape[0]
         t = self.t_embedder((t * 1000.0).to(hidden_states))
         if self.has_text:
