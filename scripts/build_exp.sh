@@ -1,13 +1,15 @@
 #!/bin/bash
-# builds build/exp/libzigma_exp$1.so with -DZG_SCAN_EXP=$1 (timing experiments of the scan kernel; results are wrong by design)
+# builds zigma_b200/lib/libzigma_exp<name>.so with extra nvcc flags for the scan TU (timing experiments of the scan kernel)
+#   scripts/build_exp.sh 3 "-DZG_SCAN_EXP=3"      scripts/build_exp.sh noswp "-DZG_SCAN_SWP=0"
 set -e
 cd "$(dirname "$0")/.."
-mkdir -p build/exp/obj$1
-FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -DZG_SCAN_EXP=$1"
+name=$1; extra=${2:--DZG_SCAN_EXP=$1}
+mkdir -p build/exp/obj$name
+FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC $extra"
 for f in zigma_b200/csrc/*.cu; do
-  o=build/exp/obj$1/$(basename ${f%.cu}).o
+  o=build/exp/obj$name/$(basename ${f%.cu}).o
   case $(basename $f) in scan_fwd_bf16.cu) nvcc $FLAGS -c $f -o $o & ;; *) cp build/obj/$(basename ${f%.cu}).o $o ;; esac
 done
 wait
-nvcc -gencode arch=compute_100a,code=sm_100a -shared -o zigma_b200/lib/libzigma_exp$1.so build/exp/obj$1/*.o -lcudart -lcuda
-echo built zigma_b200/lib/libzigma_exp$1.so
+nvcc -gencode arch=compute_100a,code=sm_100a -shared -o zigma_b200/lib/libzigma_exp$name.so build/exp/obj$name/*.o -lcudart -lcuda
+echo built zigma_b200/lib/libzigma_exp$name.so

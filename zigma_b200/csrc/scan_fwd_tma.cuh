@@ -41,6 +41,9 @@
 #ifndef ZG_SCAN_EXP
 #define ZG_SCAN_EXP 0      // 1, 2: timing experiments (wrong results), see DESIGN.md
 #endif
+#ifndef ZG_SCAN_SWP
+#define ZG_SCAN_SWP 1      // hand software-pipelined recurrence loop (0: the straight loop)
+#endif
 #ifndef ZG_SCAN_TMA_NPOLY_DEFAULT
 #define ZG_SCAN_TMA_NPOLY_DEFAULT 0
 #endif
@@ -169,10 +172,58 @@ template <typename T> __device__ __forceinline__ void pt_mma_k8(float &d0, float
 // one stage (8 steps) of the recurrence for this thread's 16 / TPC states (NPAIR fp32x2 pairs); NP of the pairs use the FMA-pipe exp2.
 // ddu_c: this channel's (delta', delta' u) pairs, one per step.  ypart: where this thread's partial y of step t goes (+ t * ypitch):
 // with two threads per channel the two halves overwrite the pair they were computed from, else a separate tile.
+// Software-pipelined by hand (ZG_SCAN_SWP, default on): ptxas emits the unrolled steps strictly one after the other
+// (LDS -> FMUL2 -> 8 MUFU -> FFMA2 chain -> STS, ~140 cycles of dependent latency per step and warp), so the decay factors
+// exp2(delta' A) of step t + 1 -- which depend on nothing but (delta', A) -- are issued BEFORE the FMA part of step t.
 template <int NP, int TPC>
-__device__ __forceinline__ void pt_main_stage(const unsigned char *ddu_c, const float *bcf_p, unsigned char *ypart, int ypitch,
+__device__ __forceinline__ void pt_main_stage(const unsigned char *__restrict__ ddu_c, const float *__restrict__ bcf_p, unsigned char *__restrict__ ypart, int ypitch,
                                               zg_f2 (&h2)[8 / TPC], const zg_f2 (&Al2p)[8 / TPC], bool store = true) {
     constexpr int NPAIR = 8 / TPC, NQ = 4 / TPC;           // state pairs per thread; float4 loads of B (and of C) per step
+    auto decay = [&](float dlx, zg_f2 (&a)[NPAIR]) {
+        const zg_f2 dl = zg_splat2(dlx);
+#pragma unroll
+        for (int q = 0; q < NPAIR; ++q) {
+            const zg_f2 x = zg_mul2(dl, Al2p[q]);
+#if ZG_SCAN_EXP == 5
+            a[q] = zg_add2(x, zg_splat2(1.f));              // experiment: everything but the exponentials
+#else
+            a[q] = (q < NP) ? zg_ex2_poly2_neg(x) : zg_ex2_mufu2(x);
+#endif
+        }
+    };
+#if ZG_SCAN_SWP
+    zg_f2 a_cur[NPAIR];
+    float2 dd = *reinterpret_cast<const float2 *>(ddu_c);
+    decay(dd.x, a_cur);
+#pragma unroll
+    for (int t = 0; t < PT_TL; ++t) {
+        const float4 *bc = reinterpret_cast<const float4 *>(bcf_p + t * 32);
+        zg_f2 Bp[NPAIR], Cp[NPAIR];
+#pragma unroll
+        for (int k = 0; k < NQ; ++k) {
+            const float4 Bk = bc[k], Ck = bc[4 + k];
+            Bp[2 * k] = make_float2(Bk.x, Bk.y); Bp[2 * k + 1] = make_float2(Bk.z, Bk.w);
+            Cp[2 * k] = make_float2(Ck.x, Ck.y); Cp[2 * k + 1] = make_float2(Ck.z, Ck.w);
+        }
+        const zg_f2 du = zg_splat2(dd.y);
+        zg_f2 a_nxt[NPAIR];
+        if (t + 1 < PT_TL) {                               // next step's pair and decays: in flight during this step's FMAs
+            dd = *reinterpret_cast<const float2 *>(ddu_c + (t + 1) * PT_F32ROW);
+            decay(dd.x, a_nxt);
+        }
+        zg_f2 y2 = zg_splat2(0.f);
+#pragma unroll
+        for (int q = 0; q < NPAIR; ++q) {
+            h2[q] = zg_fma2(a_cur[q], h2[q], zg_mul2(du, Bp[q]));
+            y2 = zg_fma2(Cp[q], h2[q], y2);
+        }
+        *reinterpret_cast<float *>(ypart + t * ypitch) = y2.x + y2.y;
+        if (t + 1 < PT_TL) {
+#pragma unroll
+            for (int q = 0; q < NPAIR; ++q) a_cur[q] = a_nxt[q];
+        }
+    }
+#else
 #pragma unroll
     for (int t = 0; t < PT_TL; ++t) {
         const float2 dd = *reinterpret_cast<const float2 *>(ddu_c + t * PT_F32ROW);      // (delta', delta' * u)
@@ -184,17 +235,13 @@ __device__ __forceinline__ void pt_main_stage(const unsigned char *ddu_c, const 
             Bp[2 * k] = make_float2(Bk.x, Bk.y); Bp[2 * k + 1] = make_float2(Bk.z, Bk.w);
             Cp[2 * k] = make_float2(Ck.x, Ck.y); Cp[2 * k + 1] = make_float2(Ck.z, Ck.w);
         }
-        const zg_f2 dl = zg_splat2(dd.x), du = zg_splat2(dd.y);
+        const zg_f2 du = zg_splat2(dd.y);
+        zg_f2 a[NPAIR];
+        decay(dd.x, a);
         zg_f2 y2 = zg_splat2(0.f);
 #pragma unroll
         for (int q = 0; q < NPAIR; ++q) {
-            const zg_f2 x = zg_mul2(dl, Al2p[q]);
-#if ZG_SCAN_EXP == 5
-            const zg_f2 a = zg_add2(x, zg_splat2(1.f));      // experiment: everything but the exponentials
-#else
-            const zg_f2 a = (q < NP) ? zg_ex2_poly2_neg(x) : zg_ex2_mufu2(x);
-#endif
-            h2[q] = zg_fma2(a, h2[q], zg_mul2(du, Bp[q]));
+            h2[q] = zg_fma2(a[q], h2[q], zg_mul2(du, Bp[q]));
             y2 = zg_fma2(Cp[q], h2[q], y2);
         }
         // (TPC == 2: both threads of the channel have read the pair -- one converged LDS -- before either overwrites its half)
@@ -204,6 +251,7 @@ __device__ __forceinline__ void pt_main_stage(const unsigned char *ddu_c, const 
         *reinterpret_cast<float *>(ypart + t * ypitch) = y2.x + y2.y;
 #endif
     }
+#endif
 }
 
 struct PtMaps { CUtensorMap u, d, z; };    // (channels | x_dbl columns, seqlen, batch) tensor tiles of u, delta | x_dbl, z
