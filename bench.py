@@ -113,10 +113,12 @@ def measured_peaks():
 # ------------------------------------------------------------------------------------------------
 def cpu_reference_setup(name):
     import torch
-    from oracle import zigma_oracle as zo, synth as osynth
+    from oracle import zigma_oracle as zo, synth as osynth, c_oracle
     from oracle.shapes import zigma_state_shapes
     wl = WORKLOADS[name]
     zo.USE_C_SCAN = True                       # the plain-C OpenMP port of the recurrence (fp32)
+    # all host cores for the C loops whatever the launcher exported (torchrun sets OMP_NUM_THREADS=1 in every rank)
+    c_oracle.set_threads(os.cpu_count() or 1)
     sd = osynth.synth_state_dict(zigma_state_shapes(wl["cfg"]), seed=0)
     cfg = dict(wl["cfg"], norm_epsilon=1e-5)
     return zo, osynth, sd, cfg, torch

@@ -24,6 +24,11 @@ def lib():
     return _lib
 
 
+def set_threads(n):
+    """OpenMP threads of the C loops (returns the resulting maximum)."""
+    return int(lib().zigma_oracle_set_threads(int(n)))
+
+
 def _p(a):
     return None if a is None else a.ctypes.data_as(ctypes.POINTER(ctypes.c_float))
 

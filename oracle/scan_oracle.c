@@ -79,3 +79,12 @@ int zigma_oracle_conv1d_fwd(const float *x, const float *w, const float *bias, i
     }
     return 0;
 }
+
+/* number of OpenMP threads of the two loops above (0 = leave the runtime default).  bench.py's CPU arm calls this: launchers such
+ * as torchrun export OMP_NUM_THREADS=1 into every rank, which would silently turn the all-cores baseline into a 1-thread run. */
+#ifdef _OPENMP
+#include <omp.h>
+int zigma_oracle_set_threads(int n) { if (n > 0) omp_set_num_threads(n); return omp_get_max_threads(); }
+#else
+int zigma_oracle_set_threads(int n) { (void)n; return 1; }
+#endif
