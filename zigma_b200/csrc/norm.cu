@@ -6,6 +6,7 @@
 // HBM-bound: one warp per token row, 16-byte vector loads, the fp32 row lives in registers between
 // the statistics pass and the normalisation pass (single global read of every operand).
 #include "zg_common.cuh"
+#include <stdlib.h>
 
 namespace zg {
 
@@ -413,8 +414,163 @@ __global__ void __launch_bounds__(128, (MAXQ <= 6) ? 6 : 1) block_tail_kernel(co
     }
 }
 
+#ifndef ZG_TAIL_PREFETCH_MOD
+#define ZG_TAIL_PREFETCH_MOD 1
+#endif
+#ifndef ZG_TAIL_MINB
+#define ZG_TAIL_MINB 12
+#endif
+// Round 2: FOUR warps per row (one 128-thread CTA = one token row).  The one-warp-per-row kernel above keeps a whole row in the
+// registers of 32 lanes (67 registers at D = 640 -> 7 CTAs = 28 warps per SM, 42 % occupancy) and ncu shows it purely
+// latency-bound: long_scoreboard 12.9 warps per issue, issue 36 %, 4.5 TB/s (profiles/r02_tail_conv_ncu.txt).  Spreading the row
+// over 128 lanes leaves 1-2 quads per lane (about half the registers, twice the resident warps) at the price of one
+// shared-memory reduction per statistic.  Same arithmetic and rounding points.  Measured at config 2 (672 MB per call):
+// 149.7 us (one warp per row) -> 136.5 us (this kernel, 40 registers, 12 CTAs / SM) -> 121.1 us = 5.54 TB/s = 0.84 of the measured
+// HBM peak with the scale / shift rows prefetched too (ZG_TAIL_PREFETCH_MOD); 32 registers / 16 CTAs without that prefetch: 122.0 us.
+template <typename T, int MAXQ>
+__global__ void __launch_bounds__(128, ZG_TAIL_MINB) block_tail_row4_kernel(const zg_block_tail_params p) {
+    __shared__ float red[3][4];
+    const int64_t row = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int D = p.dim, nq = D >> 2;
+    const int b = (int)(row / p.seqlen), l = (int)(row % p.seqlen);
+    const T *x = reinterpret_cast<const T *>(p.x) + row * D;
+    const T *mix = nullptr;
+    if (p.mix) {
+        const int64_t src = (int64_t)b * p.seqlen + (p.rowmap ? p.rowmap[l] : l);
+        mix = reinterpret_cast<const T *>(p.mix) + src * D;
+    }
+    const T *gate = p.gate ? reinterpret_cast<const T *>(p.gate) + (int64_t)b * p.mod_rs : nullptr;
+    const T *shift = p.shift ? reinterpret_cast<const T *>(p.shift) + (int64_t)b * p.mod_rs : nullptr;
+    const T *scale = p.scale ? reinterpret_cast<const T *>(p.scale) + (int64_t)b * p.mod_rs : nullptr;
+    const T *nw = reinterpret_cast<const T *>(p.norm_w);
+    const float *res = p.residual ? p.residual + row * D : nullptr;
+    float *rout = p.residual_out ? p.residual_out + row * D : nullptr;
+    T *normed = reinterpret_cast<T *>(p.normed) + row * D;
+    T *modded = p.modded ? reinterpret_cast<T *>(p.modded) + row * D : nullptr;
+    auto block_sum = [&](float v, int slot) {
+        v = zg_warp_sum(v);
+        if (lane == 0) red[slot][warp] = v;
+        __syncthreads();
+        return (red[slot][0] + red[slot][1]) + (red[slot][2] + red[slot][3]);
+    };
+
+    // every load of the row (and of the per-column operands) is issued before the first use
+    Raw4<T> rx[MAXQ], rm[MAXQ], rg[MAXQ], rw[MAXQ];
+#if ZG_TAIL_PREFETCH_MOD
+    Raw4<T> rsc[MAXQ], rsh[MAXQ];
+#endif
+    float4 rr[MAXQ];
+#pragma unroll
+    for (int k = 0; k < MAXQ; ++k) {
+        const int q = tid + 128 * k;
+        if (q < nq) {
+            rx[k] = ldraw<T>(x, 4 * q);
+            if (mix) { rm[k] = ldraw<T>(mix, 4 * q); rg[k] = ldraw<T>(gate, 4 * q); }
+            if (res) rr[k] = *reinterpret_cast<const float4 *>(res + 4 * q);
+            rw[k] = ldraw<T>(nw, 4 * q);
+#if ZG_TAIL_PREFETCH_MOD
+            if (modded) { rsc[k] = ldraw<T>(scale, 4 * q); rsh[k] = ldraw<T>(shift, 4 * q); }
+#endif
+        }
+    }
+    float r[MAXQ][4];
+    float sumsq = 0.f;
+#pragma unroll
+    for (int k = 0; k < MAXQ; ++k) {
+        const int q = tid + 128 * k;
+        if (q < nq) {
+            cvt4<T>(rx[k], r[k]);
+            if (mix) {
+                float m[4], g[4];
+                cvt4<T>(rm[k], m);
+                cvt4<T>(rg[k], g);
+#pragma unroll
+                for (int i = 0; i < 4; ++i)   // x + gate * mixer(...)  each op rounded to T as in eager torch
+                    r[k][i] = round_to<T>(r[k][i] + round_to<T>(g[i] * m[i]));
+            }
+            if (res) {
+                r[k][0] += rr[k].x; r[k][1] += rr[k].y; r[k][2] += rr[k].z; r[k][3] += rr[k].w;
+            }
+            if (rout) st4<float>(rout, 4 * q, r[k]);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) sumsq += r[k][i] * r[k][i];
+        }
+    }
+    const float rstd = 1.f / sqrtf(block_sum(sumsq, 0) / D + p.eps);
+    if (p.rstd && tid == 0) p.rstd[row] = rstd;
+    float sum2 = 0.f;
+#pragma unroll
+    for (int k = 0; k < MAXQ; ++k) {
+        const int q = tid + 128 * k;
+        if (q < nq) {
+            float w[4];
+            cvt4<T>(rw[k], w);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                r[k][i] = round_to<T>(r[k][i] * rstd * w[i]);   // RMSNorm output as stored by the reference
+                sum2 += r[k][i];
+            }
+        }
+    }
+    if (p.final_layer) {
+        // norm_final = LayerNorm(no affine, eps 1e-6) on the materialised norm_f output (model_zigma.py:320,335)
+        const float mean = block_sum(sum2, 1) / D;
+        float s2 = 0.f;
+#pragma unroll
+        for (int k = 0; k < MAXQ; ++k)
+            if (tid + 128 * k < nq)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) { const float d = r[k][i] - mean; s2 += d * d; }
+        const float rstd2 = 1.f / sqrtf(block_sum(s2, 2) / D + 1e-6f);
+#pragma unroll
+        for (int k = 0; k < MAXQ; ++k) {
+            const int q = tid + 128 * k;
+            if (q < nq) {
+                float o[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) o[i] = (r[k][i] - mean) * rstd2;
+                st4<T>(normed, 4 * q, o);
+            }
+        }
+        return;
+    }
+#pragma unroll
+    for (int k = 0; k < MAXQ; ++k) {
+        const int q = tid + 128 * k;
+        if (q < nq) {
+            st4<T>(normed, 4 * q, r[k]);
+            if (modded) {
+                float sc[4], sh[4], o[4];
+#if ZG_TAIL_PREFETCH_MOD
+                cvt4<T>(rsc[k], sc);
+                cvt4<T>(rsh[k], sh);
+#else
+                ld4<T>(scale, 4 * q, sc);
+                ld4<T>(shift, 4 * q, sh);
+#endif
+#pragma unroll
+                for (int i = 0; i < 4; ++i)   // x * (1 + scale) + shift, eager-torch rounding points
+                    o[i] = round_to<T>(r[k][i] * round_to<T>(1.f + sc[i])) + sh[i];
+                st4<T>(modded, 4 * q, o);
+            }
+        }
+    }
+}
+
 template <typename T> static int block_tail_t(const zg_block_tail_params &p, cudaStream_t s) {
     const int64_t nrows = (int64_t)p.batch * p.seqlen;
+    static int row4 = -1;       // ZG_TAIL_ROW4=0: the round-1 kernel (one warp per row)
+    if (row4 < 0) { const char *e = getenv("ZG_TAIL_ROW4"); row4 = e ? atoi(e) : 1; }
+    if (row4 && nrows <= 0x7fffffffLL && p.dim <= 2048) {
+        const unsigned g4 = (unsigned)nrows;
+        if (p.dim <= 512) block_tail_row4_kernel<T, 1><<<g4, 128, 0, s>>>(p);
+        else if (p.dim <= 1024) block_tail_row4_kernel<T, 2><<<g4, 128, 0, s>>>(p);
+        else if (p.dim <= 1536) block_tail_row4_kernel<T, 3><<<g4, 128, 0, s>>>(p);
+        else block_tail_row4_kernel<T, 4><<<g4, 128, 0, s>>>(p);
+        zg_count_launch();
+        return zg_check_launch("block_tail_fwd");
+    }
     const unsigned grid = (unsigned)((nrows * 32 + 127) / 128);
     // MAXQ = ceil(D / 128) exactly for the model widths of the reference zoo (368, 640, 768, 1024, 1536): the raw
     // operand vectors of a row live in registers, so an over-sized MAXQ costs occupancy (ncu round 1: 92 registers at
