@@ -128,7 +128,10 @@ __global__ void __launch_bounds__(128, 5) conv_fwd_dimc_kernel(const zg_conv_par
 // the generic kernel's 28 (ncu round 1: the generic kernel was instruction-issue bound at 52 % issue
 // utilisation, 130 us for 335 MB).
 template <typename T>
-__global__ void __launch_bounds__(128, 6) conv_fwd_tok4_kernel(const zg_conv_params p) {
+#ifndef ZG_CONV_MINB
+#define ZG_CONV_MINB 8      // (64 registers, 8 CTAs per SM: 74.0 us vs 75.4 at 6; fetching 4 rows per batch instead of 8: 83-88 us)
+#endif
+__global__ void __launch_bounds__(128, ZG_CONV_MINB) conv_fwd_tok4_kernel(const zg_conv_params p) {
     static_assert(sizeof(T) == 2, "16-bit I/O");
     const int E = p.dim, L = p.seqlen, W = p.width;
     const int nvec = E >> 2;
@@ -177,17 +180,21 @@ __global__ void __launch_bounds__(128, 6) conv_fwd_tok4_kernel(const zg_conv_par
         unpack(hist >= 2 ? *row_ptr(l0 - 2) : zero, x2);
         unpack(hist >= 3 ? *row_ptr(l0 - 3) : zero, x3);
     }
+#ifndef ZG_CONV_RB4
+#define ZG_CONV_RB4 CONV_RB
+#endif
+    constexpr int RB4 = ZG_CONV_RB4;       // rows fetched per batch of independent loads in this kernel
 #pragma unroll 1
-    for (int lb = 0; lb < CONV_LCH; lb += CONV_RB) {
+    for (int lb = 0; lb < CONV_LCH; lb += RB4) {
         if (seg > 0 && lb > 0 && ((l0 + lb) % seg) == 0) {      // a new segment starts with this batch of rows: zero history
 #pragma unroll
             for (int h = 0; h < 2; ++h) x1[h] = x2[h] = x3[h] = make_float2(0.f, 0.f);
         }
-        uint2 raw[CONV_RB];
+        uint2 raw[RB4];
 #pragma unroll
-        for (int j = 0; j < CONV_RB; ++j) raw[j] = *row_ptr(l0 + lb + j);
+        for (int j = 0; j < RB4; ++j) raw[j] = *row_ptr(l0 + lb + j);
 #pragma unroll
-        for (int j = 0; j < CONV_RB; ++j) {
+        for (int j = 0; j < RB4; ++j) {
             zg_f2 x0[2];
             unpack(raw[j], x0);
             uint2 o;
