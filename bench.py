@@ -536,12 +536,13 @@ def main():
         # bounded sample of the same workload on the host cores: ONE evaluation at a reduced batch (the full batch is what
         # `--impl reference` times); reported per token
         cores = os.cpu_count() or 1
+        threads = int(os.environ.get("ZIGMA_REF_THREADS", "0")) or min(cores, 32)
         sbs = max(1, min(bs, 8))
         st = cpu_reference_setup(name)
-        cpu_reference_eval(name, 1, st, cores)
-        dt, _ = cpu_reference_eval(name, sbs, st, cores)
+        cpu_reference_eval(name, 1, st, threads)
+        dt, _ = cpu_reference_eval(name, sbs, st, threads)
         line["cpu_baseline"] = {"value": sbs * wl["tokens"] / dt, "unit": "tokens/s", "cores": cores, "kind": "port",
-                                "sample": f"1 denoiser evaluation at bs={sbs} of the same workload (fp32 CPU restatement of the reference path: torch GEMMs + OpenMP C scan); the full bs={bs} evaluation is what --impl reference times"}
+                                "sample": f"1 denoiser evaluation at bs={sbs} of the same workload (fp32 CPU restatement of the reference path: torch GEMMs on {threads} threads + OpenMP C scan on all cores); the full bs={bs} evaluation is what --impl reference times"}
     print(json.dumps(line))
 
 
