@@ -466,18 +466,19 @@ template <int BN, int CL, bool TWO = false> static int launch_gemm(const zg_gemm
                p.rows_per_batch > 0 ? p.rows_per_batch : p.M, tma_store_ok ? 1 : 0};
     const int smem = gemm_stages(BN, TWO) * (G_BM * G_BK * 2 + (TWO ? BN / 2 : BN) * G_BK * 2) + 4 * 2 * 32 * 128 + 1024 + 512;
     auto kern = gemm_bf16_tn_kernel<BN, CL, TWO>;
-    static bool attr = false;
-    if (!attr) {
+    // per DEVICE (function attributes and SM counts are device state; one process may drive several GPUs)
+    static bool attr_dev[64] = {};
+    static int sms_dev[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const int di = dev & 63;
+    if (!attr_dev[di]) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return zg_set_error("gemm_bf16_tn: cudaFuncSetAttribute(%d): %s", smem, cudaGetErrorString(e));
-        attr = true;
+        attr_dev[di] = true;
     }
-    static int sms = 0;
-    if (!sms) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    }
+    if (!sms_dev[di]) cudaDeviceGetAttribute(&sms_dev[di], cudaDevAttrMultiProcessorCount, dev);
+    const int sms = sms_dev[di];
     const int m_tiles = (p.M + G_BM - 1) / G_BM, n_tiles = (p.N + BN - 1) / BN;
     const int work = ((m_tiles + CL - 1) / CL) * n_tiles;          // cluster work items
     int clusters = sms / CL;

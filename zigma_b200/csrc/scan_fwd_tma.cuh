@@ -584,12 +584,14 @@ template <typename T, int R, int NPOLY, bool CKPT, int TPC = 2> int pt_launch(co
     if (!rc && p.z && !p.z_rowmap) rc = pt_make_map<T>(&maps.z, p.z, p.dim, p.seqlen, p.batch, p.z_sl, p.z_sb, PT_CH, true);
     if (rc) return rc;
     auto kern = scan_fwd_tma_kernel<T, R, NPOLY, CKPT, TPC>;
-    static bool attr_set = false;       // per instantiation (the library drives one device per process)
-    if (!attr_set) {
+    static bool attr_dev[64] = {};      // per instantiation and device
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!attr_dev[dev & 63]) {
         cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, LY::TOTAL);
         if (err != cudaSuccess) return zg_set_error("scan_fwd(tma): cudaFuncSetAttribute(%d B smem): %s", LY::TOTAL, cudaGetErrorString(err));
         cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        attr_set = true;
+        attr_dev[dev & 63] = true;
     }
     const long long nblk = (long long)(p.dim / PT_CH) * p.batch;
     kern<<<(unsigned)nblk, 64 * TPC, LY::TOTAL, stream>>>(p, maps);

@@ -242,8 +242,9 @@ class SelectiveScanFn(torch.autograd.Function):
         ctx.delta_softplus = delta_softplus
         ctx.has_D, ctx.has_z, ctx.has_bias = D is not None, z is not None, delta_bias is not None
         if need_grad:
-            ctx.saved = saved
-            ctx.ckpt = ckpt
+            # (autograd's own storage: version checks catch an in-place change between forward and backward, saved-tensor hooks
+            # and checkpointing see the tensors)
+            ctx.save_for_backward(*saved, ckpt)
         if return_last_state:
             ctx.mark_non_differentiable(last)
             return out, last
@@ -251,8 +252,9 @@ class SelectiveScanFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dout, *args):
-        du, ddelta, dA, dB, dC, dD, dbias, dz = _scan_bwd(ctx.saved, ctx.ckpt, dout, ctx.delta_softplus)
-        u = ctx.saved[0]
+        *saved, ckpt = ctx.saved_tensors
+        du, ddelta, dA, dB, dC, dD, dbias, dz = _scan_bwd(tuple(saved), ckpt, dout, ctx.delta_softplus)
+        u = saved[0]
         dB = dB.to(u.dtype)
         dC = dC.to(u.dtype)
         if ctx.squeeze_B:
@@ -315,7 +317,7 @@ def _inner_fwd(xz, conv1d_weight, conv1d_bias, x_proj_weight, delta_proj_weight,
 def _inner_bwd(ctx, dout_y, out_proj_weight=None, dout_flat=None):
     """Backward shared by the two inner functions (selective_scan_interface.py:367-434).
     dout_y: gradient wrt the scan output (b, d, l)."""
-    (xz, conv_w, conv_b, x_dbl, x_proj_weight, delta_proj_weight, A, B, C, D, delta_bias, ckpt) = ctx.saved
+    (xz, conv_w, conv_b, x_dbl, x_proj_weight, delta_proj_weight, A, B, C, D, delta_bias, ckpt) = ctx.saved_tensors[:12]
     bt, _, L = xz.shape
     R = delta_proj_weight.shape[1]
     N = A.shape[-1]
@@ -373,7 +375,7 @@ class MambaInnerFnNoOutProj(torch.autograd.Function):
         ctx.var_b, ctx.var_c = var_b, var_c
         ctx.has_B_bias, ctx.has_C_bias = B_proj_bias is not None, C_proj_bias is not None
         if need_grad:
-            ctx.saved = (xz, conv_w, conv_b, x_dbl, xw, dw, A, Bm, Cm, D, delta_bias, ckpt)
+            ctx.save_for_backward(xz, conv_w, conv_b, x_dbl, xw, dw, A, Bm, Cm, D, delta_bias, ckpt)
         return out_z
 
     @staticmethod
@@ -405,18 +407,17 @@ class MambaInnerFn(torch.autograd.Function):
         ctx.has_B_bias, ctx.has_C_bias = B_proj_bias is not None, C_proj_bias is not None
         ctx.has_out_bias = out_proj_bias is not None
         if need_grad:
-            ctx.saved = (xz, conv_w, conv_b, x_dbl, xw, dw, A, Bm, Cm, D, delta_bias, ckpt)
-            ctx.out_proj_weight = out_proj_weight
-            ctx.out_z = out_z   # reference recomputes out_z in the bwd kernel; keeping it costs B*E*L*2 bytes
+            # (out_z: the reference recomputes it in the bwd kernel; keeping it costs B*E*L*2 bytes)
+            ctx.save_for_backward(xz, conv_w, conv_b, x_dbl, xw, dw, A, Bm, Cm, D, delta_bias, ckpt, out_proj_weight, out_z)
         return F.linear(out_z.transpose(1, 2), out_proj_weight, out_proj_bias)
 
     @staticmethod
     def backward(ctx, dout):
-        W = ctx.out_proj_weight
+        W, out_z = ctx.saved_tensors[12:14]
         bt, L, Dm = dout.shape
         dout2 = dout.reshape(bt * L, Dm)
         dout_y = (dout2 @ W).reshape(bt, L, -1).transpose(1, 2)                      # (b, d, l)
-        dW = dout2.t() @ ctx.out_z.transpose(1, 2).reshape(bt * L, -1)
+        dW = dout2.t() @ out_z.transpose(1, 2).reshape(bt * L, -1)
         dbias = dout2.sum(0) if ctx.has_out_bias else None
         (dxz, dcw, dcb, dxw, ddw, dA, dB, dC, dD, dbias_dt, dBb, dCb) = _inner_bwd(ctx, dout_y)
         return (dxz, dcw, dcb, dxw, ddw, dW, dbias, dA, dB, dC, dD, dbias_dt, dBb, dCb, None, None)
@@ -476,7 +477,7 @@ class MambaInnerTokFn(torch.autograd.Function):
         y, ckpt, x_dbl, _ = _tok_core_fwd(xz, conv_w, conv_b, x_proj_weight, delta_proj_weight, A, D, delta_bias,
                                           rowmap, bt, L, need_grad)
         if need_grad:
-            ctx.saved = (xz, conv_w, conv_b, x_dbl, x_proj_weight, delta_proj_weight, A, D, delta_bias, ckpt, rowmap)
+            ctx.save_for_backward(xz, conv_w, conv_b, x_dbl, x_proj_weight, delta_proj_weight, A, D, delta_bias, ckpt, rowmap)
             ctx.dims = (bt, L)
             ctx.wshape = conv1d_weight.shape
         return y.transpose(1, 2).reshape(bt * L, -1)
@@ -484,7 +485,7 @@ class MambaInnerTokFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dy):
         from .causal_conv1d_interface import _conv_fwd, _conv_bwd
-        (xz, conv_w, conv_b, x_dbl, x_proj_w, dt_proj_w, A, D, delta_bias, ckpt, rowmap) = ctx.saved
+        (xz, conv_w, conv_b, x_dbl, x_proj_w, dt_proj_w, A, D, delta_bias, ckpt, rowmap) = ctx.saved_tensors
         bt, L = ctx.dims
         E = xz.shape[1] // 2
         R, N = dt_proj_w.shape[1], A.shape[1]
