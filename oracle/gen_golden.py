@@ -217,6 +217,9 @@ MODEL_CASES = {
     # has_text: the gated cross-attention branch of every block + the text conditioning path (model_zigma.py:95-135, 446-458, 930-933)
     "tiny_text": (dict(in_channels=4, embed_dim=64, depth=3, img_dim=8, patch_size=1, scan_type="zigzagN8", use_pe=2, has_text=True,
                        d_context=24, n_context_token=7), 2, "fp32"),
+    # has_text on a factorised video scan (spatial, spatial, temporal layers): the cross-attention branch on (b, t k) tokens
+    "tiny_video_text": (dict(in_channels=4, embed_dim=64, depth=3, img_dim=8, patch_size=2, scan_type="zzvideo_sst", use_pe=2,
+                             video_frames=8, tpe=True, has_text=True, d_context=24, n_context_token=7), 2, "fp32"),
     "full_zigzag8_b1": (dict(in_channels=4, embed_dim=640, depth=18, img_dim=32, patch_size=1, scan_type="zigzagN8", use_pe=2), 1, "fp32"),
 }
 

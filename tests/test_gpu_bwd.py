@@ -189,6 +189,52 @@ def test_scan_bwd_staged_kernel_groups_rowmap_vs_oracle_autograd(dtype):
             check_close(got, want, f"staged {layout} {name}", **tol)
 
 
+@pytest.mark.parametrize("const_b,const_c", [(True, False), (False, True), (True, True)])
+@pytest.mark.parametrize("N", [4, 16])
+def test_selective_scan_bwd_constant_bc_vs_oracle_autograd(const_b, const_c, N):
+    """Constant (dim, dstate) fp32 B and / or C (the non input-dependent forms selective_scan.cpp:238-278 accepts; their
+    gradients are per-channel sums over batch and sequence, selective_scan_bwd_kernel.cuh:297-316) through the public
+    selective_scan_fn, against autograd through the CPU oracle."""
+    from zigma_b200 import selective_scan_fn
+    Bt, E, L = 2, 96, 45
+    inp = synth.synth_scan_inputs(Bt, E, L, N, 1, seed=41)
+    g = torch.Generator().manual_seed(7)
+    if const_b:
+        inp["B"] = torch.randn(E, N, generator=g) * 0.5
+    if const_c:
+        inp["C"] = torch.randn(E, N, generator=g) * 0.5
+    gout = torch.randn(Bt, E, L, generator=g)
+    ref = {k: v.float().clone().requires_grad_() for k, v in inp.items()}
+    out_ref = zo.selective_scan(ref["u"], ref["delta"], ref["A"], ref["B"], ref["C"], ref["D"], ref["z"], ref["delta_bias"], True)
+    out_ref.backward(gout)
+    d = {k: v.to(DEV).requires_grad_() for k, v in inp.items()}
+    out = selective_scan_fn(d["u"], d["delta"], d["A"], d["B"], d["C"], d["D"], z=d["z"], delta_bias=d["delta_bias"], delta_softplus=True)
+    check_close(out, out_ref, f"constant B={const_b} C={const_c} N={N} fwd", atol=1e-4, max_strict_viol=1e-2)
+    out.backward(gout.to(DEV))
+    for k in ("u", "delta", "z", "A", "B", "C", "D", "delta_bias"):
+        assert d[k].grad.shape == ref[k].grad.shape and d[k].grad.dtype == d[k].dtype
+        check_close(d[k].grad, ref[k].grad, f"constant B={const_b} C={const_c} N={N} d{k}", atol=1e-4, max_strict_viol=1e-2)
+
+
+@pytest.mark.parametrize("N", [24, 32, 64])
+def test_selective_scan_bwd_wide_state_vs_oracle_autograd(N):
+    """dstate up to 64 in the backward (what the forward accepts; the reference takes up to 256, selective_scan.cpp:262), generic
+    kernel: against autograd through the CPU oracle."""
+    from zigma_b200 import selective_scan_fn
+    Bt, E, L = 2, 64, 40
+    inp = synth.synth_scan_inputs(Bt, E, L, N, 1, seed=43)
+    gout = torch.randn(Bt, E, L, generator=torch.Generator().manual_seed(8))
+    ref = {k: v.float().clone().requires_grad_() for k, v in inp.items()}
+    out_ref = zo.selective_scan(ref["u"], ref["delta"], ref["A"], ref["B"], ref["C"], ref["D"], ref["z"], ref["delta_bias"], True)
+    out_ref.backward(gout)
+    d = {k: v.to(DEV).requires_grad_() for k, v in inp.items()}
+    out = selective_scan_fn(d["u"], d["delta"], d["A"], d["B"], d["C"], d["D"], z=d["z"], delta_bias=d["delta_bias"], delta_softplus=True)
+    check_close(out, out_ref, f"dstate {N} fwd", atol=1e-4, max_strict_viol=1e-2)
+    out.backward(gout.to(DEV))
+    for k in ("u", "delta", "z", "A", "B", "C", "D", "delta_bias"):
+        check_close(d[k].grad, ref[k].grad, f"dstate {N} d{k}", atol=1e-4, max_strict_viol=1e-2)
+
+
 def test_scan_bwd_full_size_properties():
     """BASELINE config-2 layer shape (bs 16 x 1280 x 1024, bf16, token-major): (a) every gradient is linear in dout --
     bwd(2 dout) == 2 bwd(dout) exactly for the per-element outputs (power-of-two scaling commutes with every rounding),

@@ -37,7 +37,7 @@ def test_mamba_inner_fn_golden():
     assert all(v.grad is not None and torch.isfinite(v.grad).all() and v.grad.abs().sum() > 0 for v in req.values())
 
 
-@pytest.mark.parametrize("name", ["tiny_zigzag8", "tiny_sweep2", "tiny_hilbert2", "tiny_patch2_cls", "tiny_video_sst", "tiny_text"])
+@pytest.mark.parametrize("name", ["tiny_zigzag8", "tiny_sweep2", "tiny_hilbert2", "tiny_patch2_cls", "tiny_video_sst", "tiny_text", "tiny_video_text"])
 @pytest.mark.parametrize("path", ["engine", "engine_nograph", "autograd"])
 def test_zigma_forward_golden_fp32(name, path, monkeypatch):
     g, cfg, shapes = model_case(name)
@@ -250,6 +250,24 @@ def test_full_depth_configs_bf16_batch16(name):
     sd16 = {kk: v.bfloat16().float() for kk, v in sd.items()}                # the oracle sees the bf16-rounded weights
     want = _oracle_forward(cfg, sd16, x[k:k + 1].float(), tt[k:k + 1].float(), None if y is None else y[k:k + 1])
     check_close(one, want, f"{name} full depth bf16 bs={bs} row {k} vs fp32 oracle", rtol=8e-2, atol=8e-2, scale_atol=False, max_strict_viol=1.0)
+
+
+def test_has_text_video_bf16_copy_free_temporal_layers():
+    """has_text on a factorised video scan in bf16 at a width that takes the hot-path kernels (D = 128): the spatial layers run on
+    (b t) sequences and the temporal layers copy-free through the composite row tables; the cross-attention branch needs the
+    mixer output un-permuted first (each layer's own table).  Against the fp32 oracle on the bf16-rounded weights."""
+    from zigma_b200 import ZigMa
+    cfg = dict(in_channels=4, embed_dim=128, depth=3, img_dim=8, patch_size=2, scan_type="zzvideo_sst", use_pe=2, video_frames=8, tpe=True,
+               has_text=True, d_context=24, n_context_token=7)
+    m = ZigMa(device=DEV, dtype=torch.bfloat16, **cfg).eval()
+    sd = synth.synth_state_dict({k: tuple(v.shape) for k, v in m.state_dict().items()}, seed=0, dtype=torch.bfloat16)
+    m.load_state_dict(sd)
+    x, tt, y = model_io(cfg, 2)
+    with torch.no_grad():
+        out = m(x.to(DEV).bfloat16(), tt.to(DEV).bfloat16(), y.to(DEV).bfloat16())
+    assert m._engine is not None, "ZigMa.forward did not take the engine"
+    want = _oracle_forward(cfg, {k: v.float() for k, v in sd.items()}, x.bfloat16().float(), tt.bfloat16().float(), y.bfloat16().float())
+    check_close(out, want, "has_text + video bf16 engine vs fp32 oracle", rtol=6e-2, atol=6e-2, scale_atol=False, max_strict_viol=1.0)
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])

@@ -65,7 +65,7 @@ def test_mamba_inner_oracle_matches_reference():
     check_close(out, g["out"], "mamba_inner oracle")
 
 
-@pytest.mark.parametrize("name", ["tiny_zigzag8", "tiny_sweep2", "tiny_hilbert2", "tiny_patch2_cls", "tiny_video_sst", "tiny_text"])
+@pytest.mark.parametrize("name", ["tiny_zigzag8", "tiny_sweep2", "tiny_hilbert2", "tiny_patch2_cls", "tiny_video_sst", "tiny_text", "tiny_video_text"])
 def test_zigma_forward_oracle_matches_reference(name):
     from oracle.gen_golden import model_io
     g, cfg, shapes = model_case(name)

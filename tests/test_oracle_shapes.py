@@ -26,7 +26,7 @@ def test_shapes_match_product_model(name):
     assert zigma_state_shapes(cfg) == {k: tuple(v.shape) for k, v in m.state_dict().items()}
 
 
-@pytest.mark.parametrize("name", ["tiny_zigzag8", "tiny_sweep2", "tiny_hilbert2", "tiny_patch2_cls", "tiny_video_sst", "tiny_text"])
+@pytest.mark.parametrize("name", ["tiny_zigzag8", "tiny_sweep2", "tiny_hilbert2", "tiny_patch2_cls", "tiny_video_sst", "tiny_text", "tiny_video_text"])
 def test_shapes_match_reference_recorded_tables(name):
     from oracle.shapes import zigma_state_shapes
     _, cfg, shapes = model_case(name)

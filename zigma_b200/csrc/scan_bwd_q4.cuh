@@ -366,6 +366,7 @@ template <typename T> int try_launch_scan_bwd_q4(const zg_scan_bwd_params &q, cu
     if (staged_ok < 0) { const char *e = getenv("ZG_SCAN_BWD_STAGED"); staged_ok = e ? atoi(e) : 1; }
     const zg_scan_params &p = q.fwd;
     if (!enabled || p.dstate != 16 || p.ckpt_every != Q4_TS) return -1;
+    if (!(p.flags & ZG_SCAN_VARIABLE_B) || !(p.flags & ZG_SCAN_VARIABLE_C)) return -1;      // constant B / C: the generic kernel
     if ((reinterpret_cast<uintptr_t>(p.A) | reinterpret_cast<uintptr_t>(p.ckpt)) % 16 != 0) return -1;
     const int per_group = p.dim / p.ngroups;
     const long long nblk = (long long)p.ngroups * ((per_group + Q4_CH - 1) / Q4_CH) * p.batch;

@@ -329,10 +329,11 @@ class ZigMaEngine:
                 # reads it; the attention branch (library SDPA on 77 text tokens) then takes the place of the mixer output
                 # in the fused tail:  hidden2 = hidden + gate_msa * msa(modulate(norm_msa(hidden)))
                 blk = m.blocks[i]
-                if fold != 1:
-                    raise NotImplementedError("zigma_b200 engine: has_text together with factorised video scans")
-                mixed = mix if rowmap is None else mix.index_select(1, lay["perm_rev64"])
-                hidden = normed + gate.unsqueeze(1) * mixed
+                # un-permute the mixer output with the layer's own row table: (B fold, L / fold) rows for a spatial video layer
+                # (same memory as (B, L)), the composite (k T + t) table of a copy-free temporal layer, the zigzag table otherwise
+                mixed = mix if rowmap is None else mix.reshape(-1, rowmap.numel(), D).index_select(1, rowmap.long())
+                hidden = normed + gate.unsqueeze(1) * mixed.reshape(B, L, D)
+                fold = 1
                 q_in = blk.norm_msa(hidden) * (1 + mods[:, i, 4].unsqueeze(1)) + mods[:, i, 3].unsqueeze(1)
                 mix, rowmap, gate, normed = blk.msa(q_in, text=text, mask=None).contiguous(), None, mods[:, i, 5], hidden
             if fold != 1:     # spatial video layer: rows are (b t, k); same memory as (b, t k)

@@ -396,7 +396,7 @@ class ZigMa(nn.Module):
     def forward(self, hidden_states, t, y=None):
         """x: (N, C, H, W) latents (video: (N, T, C, H, W)); t: (N,) timesteps; y: (N,) labels."""
         use_engine = (not torch.is_grad_enabled()) and (not self.training) and hidden_states.is_cuda \
-            and self.fused_add_norm and self.residual_in_fp32 and self.use_pe != 3 and not (self.has_text and self.video_frames > 0) \
+            and self.fused_add_norm and self.residual_in_fp32 and self.use_pe != 3 \
             and self._engine_norms_ok()
         if use_engine:
             from .engine import ZigMaEngine
@@ -410,7 +410,7 @@ class ZigMa(nn.Module):
         """The flow-matching sampler's fixed-grid Euler loop over ``linspace(t0, t1, num_steps)`` (num_steps - 1 evaluations;
         transport/integrators.py:83-123 with sampler_type "euler") as ONE CUDA-graph replay on the sampling engine."""
         if self.training or not x0.is_cuda or not (self.fused_add_norm and self.residual_in_fp32 and self.use_pe != 3
-                                                  and not (self.has_text and self.video_frames > 0) and self._engine_norms_ok()):
+                                                  and self._engine_norms_ok()):
             raise RuntimeError("ZigMa.sample_euler: needs an eval-mode CUDA model the sampling engine supports")
         from .engine import ZigMaEngine
         if self._engine is None:

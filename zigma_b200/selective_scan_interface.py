@@ -170,21 +170,21 @@ def _scan_bwd(saved, ckpt, dout, delta_softplus, dz_out=None, z_rowmap=None):
     u, delta, z, B, C, D, delta_bias, A = saved
     batch, dim, seqlen = u.shape
     dstate = A.shape[1]
-    var_b, var_c = B.dim() >= 3, C.dim() >= 3
-    if not (var_b and var_c):
-        raise NotImplementedError("zigma_b200: backward with constant (non input-dependent) B/C is not implemented")
-    ngroups = B.shape[1]
+    var_b, var_c = B.dim() >= 3, C.dim() >= 3       # constant B / C: fp32 (dim, dstate) weights (selective_scan.cpp:238-278)
+    ngroups = B.shape[1] if var_b else (C.shape[1] if var_c else 1)
+    if not (var_b and var_c) and ngroups != 1:
+        raise RuntimeError("selective_scan backward: a constant B or C comes with one group")
 
     def dense(t):      # the dstate == 16 kernel takes any strides; keep channel-first or token-major as given
         return t is None or t.stride(2) == 1 or t.stride(1) == 1
-    if dstate == 16 and all(dense(t) for t in (u, delta, z, dout)):
+    if dstate == 16 and var_b and var_c and all(dense(t) for t in (u, delta, z, dout)):
         fmt = torch.preserve_format
     else:              # generic kernel: a thread walks its own row, rows must be seq-contiguous
         def seqc(t):
             return t if (t is None or t.stride(2) == 1) else t.contiguous()
         u, delta, z, dout = seqc(u), seqc(delta), seqc(z), seqc(dout)
-        B = B if B.stride(3) == 1 else B.contiguous()
-        C = C if C.stride(3) == 1 else C.contiguous()
+        B = (B if B.stride(3) == 1 else B.contiguous()) if var_b else B.contiguous()
+        C = (C if C.stride(3) == 1 else C.contiguous()) if var_c else C.contiguous()
         fmt = torch.contiguous_format
     dev = u.device
     du, ddelta = torch.empty_like(u, memory_format=fmt), torch.empty_like(delta, memory_format=fmt)
@@ -194,8 +194,8 @@ def _scan_bwd(saved, ckpt, dout, delta_softplus, dz_out=None, z_rowmap=None):
     dA = torch.zeros((dim, dstate), dtype=torch.float32, device=dev)
     dD = torch.zeros((dim,), dtype=torch.float32, device=dev)
     dbias = torch.zeros((dim,), dtype=torch.float32, device=dev)
-    dB = torch.zeros((batch, ngroups, dstate, seqlen), dtype=torch.float32, device=dev)
-    dC = torch.zeros((batch, ngroups, dstate, seqlen), dtype=torch.float32, device=dev)
+    dB = torch.zeros((batch, ngroups, dstate, seqlen) if var_b else (dim, dstate), dtype=torch.float32, device=dev)
+    dC = torch.zeros((batch, ngroups, dstate, seqlen) if var_c else (dim, dstate), dtype=torch.float32, device=dev)
 
     q = _lib.ScanBwdParams()
     p = q.fwd
@@ -207,11 +207,13 @@ def _scan_bwd(saved, ckpt, dout, delta_softplus, dz_out=None, z_rowmap=None):
     p.delta_sb, p.delta_sd, p.delta_sl = _strides3(delta)
     if z is not None:
         p.z_sb, p.z_sd, p.z_sl = _strides3(z)
-    p.B_sb, p.B_sg, p.B_sn, p.B_sl = B.stride()
-    p.C_sb, p.C_sg, p.C_sn, p.C_sl = C.stride()
+    if var_b:
+        p.B_sb, p.B_sg, p.B_sn, p.B_sl = B.stride()
+    if var_c:
+        p.C_sb, p.C_sg, p.C_sn, p.C_sl = C.stride()
     p.batch, p.dim, p.seqlen, p.dstate, p.ngroups = batch, dim, seqlen, dstate, ngroups
     p.dtype, p.ckpt_every = _lib.dt(u), CKPT_EVERY
-    p.flags = (_lib.SCAN_DELTA_SOFTPLUS if delta_softplus else 0) | _lib.SCAN_VARIABLE_B | _lib.SCAN_VARIABLE_C
+    p.flags = (_lib.SCAN_DELTA_SOFTPLUS if delta_softplus else 0) | (_lib.SCAN_VARIABLE_B if var_b else 0) | (_lib.SCAN_VARIABLE_C if var_c else 0)
     q.dout = _lib.ptr(dout)
     q.dout_sb, q.dout_sd, q.dout_sl = _strides3(dout)
     q.du, q.ddelta, q.dz = _lib.ptr(du), _lib.ptr(ddelta), _lib.ptr(dz)
@@ -254,9 +256,8 @@ class SelectiveScanFn(torch.autograd.Function):
     def backward(ctx, dout, *args):
         *saved, ckpt = ctx.saved_tensors
         du, ddelta, dA, dB, dC, dD, dbias, dz = _scan_bwd(tuple(saved), ckpt, dout, ctx.delta_softplus)
-        u = saved[0]
-        dB = dB.to(u.dtype)
-        dC = dC.to(u.dtype)
+        dB = dB.to(saved[3].dtype)          # the activation dtype for input-dependent B / C, fp32 for constant ones
+        dC = dC.to(saved[4].dtype)
         if ctx.squeeze_B:
             dB = dB.squeeze(1)
         if ctx.squeeze_C:
