@@ -180,6 +180,75 @@ def test_selective_scan_hot_path_four_threads_per_channel_variant():
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-1000:]
 
 
+@pytest.mark.parametrize("mode", ["1", "2"])
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+def test_selective_scan_warp_private_pipeline_bit_identical(mode, dtype, monkeypatch):
+    """ZG_SCAN_WP=1 / 2 (scan_fwd_wp.cuh: every warp runs its own staging ring, no block barrier; cp.async or TMA staging of
+    u / delta) against ZG_SCAN_WP=0 (scan_fwd_tma_kernel): the same operations in the same order per channel, so every output --
+    out, last state, checkpoints, the reversed / accumulated output of the v2 sweep, the two-level z batch -- is bit identical.
+    (The CTA-wide kernel itself is checked against the C oracle by the tests above and below.)"""
+    from zigma_b200.selective_scan_interface import _scan_fwd
+    N = 16
+
+    def both(fn):
+        monkeypatch.setenv("ZG_SCAN_WP", "0")
+        a = fn()
+        monkeypatch.setenv("ZG_SCAN_WP", mode)
+        b = fn()
+        torch.cuda.synchronize()
+        return a, b
+
+    def same(a, b, what):
+        for i, (x, y) in enumerate(zip(a, b)):
+            if x is None or not torch.is_tensor(x):
+                continue
+            assert torch.equal(x, y), f"{what}: output {i} differs, max|diff| {(x.float() - y.float()).abs().max().item():.3e}"
+
+    for shape, G in (((2, 192, 264), 1), ((3, 64, 8), 1), ((1, 128, 1024), 1), ((2, 256, 40), 2), ((5, 320, 16), 1)):
+        Bt, E, L = shape
+        inp = synth.synth_scan_inputs(Bt, E, L, N, G, seed=41 + L)
+        d = {k: (v.to(dtype) if k in ("u", "delta", "z", "B", "C") else v).to(DEV) for k, v in inp.items()}
+        tm = lambda x: x.transpose(1, 2).contiguous().transpose(1, 2)
+        u, dl, z = tm(d["u"]), tm(d["delta"]), tm(d["z"])
+        Bv, Cv = d["B"].transpose(2, 3).contiguous().transpose(2, 3), d["C"].transpose(2, 3).contiguous().transpose(2, 3)
+        perm = torch.from_numpy(np.random.RandomState(3).permutation(L)).to(DEV).to(torch.int32)
+        # the model's call: z gathered through the table, D, bias, softplus, last state, checkpoints
+        same(*both(lambda: _scan_fwd(u, dl, d["A"], Bv, Cv, d["D"], z, d["delta_bias"], True, z_rowmap=perm, want_last_state=True, want_ckpt=True)),
+             f"wp {mode} {dtype} {shape} full")
+        same(*both(lambda: _scan_fwd(u, dl, d["A"], Bv, Cv, d["D"], z, d["delta_bias"], True, want_last_state=False)), f"wp {mode} {dtype} {shape} z in order")
+        same(*both(lambda: _scan_fwd(u, dl, d["A"], Bv, Cv, None, None, None, False, want_last_state=True)), f"wp {mode} {dtype} {shape} bare")
+        # second sweep of scan_type v2: reversed and accumulated into an existing output
+        P = torch.randn(Bt, L, E, device=DEV).to(dtype)
+
+        def sweep2():
+            buf = P.clone()
+            _scan_fwd(u, dl, d["A"], Bv, Cv, d["D"], z, d["delta_bias"], True, want_last_state=False, out=buf.transpose(1, 2), out_reverse=True, out_accumulate=True)
+            return (buf,)
+        same(*both(sweep2), f"wp {mode} {dtype} {shape} reverse + accumulate")
+    # two-level z batch of the temporal video layers
+    Bt, T, K, E = 2, 16, 8, 128
+    xz = torch.randn(Bt, T * K, 2 * E, device=DEV).to(dtype)
+    inp = synth.synth_scan_inputs(Bt * K, E, T, N, 1, seed=33)
+    d = {k: (v.to(dtype) if k in ("u", "delta", "B", "C") else v).to(DEV) for k, v in inp.items()}
+    tm = lambda x: x.transpose(1, 2).contiguous().transpose(1, 2)
+    Bv, Cv = d["B"].transpose(2, 3).contiguous().transpose(2, 3), d["C"].transpose(2, 3).contiguous().transpose(2, 3)
+    z_btk = xz.view(Bt, T, K, 2 * E)[:, :, :, E:]
+    perm = torch.randperm(T, device=DEV).to(torch.int32)
+    same(*both(lambda: _scan_fwd(tm(d["u"]), tm(d["delta"]), d["A"], Bv, Cv, d["D"], None, d["delta_bias"], True, z_rowmap=perm, want_last_state=False, z_btk=z_btk)),
+         f"wp {mode} {dtype} z_btk")
+
+
+@pytest.mark.parametrize("wp", ["1", "2"])
+def test_selective_scan_warp_private_pipeline_vs_oracle(wp):
+    """The hot-path scan tests (C oracle, zigzag table, v2 sweep, temporal layout) with ZG_SCAN_WP set, in a child process."""
+    import os, subprocess, sys
+    from util import ROOT
+    env = dict(os.environ, ZG_SCAN_WP=wp)
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_gpu_ops.py"), "-m", "gpu", "-q", "-x", "-p", "no:cacheprovider",
+                        "-k", "tma_pipeline or out_reverse or temporal_layout or z_rowmap"], capture_output=True, text=True, cwd=ROOT, env=env, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-1000:]
+
+
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
 def test_selective_scan_out_reverse_accumulate(dtype):
     """ZG_SCAN_OUT_REVERSE | ZG_SCAN_OUT_ACCUMULATE: the kernel writes step l to position L-1-l and adds into `out` with the

@@ -44,6 +44,9 @@
 #ifndef ZG_SCAN_SWP
 #define ZG_SCAN_SWP 1      // hand software-pipelined recurrence loop (0: the straight loop)
 #endif
+#ifndef ZG_SCAN_WP_DEFAULT
+#define ZG_SCAN_WP_DEFAULT 0   // 0: CTA-wide phases (this file); 1 / 2: warp-private pipeline (scan_fwd_wp.cuh), cp.async / TMA staging
+#endif
 #ifndef ZG_SCAN_TMA_NPOLY_DEFAULT
 #define ZG_SCAN_TMA_NPOLY_DEFAULT 0
 #endif
@@ -175,7 +178,7 @@ template <typename T> __device__ __forceinline__ void pt_mma_k8(float &d0, float
 // Software-pipelined by hand (ZG_SCAN_SWP, default on): ptxas emits the unrolled steps strictly one after the other
 // (LDS -> FMUL2 -> 8 MUFU -> FFMA2 chain -> STS, ~140 cycles of dependent latency per step and warp), so the decay factors
 // exp2(delta' A) of step t + 1 -- which depend on nothing but (delta', A) -- are issued BEFORE the FMA part of step t.
-template <int NP, int TPC>
+template <int NP, int TPC, int PITCH = PT_F32ROW>
 __device__ __forceinline__ void pt_main_stage(const unsigned char *__restrict__ ddu_c, const float *__restrict__ bcf_p, unsigned char *__restrict__ ypart, int ypitch,
                                               zg_f2 (&h2)[8 / TPC], const zg_f2 (&Al2p)[8 / TPC], bool store = true) {
     constexpr int NPAIR = 8 / TPC, NQ = 4 / TPC;           // state pairs per thread; float4 loads of B (and of C) per step
@@ -208,7 +211,7 @@ __device__ __forceinline__ void pt_main_stage(const unsigned char *__restrict__ 
         const zg_f2 du = zg_splat2(dd.y);
         zg_f2 a_nxt[NPAIR];
         if (t + 1 < PT_TL) {                               // next step's pair and decays: in flight during this step's FMAs
-            dd = *reinterpret_cast<const float2 *>(ddu_c + (t + 1) * PT_F32ROW);
+            dd = *reinterpret_cast<const float2 *>(ddu_c + (t + 1) * PITCH);
             decay(dd.x, a_nxt);
         }
         zg_f2 y2 = zg_splat2(0.f);
@@ -226,7 +229,7 @@ __device__ __forceinline__ void pt_main_stage(const unsigned char *__restrict__ 
 #else
 #pragma unroll
     for (int t = 0; t < PT_TL; ++t) {
-        const float2 dd = *reinterpret_cast<const float2 *>(ddu_c + t * PT_F32ROW);      // (delta', delta' * u)
+        const float2 dd = *reinterpret_cast<const float2 *>(ddu_c + t * PITCH);      // (delta', delta' * u)
         const float4 *bc = reinterpret_cast<const float4 *>(bcf_p + t * 32);
         zg_f2 Bp[NPAIR], Cp[NPAIR];
 #pragma unroll
@@ -625,6 +628,14 @@ template <typename T, int R> int pt_launch_variant(const zg_scan_params &p, cuda
     return pt_launch<T, R, 0, false>(p, stream);
 }
 
+// warp-private pipeline (scan_fwd_wp.cuh), compiled in its own translation units
+int scan_fwd_wp_bf16(const zg_scan_params &p, cudaStream_t stream, int mode);
+int scan_fwd_wp_f16(const zg_scan_params &p, cudaStream_t stream, int mode);
+template <typename T> inline int wp_dispatch(const zg_scan_params &p, cudaStream_t stream, int mode) {
+    if constexpr (std::is_same<T, __nv_bfloat16>::value) return scan_fwd_wp_bf16(p, stream, mode);
+    else return scan_fwd_wp_f16(p, stream, mode);
+}
+
 // host-side eligibility test + launch; returns -1 when the call does not fit the specialisation (never for a fused request:
 // that one is an error, reported through zg_set_error with a positive return code)
 template <typename T> int try_launch_scan_fwd_tma(const zg_scan_params &p, cudaStream_t stream) {
@@ -657,7 +668,13 @@ template <typename T> int try_launch_scan_fwd_tma(const zg_scan_params &p, cudaS
         return decline("batch element too large for 32-bit offsets");
     if ((long long)(p.dim / PT_CH) * p.batch > 0x7fffffffLL) return decline("grid too large");
     if (p.z_batch_inner > 0 && (!p.z || !p.z_rowmap || p.z_sbi % 8 != 0)) return decline("z_batch_inner needs z with a z_rowmap and 16-byte aligned rows");
-    if (!fuse) return pt_launch_variant<T, 0>(p, stream);
+    if (!fuse) {
+        // ZG_SCAN_WP: the warp-private pipeline (scan_fwd_wp.cuh): 1 = cp.async staging, 2 = TMA tiles for u / delta, 0 = this file's kernel
+        // (read at every call, unlike the other switches: the tests compare the kernels bit for bit inside one process)
+        const int wp_mode = pt_env_int("ZG_SCAN_WP", ZG_SCAN_WP_DEFAULT);
+        if (wp_mode == 1 || wp_mode == 2) return wp_dispatch<T>(p, stream, wp_mode);
+        return pt_launch_variant<T, 0>(p, stream);
+    }
     // fused prologue: B and C must be the tail of the dt_x rows (the x_dbl rows of x_proj)
     const T *x = reinterpret_cast<const T *>(p.dt_x);
     if (p.ngroups != 1 || reinterpret_cast<const T *>(p.B) != x + p.dt_rank || reinterpret_cast<const T *>(p.C) != x + p.dt_rank + 16 ||
