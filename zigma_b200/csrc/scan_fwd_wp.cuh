@@ -24,11 +24,14 @@
 
 namespace zg {
 
+#ifndef ZG_SCAN_WP_SYNC_DEFAULT
+#define ZG_SCAN_WP_SYNC_DEFAULT 8     // stages between two fairness barriers of a CTA (0: none)
+#endif
 #ifndef ZG_SCAN_WP_NPOLY_DEFAULT
 #define ZG_SCAN_WP_NPOLY_DEFAULT 0
 #endif
 constexpr int WP_CH = 16;             // channels per warp
-constexpr int WP_MAX_WARPS = 9;       // independent warps per CTA: chosen per launch (wp_pick_warps), at most this many
+constexpr int WP_MAX_WARPS = 18;      // independent warps per CTA: chosen per launch (wp_pick_shape), at most this many
 
 struct WpLayout {                     // per warp
     static constexpr int NSTAGE = 3;
@@ -42,8 +45,10 @@ struct WpLayout {                     // per warp
 };
 
 template <typename T, bool CKPT, bool PLAIN, bool TMA, int NPOLY = 0>
-// (288 threads x 4 CTAs: the register cap that lets 36 warps live on an SM, 56 per thread)
-__global__ void __launch_bounds__(32 * WP_MAX_WARPS, 4) scan_fwd_wp_kernel(const zg_scan_params p, const __grid_constant__ PtMaps maps) {
+// (576 threads x 2 CTAs: the register cap that lets 36 warps live on an SM, 56 per thread)
+// sync_every = K > 0: the warps of the CTA meet at a named barrier every K stages.  They exchange nothing -- the barrier is a
+// fairness throttle (see wp_pick_shape): a warp that has run ahead sleeps there and leaves the MUFU pipe to the others.
+__global__ void __launch_bounds__(32 * WP_MAX_WARPS, 2) scan_fwd_wp_kernel(const zg_scan_params p, const __grid_constant__ PtMaps maps, const int sync_every) {
     static_assert(sizeof(T) == 2, "16-bit I/O only");
     using LY = WpLayout;
     constexpr int NSTAGE = LY::NSTAGE, TL = PT_TL, TILE = LY::TILE, NPAIR = 4;
@@ -62,6 +67,9 @@ __global__ void __launch_bounds__(32 * WP_MAX_WARPS, 4) scan_fwd_wp_kernel(const
     const int units = units_per_group * p.ngroups;                 // 16-channel units of a batch row
     const int wu = blockIdx.x * (int)(blockDim.x >> 5) + warp;     // warps are independent: any number of them per CTA
     if (wu >= units * p.batch) return;
+    // warps of this CTA that have work (the last CTA may be short): the participants of the fairness barrier
+    const int cta_warps = min((int)(blockDim.x >> 5), units * p.batch - (int)blockIdx.x * (int)(blockDim.x >> 5));
+    int sync_left = sync_every;
     const int b = wu / units;
     const int unit = wu % units;
     const int g = unit / units_per_group;
@@ -226,6 +234,10 @@ __global__ void __launch_bounds__(32 * WP_MAX_WARPS, 4) scan_fwd_wp_kernel(const
         issue_stage(slot);
         slot = nslot;
         if (++nslot == NSTAGE) { nslot = 0; npar ^= 1; }
+        if (sync_every > 0 && --sync_left == 0) {       // every warp of the CTA runs the same number of stages
+            sync_left = sync_every;
+            asm volatile("bar.sync 1, %0;" ::"r"(cta_warps * 32) : "memory");
+        }
     }
     if (p.last_state) {
         float4 *dst = reinterpret_cast<float4 *>(p.last_state + ((int64_t)b * E + e) * 16 + 8 * part);
@@ -234,24 +246,24 @@ __global__ void __launch_bounds__(32 * WP_MAX_WARPS, 4) scan_fwd_wp_kernel(const
     }
 }
 
-// Warps per CTA.  The warps are independent, so the CTA size only decides how evenly the 16-channel units spread over the SMs:
-// the kernel time is the time of the fullest SM.  Pick the size whose fullest SM holds the fewest warps (ties: the larger CTA),
-// within 36 resident warps (56 registers), 32 CTAs and the shared memory of an SM; one wave whenever the problem allows it.
-// Config 2 (5120 units, 148 SMs): 4 warps -> 9 CTAs = 36 warps on the fullest SM, 5 warps -> 7 CTAs = 35 (average 34.6).
-inline int wp_pick_warps(long long units, int sms) {
+// CTA shape.  The warps exchange nothing, so the CTA size is free; what it decides is how the SM's warp schedulers treat the
+// warps.  ncu of 4- / 5-warp CTAs (gpurun_out/r02b_scan_wp1_np0): only 6.1 of the 8.75 resident warps per sub-partition are alive
+// on average although every warp has the same work -- the schedulers favour the oldest warps, those finish at ~40 % of the
+// kernel time, and the youngest ones run the tail with too few peers to keep the MUFU pipe busy (74 % over the whole kernel).
+// When the whole problem fits one wave, the warps of an SM are therefore packed into ONE or TWO large CTAs whose warps meet at a
+// barrier every `sync_every` stages: a warp that has run ahead sleeps and the laggards get the pipe, so the warps of a CTA finish
+// together; with two CTAs per SM either of them alone (>= 4 warps per sub-partition) keeps the pipe busy while the other is
+// starved, so unfairness BETWEEN the two costs nothing.  Problems of several waves keep small CTAs (finished CTAs are replaced).
+struct WpShape { int warps, sync_every; };
+inline WpShape wp_pick_shape(long long units, int sms) {
     const int forced = pt_env_int("ZG_SCAN_WP_WARPS", 0);
-    if (forced >= 1 && forced <= WP_MAX_WARPS) return forced;
-    int best = 4;
-    long long best_cost = -1;
-    for (int w = 1; w <= 8; ++w) {
-        const long long ctas = (units + w - 1) / w;
-        const long long per_sm = (ctas + sms - 1) / sms;                     // CTAs on the fullest SM if everything were resident
-        const int fit = std::min({36 / w, 32, (int)((227 * 1024) / (w * WpLayout::WARP_BYTES + 1024))});   // CTAs an SM can hold
-        // more than one wave: whole waves of `fit` CTAs, then the rest
-        const long long cost = per_sm <= fit ? per_sm * w : ((ctas + (long long)fit * sms - 1) / ((long long)fit * sms)) * fit * w;
-        if (best_cost < 0 || cost < best_cost || (cost == best_cost && w <= 4)) { best = w; best_cost = cost; }
-    }
-    return best;
+    const int sync_env = pt_env_int("ZG_SCAN_WP_SYNC", ZG_SCAN_WP_SYNC_DEFAULT);
+    if (forced >= 1 && forced <= WP_MAX_WARPS) return {forced, sync_env};
+    if (units > 36LL * sms) return {4, 0};                                   // several waves
+    const long long per_sm = (units + sms - 1) / sms;                        // warps on the fullest SM
+    const int ctas_per_sm = per_sm > WP_MAX_WARPS ? 2 : 1;
+    const int w = (int)((units + (long long)sms * ctas_per_sm - 1) / ((long long)sms * ctas_per_sm));
+    return {w, sync_env};
 }
 
 template <typename T, bool CKPT, bool PLAIN, bool TMA, int NPOLY = 0> int wp_launch(const zg_scan_params &p, cudaStream_t stream) {
@@ -276,9 +288,10 @@ template <typename T, bool CKPT, bool PLAIN, bool TMA, int NPOLY = 0> int wp_lau
         attr_dev[dev & 63] = true;
     }
     const long long units = (long long)(p.dim / WP_CH) * p.batch;
-    const int w = wp_pick_warps(units, sms_dev[dev & 63] > 0 ? sms_dev[dev & 63] : 148);
+    const WpShape sh = wp_pick_shape(units, sms_dev[dev & 63] > 0 ? sms_dev[dev & 63] : 148);
+    const int w = sh.warps;
     const long long nblk = (units + w - 1) / w;
-    kern<<<(unsigned)nblk, 32 * w, w * LY::WARP_BYTES, stream>>>(p, maps);
+    kern<<<(unsigned)nblk, 32 * w, w * LY::WARP_BYTES, stream>>>(p, maps, sh.sync_every);
     zg_count_launch();
     return zg_check_launch("scan_fwd(wp)");
 }
