@@ -45,7 +45,7 @@
 #define ZG_SCAN_SWP 1      // hand software-pipelined recurrence loop (0: the straight loop)
 #endif
 #ifndef ZG_SCAN_WP_DEFAULT
-#define ZG_SCAN_WP_DEFAULT 0   // 0: CTA-wide phases (this file); 1 / 2: warp-private pipeline (scan_fwd_wp.cuh), cp.async / TMA staging
+#define ZG_SCAN_WP_DEFAULT 0   // 0: CTA-wide phases (this file); 1 / 2: warp-private pipeline (scan_fwd_wp.cuh), cp.async / TMA staging; 3 / 4: two channels per lane (scan_fwd_wp2.cuh)
 #endif
 #ifndef ZG_SCAN_TMA_NPOLY_DEFAULT
 #define ZG_SCAN_TMA_NPOLY_DEFAULT 0
@@ -631,9 +631,11 @@ template <typename T, int R> int pt_launch_variant(const zg_scan_params &p, cuda
 // warp-private pipeline (scan_fwd_wp.cuh), compiled in its own translation units
 int scan_fwd_wp_bf16(const zg_scan_params &p, cudaStream_t stream, int mode);
 int scan_fwd_wp_f16(const zg_scan_params &p, cudaStream_t stream, int mode);
+int scan_fwd_wp2_bf16(const zg_scan_params &p, cudaStream_t stream, int mode);     // two channels per lane (scan_fwd_wp2.cuh)
+int scan_fwd_wp2_f16(const zg_scan_params &p, cudaStream_t stream, int mode);
 template <typename T> inline int wp_dispatch(const zg_scan_params &p, cudaStream_t stream, int mode) {
-    if constexpr (std::is_same<T, __nv_bfloat16>::value) return scan_fwd_wp_bf16(p, stream, mode);
-    else return scan_fwd_wp_f16(p, stream, mode);
+    if constexpr (std::is_same<T, __nv_bfloat16>::value) return mode >= 3 ? scan_fwd_wp2_bf16(p, stream, mode) : scan_fwd_wp_bf16(p, stream, mode);
+    else return mode >= 3 ? scan_fwd_wp2_f16(p, stream, mode) : scan_fwd_wp_f16(p, stream, mode);
 }
 
 // host-side eligibility test + launch; returns -1 when the call does not fit the specialisation (never for a fused request:
@@ -669,10 +671,11 @@ template <typename T> int try_launch_scan_fwd_tma(const zg_scan_params &p, cudaS
     if ((long long)(p.dim / PT_CH) * p.batch > 0x7fffffffLL) return decline("grid too large");
     if (p.z_batch_inner > 0 && (!p.z || !p.z_rowmap || p.z_sbi % 8 != 0)) return decline("z_batch_inner needs z with a z_rowmap and 16-byte aligned rows");
     if (!fuse) {
-        // ZG_SCAN_WP: the warp-private pipeline (scan_fwd_wp.cuh): 1 = cp.async staging, 2 = TMA tiles for u / delta, 0 = this file's kernel
+        // ZG_SCAN_WP: the warp-private pipelines: 1 / 2 = scan_fwd_wp.cuh (one channel per lane; cp.async staging / TMA tiles for
+        // u and delta), 3 / 4 = scan_fwd_wp2.cuh (two channels per lane; cp.async / TMA), 0 = this file's kernel
         // (read at every call, unlike the other switches: the tests compare the kernels bit for bit inside one process)
         const int wp_mode = pt_env_int("ZG_SCAN_WP", ZG_SCAN_WP_DEFAULT);
-        if (wp_mode == 1 || wp_mode == 2) return wp_dispatch<T>(p, stream, wp_mode);
+        if (wp_mode >= 1 && wp_mode <= 4) return wp_dispatch<T>(p, stream, wp_mode);
         return pt_launch_variant<T, 0>(p, stream);
     }
     // fused prologue: B and C must be the tail of the dt_x rows (the x_dbl rows of x_proj)

@@ -25,7 +25,7 @@
 namespace zg {
 
 #ifndef ZG_SCAN_WP_SYNC_DEFAULT
-#define ZG_SCAN_WP_SYNC_DEFAULT 8     // stages between two fairness barriers of a CTA (0: none)
+#define ZG_SCAN_WP_SYNC_DEFAULT 0     // stages between two fairness barriers of a CTA (0: none -- measured: every setting loses, see wp_pick_shape)
 #endif
 #ifndef ZG_SCAN_WP_NPOLY_DEFAULT
 #define ZG_SCAN_WP_NPOLY_DEFAULT 0
