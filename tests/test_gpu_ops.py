@@ -180,11 +180,12 @@ def test_selective_scan_hot_path_four_threads_per_channel_variant():
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-1000:]
 
 
-@pytest.mark.parametrize("mode", ["1", "2", "3", "4"])
+@pytest.mark.parametrize("mode", ["1", "2", "3", "4", "5"])
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
 def test_selective_scan_warp_private_pipeline_bit_identical(mode, dtype, monkeypatch):
     """ZG_SCAN_WP=1 / 2 (scan_fwd_wp.cuh: every warp runs its own staging ring, no block barrier; cp.async or TMA staging of
-    u / delta) and 3 / 4 (scan_fwd_wp2.cuh: the same with two channels per lane) against ZG_SCAN_WP=0 (scan_fwd_tma_kernel): the same operations in the same order per channel, so every output --
+    u / delta), 3 / 4 (scan_fwd_wp2.cuh: the same with two channels per lane) and 5 (scan_fwd_wph.cuh: CTAs that mix both kinds of
+    warps) against ZG_SCAN_WP=0 (scan_fwd_tma_kernel): the same operations in the same order per channel, so every output --
     out, last state, checkpoints, the reversed / accumulated output of the v2 sweep, the two-level z batch -- is bit identical.
     (The CTA-wide kernel itself is checked against the C oracle by the tests above and below.)"""
     from zigma_b200.selective_scan_interface import _scan_fwd
@@ -238,7 +239,7 @@ def test_selective_scan_warp_private_pipeline_bit_identical(mode, dtype, monkeyp
          f"wp {mode} {dtype} z_btk")
 
 
-@pytest.mark.parametrize("wp", ["1", "2", "3", "4"])
+@pytest.mark.parametrize("wp", ["1", "2", "3", "4", "5"])
 def test_selective_scan_warp_private_pipeline_vs_oracle(wp):
     """The hot-path scan tests (C oracle, zigzag table, v2 sweep, temporal layout) with ZG_SCAN_WP set, in a child process."""
     import os, subprocess, sys

@@ -633,9 +633,13 @@ int scan_fwd_wp_bf16(const zg_scan_params &p, cudaStream_t stream, int mode);
 int scan_fwd_wp_f16(const zg_scan_params &p, cudaStream_t stream, int mode);
 int scan_fwd_wp2_bf16(const zg_scan_params &p, cudaStream_t stream, int mode);     // two channels per lane (scan_fwd_wp2.cuh)
 int scan_fwd_wp2_f16(const zg_scan_params &p, cudaStream_t stream, int mode);
+int scan_fwd_wph_bf16(const zg_scan_params &p, cudaStream_t stream);               // mixed 32- / 16-channel warps (scan_fwd_wph.cuh)
+int scan_fwd_wph_f16(const zg_scan_params &p, cudaStream_t stream);
 template <typename T> inline int wp_dispatch(const zg_scan_params &p, cudaStream_t stream, int mode) {
-    if constexpr (std::is_same<T, __nv_bfloat16>::value) return mode >= 3 ? scan_fwd_wp2_bf16(p, stream, mode) : scan_fwd_wp_bf16(p, stream, mode);
-    else return mode >= 3 ? scan_fwd_wp2_f16(p, stream, mode) : scan_fwd_wp_f16(p, stream, mode);
+    if constexpr (std::is_same<T, __nv_bfloat16>::value)
+        return mode == 5 ? scan_fwd_wph_bf16(p, stream) : mode >= 3 ? scan_fwd_wp2_bf16(p, stream, mode) : scan_fwd_wp_bf16(p, stream, mode);
+    else
+        return mode == 5 ? scan_fwd_wph_f16(p, stream) : mode >= 3 ? scan_fwd_wp2_f16(p, stream, mode) : scan_fwd_wp_f16(p, stream, mode);
 }
 
 // host-side eligibility test + launch; returns -1 when the call does not fit the specialisation (never for a fused request:
@@ -672,10 +676,10 @@ template <typename T> int try_launch_scan_fwd_tma(const zg_scan_params &p, cudaS
     if (p.z_batch_inner > 0 && (!p.z || !p.z_rowmap || p.z_sbi % 8 != 0)) return decline("z_batch_inner needs z with a z_rowmap and 16-byte aligned rows");
     if (!fuse) {
         // ZG_SCAN_WP: the warp-private pipelines: 1 / 2 = scan_fwd_wp.cuh (one channel per lane; cp.async staging / TMA tiles for
-        // u and delta), 3 / 4 = scan_fwd_wp2.cuh (two channels per lane; cp.async / TMA), 0 = this file's kernel
+        // u and delta), 3 / 4 = scan_fwd_wp2.cuh (two channels per lane; cp.async / TMA), 5 = scan_fwd_wph.cuh (mixed warps), 0 = this file's kernel
         // (read at every call, unlike the other switches: the tests compare the kernels bit for bit inside one process)
         const int wp_mode = pt_env_int("ZG_SCAN_WP", ZG_SCAN_WP_DEFAULT);
-        if (wp_mode >= 1 && wp_mode <= 4) return wp_dispatch<T>(p, stream, wp_mode);
+        if (wp_mode >= 1 && wp_mode <= 5) return wp_dispatch<T>(p, stream, wp_mode);
         return pt_launch_variant<T, 0>(p, stream);
     }
     // fused prologue: B and C must be the tail of the dt_x rows (the x_dbl rows of x_proj)

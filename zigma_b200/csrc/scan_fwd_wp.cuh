@@ -44,40 +44,26 @@ struct WpLayout {                     // per warp
     static constexpr int WARP_BYTES = ((BAR_OFF + NSTAGE * 8 + 127) / 128) * 128;
 };
 
-template <typename T, bool CKPT, bool PLAIN, bool TMA, int NPOLY = 0>
-// (576 threads x 2 CTAs: the register cap that lets 36 warps live on an SM, 56 per thread)
-// sync_every = K > 0: the warps of the CTA meet at a named barrier every K stages.  They exchange nothing -- the barrier is a
-// fairness throttle (see wp_pick_shape): a warp that has run ahead sleeps there and leaves the MUFU pipe to the others.
-__global__ void __launch_bounds__(32 * WP_MAX_WARPS, 2) scan_fwd_wp_kernel(const zg_scan_params p, const __grid_constant__ PtMaps maps, const int sync_every) {
+// The work of one warp: 16 channels [e0, e0 + 16) of group g of batch row b, all seqlen steps.  `smem`: the warp's WpLayout bytes.
+// sync_every = K > 0: the cta_warps warps of the CTA that have work meet at a named barrier every K stages.  They exchange nothing --
+// the barrier is a fairness throttle (see wp_pick_shape; measured: it only costs).
+template <typename T, bool CKPT, bool PLAIN, bool TMA, int NPOLY>
+__device__ __forceinline__ void wp_body(const zg_scan_params &p, const PtMaps &maps, unsigned char *smem, const int lane, const int b, const int g, const int e0,
+                                        const int sync_every, const int cta_warps) {
     static_assert(sizeof(T) == 2, "16-bit I/O only");
     using LY = WpLayout;
     constexpr int NSTAGE = LY::NSTAGE, TL = PT_TL, TILE = LY::TILE, NPAIR = 4;
-    extern __shared__ __align__(1024) unsigned char smem_all[];
-    const int lane = threadIdx.x & 31;
-    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // warp-uniform for the compiler: barrier / tile addresses in uniform registers
-    unsigned char *smem = smem_all + warp * LY::WARP_BYTES;
     unsigned char *ddu = smem + LY::DDU_OFF;
     float *bcf = reinterpret_cast<float *>(smem + LY::BCF_OFF);
     uint64_t *full = reinterpret_cast<uint64_t *>(smem + LY::BAR_OFF);
 
     const int part = lane & 1;                                     // which 8 states of the channel
     const int E = p.dim, L = p.seqlen;
-    const int per_group = E / p.ngroups;
-    const int units_per_group = per_group / WP_CH;
-    const int units = units_per_group * p.ngroups;                 // 16-channel units of a batch row
-    const int wu = blockIdx.x * (int)(blockDim.x >> 5) + warp;     // warps are independent: any number of them per CTA
-    if (wu >= units * p.batch) return;
-    // warps of this CTA that have work (the last CTA may be short): the participants of the fairness barrier
-    const int cta_warps = min((int)(blockDim.x >> 5), units * p.batch - (int)blockIdx.x * (int)(blockDim.x >> 5));
-    int sync_left = sync_every;
-    const int b = wu / units;
-    const int unit = wu % units;
-    const int g = unit / units_per_group;
-    const int e0 = g * per_group + (unit % units_per_group) * WP_CH;
     const int e = e0 + (lane >> 1);                                // main phase: this thread's channel
     const bool has_z = PLAIN ? true : (p.z != nullptr);
     const bool softplus = PLAIN ? true : ((p.flags & ZG_SCAN_DELTA_SOFTPLUS) != 0);
     const int nstages = L / TL;
+    int sync_left = sync_every;
 
     // ---- per-thread constants -----------------------------------------------------------------------------------
     zg_f2 Al2p[NPAIR], h2[NPAIR];
@@ -244,6 +230,23 @@ __global__ void __launch_bounds__(32 * WP_MAX_WARPS, 2) scan_fwd_wp_kernel(const
         dst[0] = make_float4(h2[0].x, h2[0].y, h2[1].x, h2[1].y);
         dst[1] = make_float4(h2[2].x, h2[2].y, h2[3].x, h2[3].y);
     }
+}
+
+// (576 threads x 2 CTAs: the register cap that lets 36 warps live on an SM, 56 per thread)
+template <typename T, bool CKPT, bool PLAIN, bool TMA, int NPOLY = 0>
+__global__ void __launch_bounds__(32 * WP_MAX_WARPS, 2) scan_fwd_wp_kernel(const zg_scan_params p, const __grid_constant__ PtMaps maps, const int sync_every) {
+    extern __shared__ __align__(1024) unsigned char smem_all[];
+    const int lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // warp-uniform for the compiler: barrier / tile addresses in uniform registers
+    const int per_group = p.dim / p.ngroups;
+    const int units_per_group = per_group / WP_CH;
+    const int units = units_per_group * p.ngroups;                 // 16-channel units of a batch row
+    const int wu = blockIdx.x * (int)(blockDim.x >> 5) + warp;     // warps are independent: any number of them per CTA
+    if (wu >= units * p.batch) return;
+    // warps of this CTA that have work (the last CTA may be short): the participants of the fairness barrier
+    const int cta_warps = min((int)(blockDim.x >> 5), units * p.batch - (int)blockIdx.x * (int)(blockDim.x >> 5));
+    const int unit = wu % units;
+    wp_body<T, CKPT, PLAIN, TMA, NPOLY>(p, maps, smem_all + warp * WpLayout::WARP_BYTES, lane, wu / units, unit / units_per_group, unit * WP_CH, sync_every, cta_warps);
 }
 
 // CTA shape.  The warps exchange nothing, so the CTA size is free; what it decides is how the SM's warp schedulers treat the

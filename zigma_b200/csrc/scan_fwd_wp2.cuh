@@ -85,30 +85,18 @@ __device__ __forceinline__ void wp2_main_stage(const unsigned char *__restrict__
     }
 }
 
+// The work of one warp: 32 channels [e0, e0 + 32) of group g of batch row b, all seqlen steps.  `smem`: the warp's Wp2Layout bytes.
 template <typename T, bool CKPT, bool PLAIN, bool TMA>
-__global__ void __launch_bounds__(32 * WP2_MAX_WARPS, 2) scan_fwd_wp2_kernel(const zg_scan_params p, const __grid_constant__ PtMaps maps) {
+__device__ __forceinline__ void wp2_body(const zg_scan_params &p, const PtMaps &maps, unsigned char *smem, const int lane, const int b, const int g, const int e0) {
     static_assert(sizeof(T) == 2, "16-bit I/O only");
     using LY = Wp2Layout;
     constexpr int NSTAGE = LY::NSTAGE, TL = PT_TL, TILE = LY::TILE, NITEM = 4;
-    extern __shared__ __align__(1024) unsigned char smem_all[];
-    const int lane = threadIdx.x & 31;
-    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // warp-uniform for the compiler
-    unsigned char *smem = smem_all + warp * LY::WARP_BYTES;
     unsigned char *ddu = smem + LY::DDU_OFF;
     float *bcf = reinterpret_cast<float *>(smem + LY::BCF_OFF);
     uint64_t *full = reinterpret_cast<uint64_t *>(smem + LY::BAR_OFF);
 
     const int part = lane & 1;                                     // which 8 states of the lane's two channels
     const int E = p.dim, L = p.seqlen;
-    const int per_group = E / p.ngroups;
-    const int units_per_group = per_group / WP2_CH;
-    const int units = units_per_group * p.ngroups;                 // 32-channel units of a batch row
-    const int wu = blockIdx.x * (int)(blockDim.x >> 5) + warp;     // warps are independent: any number of them per CTA
-    if (wu >= units * p.batch) return;
-    const int b = wu / units;
-    const int unit = wu % units;
-    const int g = unit / units_per_group;
-    const int e0 = g * per_group + (unit % units_per_group) * WP2_CH;
     const int e = e0 + (lane >> 1) * 2;                            // main phase: this lane's first channel (the second is e + 1)
     const bool has_z = PLAIN ? true : (p.z != nullptr);
     const bool softplus = PLAIN ? true : ((p.flags & ZG_SCAN_DELTA_SOFTPLUS) != 0);
@@ -282,6 +270,20 @@ __global__ void __launch_bounds__(32 * WP2_MAX_WARPS, 2) scan_fwd_wp2_kernel(con
             dst[1] = make_float4(h2[c][2].x, h2[c][2].y, h2[c][3].x, h2[c][3].y);
         }
     }
+}
+
+template <typename T, bool CKPT, bool PLAIN, bool TMA>
+__global__ void __launch_bounds__(32 * WP2_MAX_WARPS, 2) scan_fwd_wp2_kernel(const zg_scan_params p, const __grid_constant__ PtMaps maps) {
+    extern __shared__ __align__(1024) unsigned char smem_all[];
+    const int lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // warp-uniform for the compiler
+    const int per_group = p.dim / p.ngroups;
+    const int units_per_group = per_group / WP2_CH;
+    const int units = units_per_group * p.ngroups;                 // 32-channel units of a batch row
+    const int wu = blockIdx.x * (int)(blockDim.x >> 5) + warp;     // warps are independent: any number of them per CTA
+    if (wu >= units * p.batch) return;
+    const int unit = wu % units;
+    wp2_body<T, CKPT, PLAIN, TMA>(p, maps, smem_all + warp * Wp2Layout::WARP_BYTES, lane, wu / units, unit / units_per_group, unit * WP2_CH);
 }
 
 // CTA shape: see wp_pick_shape.  Half the warps of the one-channel-per-lane kernel: up to 18 per SM (112 registers) in two CTAs.
