@@ -296,16 +296,22 @@ def scan_roofline(name, bs, dev, step_ms=None, depth=None):
         abytes = scan_algorithmic_bytes(sb, E, L, N, 2)
         ach = abytes / (kms * 1e-3) / 1e9
         floor = scan_mufu_floor_ms(sb, E, L, N)
-        res.append({"shape": f"{kind}: batch {sb} x dim {E} x seqlen {L}", "ms_per_launch": kms, "algorithmic_bytes": abytes, "achieved": ach,
+        from zigma_b200 import _lib as _zl
+        res.append({"shape": f"{kind}: batch {sb} x dim {E} x seqlen {L}", "kernel": _zl.last_scan_kernel(), "ms_per_launch": kms, "algorithmic_bytes": abytes, "achieved": ach,
                     "frac": ach / peak, "hbm_floor_ms": abytes / (peak * 1e9) * 1e3, "compute_floor_ms": floor, "frac_of_compute_floor": floor / kms})
         del xz, xc, dl, xdbl, outb
     r0 = res[0]
+    kname = res[0]["kernel"]
     traffic, tsrc = None, None
-    tp = os.path.join(ROOT, "profiles", "r02_scan_fwd_traffic.json")
-    if name == DEFAULT and os.path.exists(tp):
-        tj = json.load(open(tp))
-        traffic, tsrc = tj.get("dram_bytes_per_launch"), tj.get("source")
-    roof = {"bound": "hbm", "kernel": "zg::scan_fwd_tma_kernel<bf16> (dstate 16, token-major, TMA tensor tiles + z gathered through the zigzag table)",
+    if name == DEFAULT:     # DRAM bytes of one launch from this round's ncu capture of the kernel that actually ran
+        for fn in ("r02b_scan_fwd_traffic.json", "r02_scan_fwd_traffic.json"):
+            tp = os.path.join(ROOT, "profiles", fn)
+            if os.path.exists(tp):
+                tj = json.load(open(tp))
+                if tj.get("kernel", "zg::scan_fwd_tma_kernel") in kname:
+                    traffic, tsrc = tj.get("dram_bytes_per_launch"), tj.get("source")
+                    break
+    roof = {"bound": "hbm", "kernel": kname + " <bf16>: dstate 16, token-major, z gathered through the zigzag table",
             "achieved": r0["achieved"], "peak": peak, "unit": "GB/s", "frac": r0["frac"], "traffic": traffic, "traffic_source": tsrc,
             "peak_source": how, "ms_per_launch": r0["ms_per_launch"], "algorithmic_bytes": r0["algorithmic_bytes"],
             "hbm_floor_ms": r0["hbm_floor_ms"],

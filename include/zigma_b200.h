@@ -55,6 +55,8 @@ int zg_abi_version(void);
 const char *zg_last_error(void);
 /* number of kernels launched through this library since load (bench `gpu_launches` evidence) */
 uint64_t zg_launch_count(void);
+/* name of the kernel the most recent zg_selective_scan_fwd call launched ("" before the first call): bench / profile labels */
+const char *zg_last_scan_kernel(void);
 
 /* ---------------------------------------------------------------------------------------------
  * Selective scan (S6).  Logical shapes: u, delta, z, out (batch, dim, seqlen); any of the two

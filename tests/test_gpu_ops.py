@@ -327,8 +327,13 @@ def test_selective_scan_properties_full_size():
     Bv = xbc[:, :, :N].permute(0, 2, 1).unsqueeze(1)
     Cv = xbc[:, :, N:].permute(0, 2, 1).unsqueeze(1)
     run = lambda u_, d_, z_, B_, C_: selective_scan_fn(lg(u_), lg(d_), A, B_, C_, D, z=lg(z_), delta_bias=bias, delta_softplus=True)
+    import os
+    from zigma_b200 import _lib
     out = run(u, delta, z, Bv, Cv)
     assert out.shape == (Bt, E, L) and torch.isfinite(out.float()).all()
+    auto = "ZG_SCAN_WP" not in os.environ and torch.cuda.get_device_properties(0).multi_processor_count == 148
+    if auto:    # scan_auto_choice: 5120 units on 148 SMs -> CTAs of 8 wide + 2 narrow warps
+        assert "scan_fwd_wph_kernel" in _lib.last_scan_kernel(), _lib.last_scan_kernel()
     # causality
     u2, d2, z2, x2 = u.clone(), delta.clone(), z.clone(), xbc.clone()
     u2[:, L // 2:] = 0; d2[:, L // 2:] = 0; z2[:, L // 2:] = 1; x2[:, L // 2:] = 0
@@ -339,6 +344,8 @@ def test_selective_scan_properties_full_size():
     out3 = run(u[sl].contiguous(), delta[sl].contiguous(), z[sl].contiguous(),
                xbc[sl].contiguous()[:, :, :N].permute(0, 2, 1).unsqueeze(1), xbc[sl].contiguous()[:, :, N:].permute(0, 2, 1).unsqueeze(1))
     assert torch.equal(out[sl], out3)
+    if auto:    # ... and two batch rows are the CTA-wide kernel's: the comparison above is ACROSS the two kernels
+        assert "scan_fwd_tma_kernel" in _lib.last_scan_kernel(), _lib.last_scan_kernel()
     # sampled rows vs the C oracle
     bs, es = [0, 31, 63], [0, 5, 640, 1279]
     f = lambda x: x[bs][:, :, es].float().cpu().permute(0, 2, 1).contiguous().numpy()

@@ -91,7 +91,7 @@ class AdamWParams(C.Structure):
                                       "ema_decay", "grad_scale")])
 
 
-EXPORTS = ["zg_abi_version", "zg_last_error", "zg_launch_count", "zg_selective_scan_fwd", "zg_selective_scan_bwd",
+EXPORTS = ["zg_abi_version", "zg_last_error", "zg_launch_count", "zg_last_scan_kernel", "zg_selective_scan_fwd", "zg_selective_scan_bwd",
            "zg_causal_conv1d_fwd", "zg_causal_conv1d_bwd", "zg_add_norm_fwd", "zg_add_norm_bwd",
            "zg_block_tail_fwd", "zg_block_tail_bwd", "zg_gemm_bf16_tn", "zg_adamw_ema_step"]
 
@@ -109,7 +109,9 @@ def lib():
         l = C.CDLL(LIB_PATH)
         l.zg_last_error.restype = C.c_char_p
         l.zg_launch_count.restype = C.c_uint64
-        for name in EXPORTS[3:]:
+        l.zg_last_scan_kernel.restype = C.c_char_p
+        l.zg_last_scan_kernel.argtypes = []
+        for name in EXPORTS[4:]:
             getattr(l, name).restype = C.c_int
             getattr(l, name).argtypes = [C.c_void_p, C.c_void_p]
         _lib = l
@@ -118,6 +120,11 @@ def lib():
 
 def launch_count():
     return int(lib().zg_launch_count())
+
+
+def last_scan_kernel():
+    """Name of the kernel the most recent selective-scan forward call launched."""
+    return lib().zg_last_scan_kernel().decode()
 
 
 def call(name, params):

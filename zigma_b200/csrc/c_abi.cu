@@ -6,6 +6,7 @@
 
 static thread_local char g_err[512] = "";
 static std::atomic<uint64_t> g_launches{0};
+static std::atomic<const char *> g_scan_kernel{""};
 
 int zg_set_error(const char *fmt, ...) {
     va_list ap;
@@ -14,6 +15,7 @@ int zg_set_error(const char *fmt, ...) {
     va_end(ap);
     return 1;
 }
+void zg_note_scan_kernel(const char *name) { g_scan_kernel.store(name, std::memory_order_relaxed); }
 void zg_count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
 int zg_check_launch(const char *what) {
     cudaError_t err = cudaPeekAtLastError();
@@ -30,6 +32,7 @@ int zg_abi_version(void) { return 3; }   // 3: fused dt_proj prologue fields in 
 // int zg_abi_version(void) { return 2; }   // 2: block-tail rstd + backward, AdamW+EMA step, (batch, n_ckpt, dim, dstate) checkpoints
 const char *zg_last_error(void) { return g_err; }
 uint64_t zg_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+const char *zg_last_scan_kernel(void) { return g_scan_kernel.load(std::memory_order_relaxed); }
 
 int zg_selective_scan_fwd(const zg_scan_params *pp, void *stream) {
     ZG_REQUIRE(pp != nullptr, "selective_scan_fwd: null params");

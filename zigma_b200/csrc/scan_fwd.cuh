@@ -432,6 +432,7 @@ int launch_scan_fwd(const zg_scan_params &p, cudaStream_t stream) {
     if (nblk == 0) return 0;
     kern<<<(unsigned)nblk, SCAN_CH, smem, stream>>>(p);
     zg_count_launch();
+    zg_note_scan_kernel("zg::scan_fwd_kernel (generic: one thread per channel)");
     return zg_check_launch("scan_fwd");
 }
 

@@ -45,7 +45,7 @@
 #define ZG_SCAN_SWP 1      // hand software-pipelined recurrence loop (0: the straight loop)
 #endif
 #ifndef ZG_SCAN_WP_DEFAULT
-#define ZG_SCAN_WP_DEFAULT 0   // 0: CTA-wide phases (this file); 1 / 2: warp-private pipeline (scan_fwd_wp.cuh), cp.async / TMA staging; 3 / 4: two channels per lane (scan_fwd_wp2.cuh)
+#define ZG_SCAN_WP_DEFAULT -1  // -1: chosen per call (scan_auto_choice); 0: CTA-wide phases (this file); 1 / 2: warp-private pipeline (scan_fwd_wp.cuh), cp.async / TMA staging; 3 / 4: two channels per lane (scan_fwd_wp2.cuh); 5: mixed CTAs (scan_fwd_wph.cuh)
 #endif
 #ifndef ZG_SCAN_TMA_NPOLY_DEFAULT
 #define ZG_SCAN_TMA_NPOLY_DEFAULT 0
@@ -607,6 +607,7 @@ template <typename T, int R, int NPOLY, bool CKPT, int TPC = 2, bool PLAIN = fal
     const long long nblk = (long long)(p.dim / PT_CH) * p.batch;
     kern<<<(unsigned)nblk, 64 * TPC, LY::TOTAL, stream>>>(p, maps);
     zg_count_launch();
+    zg_note_scan_kernel(R > 0 ? "zg::scan_fwd_tma_kernel (CTA-wide phases, TMA tensor tiles, fused dt_proj prologue)" : "zg::scan_fwd_tma_kernel (CTA-wide phases, TMA tensor tiles)");
     return zg_check_launch("scan_fwd(tma)");
 }
 
@@ -633,13 +634,46 @@ int scan_fwd_wp_bf16(const zg_scan_params &p, cudaStream_t stream, int mode);
 int scan_fwd_wp_f16(const zg_scan_params &p, cudaStream_t stream, int mode);
 int scan_fwd_wp2_bf16(const zg_scan_params &p, cudaStream_t stream, int mode);     // two channels per lane (scan_fwd_wp2.cuh)
 int scan_fwd_wp2_f16(const zg_scan_params &p, cudaStream_t stream, int mode);
-int scan_fwd_wph_bf16(const zg_scan_params &p, cudaStream_t stream);               // mixed 32- / 16-channel warps (scan_fwd_wph.cuh)
-int scan_fwd_wph_f16(const zg_scan_params &p, cudaStream_t stream);
-template <typename T> inline int wp_dispatch(const zg_scan_params &p, cudaStream_t stream, int mode) {
+int scan_fwd_wph_bf16(const zg_scan_params &p, cudaStream_t stream, int nd, int ns);   // mixed 32- / 16-channel warps (scan_fwd_wph.cuh)
+int scan_fwd_wph_f16(const zg_scan_params &p, cudaStream_t stream, int nd, int ns);
+template <typename T> inline int wp_dispatch(const zg_scan_params &p, cudaStream_t stream, int mode, int nd = 0, int ns = 0) {
     if constexpr (std::is_same<T, __nv_bfloat16>::value)
-        return mode == 5 ? scan_fwd_wph_bf16(p, stream) : mode >= 3 ? scan_fwd_wp2_bf16(p, stream, mode) : scan_fwd_wp_bf16(p, stream, mode);
+        return mode == 5 ? scan_fwd_wph_bf16(p, stream, nd, ns) : mode >= 3 ? scan_fwd_wp2_bf16(p, stream, mode) : scan_fwd_wp_bf16(p, stream, mode);
     else
-        return mode == 5 ? scan_fwd_wph_f16(p, stream) : mode >= 3 ? scan_fwd_wp2_f16(p, stream, mode) : scan_fwd_wp_f16(p, stream, mode);
+        return mode == 5 ? scan_fwd_wph_f16(p, stream, nd, ns) : mode >= 3 ? scan_fwd_wp2_f16(p, stream, mode) : scan_fwd_wp_f16(p, stream, mode);
+}
+
+// Which hot-path kernel runs a call (ZG_SCAN_WP unset).  All of them compute the same bits; what differs is how the work
+// quantises over the 4 x SMs sub-partitions and how busy each keeps its MUFU pipe (measured on B200):
+// the 32-channel warps of scan_fwd_wp2 reach 85 % of the pipe against 76-79 % for 16-channel warps, but their unit of work is twice
+// as large.  In 16-channel units, with U of them and S SMs, the fullest sub-partition carries
+//     CTA-wide kernel (4 warps, one per sub-partition)      ceil(ceil(U / 4) / S)
+//     32-channel warps                                      2 ceil(ceil(ceil(U / 2) / S) / 4)
+//     mixed CTAs, two per SM, nd wide + ns narrow warps     nd / 4 * 2 + ns / 2   per CTA pair: (2 nd + ns) / 2
+// Several waves: 32-channel warps (finished CTAs are replaced, the quantisation does not matter; measured - 5 %).  One wave: the
+// 32-channel warps when they quantise no worse than the CTA-wide kernel (FacesHQ-1024 layer shape: 6 = 6, measured - 7 %), else
+// mixed CTAs when those do (config 2: U = 5120 -> 18 units per CTA = 8 + 2 warps, 9 = 9, measured - 8 %), else the CTA-wide kernel
+// (batch 16: 3 against 4).  The training forward (checkpoints) keeps the CTA-wide kernel.
+struct ScanChoice { int mode, nd, ns; };
+inline ScanChoice scan_auto_choice(const zg_scan_params &p) {
+    if (p.ckpt) return {0, 0, 0};
+    static int sms_dev[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!sms_dev[dev & 63]) cudaDeviceGetAttribute(&sms_dev[dev & 63], cudaDevAttrMultiProcessorCount, dev);
+    const long long S = sms_dev[dev & 63] > 0 ? sms_dev[dev & 63] : 148;
+    const long long U = (long long)(p.dim / 16) * p.batch;
+    if (U < 16 * S) return {0, 0, 0};      // under four units per sub-partition nothing saturates the pipe: the narrow warps' shorter steps win (batch 16: 0.211 vs 0.229 ms)
+    if (U > 36 * S) return {3, 0, 0};
+    const long long base = ((U + 3) / 4 + S - 1) / S;
+    const long long wide = 2 * ((((U + 1) / 2 + S - 1) / S + 3) / 4);
+    if (wide <= base) return {3, 0, 0};
+    const long long per_cta = (((U + S - 1) / S + 1) / 2 + 1) & ~1LL;      // units per CTA, two CTAs per SM, even
+    for (int nd = 8; nd >= 4; nd -= 4) {                                   // wide warps in multiples of 4 (one per sub-partition), at most 10 warps
+        const long long ns = per_cta - 2 * nd;
+        if (ns >= 0 && (ns & 1) == 0 && nd + ns <= 10 && per_cta / 2 <= base) return {5, nd, (int)ns};
+    }
+    return {0, 0, 0};
 }
 
 // host-side eligibility test + launch; returns -1 when the call does not fit the specialisation (never for a fused request:
@@ -680,6 +714,10 @@ template <typename T> int try_launch_scan_fwd_tma(const zg_scan_params &p, cudaS
         // (read at every call, unlike the other switches: the tests compare the kernels bit for bit inside one process)
         const int wp_mode = pt_env_int("ZG_SCAN_WP", ZG_SCAN_WP_DEFAULT);
         if (wp_mode >= 1 && wp_mode <= 5) return wp_dispatch<T>(p, stream, wp_mode);
+        if (wp_mode < 0) {
+            const ScanChoice c = scan_auto_choice(p);
+            if (c.mode) return wp_dispatch<T>(p, stream, c.mode, c.nd, c.ns);
+        }
         return pt_launch_variant<T, 0>(p, stream);
     }
     // fused prologue: B and C must be the tail of the dt_x rows (the x_dbl rows of x_proj)

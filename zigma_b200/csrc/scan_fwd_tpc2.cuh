@@ -198,6 +198,7 @@ template <typename T> int try_launch_scan_fwd_tpc2(const zg_scan_params &p, cuda
     else if (npoly == 2) launch(scan_fwd_tpc2_kernel<T, 2>);
     else launch(scan_fwd_tpc2_kernel<T, 0>);
     zg_count_launch();
+    zg_note_scan_kernel("zg::scan_fwd_tpc2_kernel (round 1: LDGSTS ring, two threads per channel)");
     return zg_check_launch("scan_fwd(tpc2)");
 }
 

@@ -154,6 +154,7 @@ __device__ __forceinline__ void wp2_body(const zg_scan_params &p, const PtMaps &
         u_step = (uint32_t)p.u_sl * (2u * TL);
         d_step = (uint32_t)p.delta_sl * (2u * TL);
     }
+    const uint64_t bc_policy = zg_l2_policy_evict_last();            // the B|C rows are re-read by every warp of the batch row: keep them in L2
     int s_issue = 0;                                               // stages are issued in order
     auto issue_stage = [&](int slot) {                             // all lanes
         if (s_issue >= nstages) return;
@@ -177,7 +178,7 @@ __device__ __forceinline__ void wp2_body(const zg_scan_params &p, const PtMaps &
             const int ln = l0 + TL + zr;
             zrow_next = (ln < L) ? (zmap ? zmap[ln] : ln) : 0;
         }
-        zg_cp_async16(raw + 3 * TILE + lane * 16, bc_src);
+        zg_cp_async16_hint(raw + 3 * TILE + lane * 16, bc_src, bc_policy);
         bc_src += bc_step;
         pt_cp_async_arrive(bar);
         ++s_issue;
@@ -322,6 +323,7 @@ template <typename T, bool CKPT, bool PLAIN, bool TMA> int wp2_launch(const zg_s
     const long long nblk = (units + w - 1) / w;
     kern<<<(unsigned)nblk, 32 * w, w * LY::WARP_BYTES, stream>>>(p, maps);
     zg_count_launch();
+    zg_note_scan_kernel(TMA ? "zg::scan_fwd_wp2_kernel (warp-private pipeline, 32 channels per warp, TMA tiles)" : "zg::scan_fwd_wp2_kernel (warp-private pipeline, 32 channels per warp, cp.async)");
     return zg_check_launch("scan_fwd(wp2)");
 }
 

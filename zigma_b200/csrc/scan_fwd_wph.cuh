@@ -59,12 +59,14 @@ template <typename T, bool CKPT, bool PLAIN> int wph_launch(const zg_scan_params
     const long long nblk = (units + per_cta - 1) / per_cta;
     kern<<<(unsigned)nblk, 32 * (nd + ns), nd * Wp2Layout::WARP_BYTES + ns * WpLayout::WARP_BYTES, stream>>>(p, maps, nd, ns);
     zg_count_launch();
+    zg_note_scan_kernel("zg::scan_fwd_wph_kernel (warp-private pipeline, CTAs of 32- and 16-channel warps, cp.async)");
     return zg_check_launch("scan_fwd(wph)");
 }
 
-// mode 5.  nd wide + ns narrow warps per CTA (ZG_SCAN_WPH_ND / ZG_SCAN_WPH_NS, default 8 + 2: config 2 on 148 SMs).
-template <typename T> int wph_launch_variant(const zg_scan_params &p, cudaStream_t stream) {
-    int nd = pt_env_int("ZG_SCAN_WPH_ND", 8), ns = pt_env_int("ZG_SCAN_WPH_NS", 2);
+// mode 5.  nd wide + ns narrow warps per CTA: the caller's choice (scan_auto_choice), else ZG_SCAN_WPH_ND / ZG_SCAN_WPH_NS
+// (default 8 + 2: config 2 on 148 SMs).
+template <typename T> int wph_launch_variant(const zg_scan_params &p, cudaStream_t stream, int nd, int ns) {
+    if (nd <= 0) { nd = pt_env_int("ZG_SCAN_WPH_ND", 8); ns = pt_env_int("ZG_SCAN_WPH_NS", 2); }
     if (nd < 0 || ns < 0 || nd + ns < 1 || nd + ns > WPH_MAX_WARPS || (ns & 1)) { nd = 8; ns = 2; }     // (an even number of narrow warps: a CTA starts at an even unit)
     const bool plain = p.z && (p.flags & ZG_SCAN_DELTA_SOFTPLUS) && !(p.flags & (ZG_SCAN_OUT_REVERSE | ZG_SCAN_OUT_ACCUMULATE));
     if (p.ckpt) return wph_launch<T, true, false>(p, stream, nd, ns);

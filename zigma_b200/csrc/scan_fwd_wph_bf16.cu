@@ -1,5 +1,5 @@
 // selective-scan forward, warp-private pipeline with mixed 32- / 16-channel warps, I/O dtype __nv_bfloat16 (own TU)
 #include "scan_fwd_wph.cuh"
 namespace zg {
-int scan_fwd_wph_bf16(const zg_scan_params &p, cudaStream_t stream) { return wph_launch_variant<__nv_bfloat16>(p, stream); }
+int scan_fwd_wph_bf16(const zg_scan_params &p, cudaStream_t stream, int nd, int ns) { return wph_launch_variant<__nv_bfloat16>(p, stream, nd, ns); }
 }  // namespace zg
