@@ -133,10 +133,32 @@ __device__ __forceinline__ float2 pt_softplus20_2(float2 x) {
     r.y = (x.y > 20.f) ? x.y : r.y;
     return r;
 }
+// 1 / d for d in [1, 2^126] on the FMA pipe: integer-subtraction seed (relative error < 12.5 %) and three Newton steps in the
+// residual form r += r (1 - d r); maximum relative error 6.8e-8 over the range (MUFU.RCP: 1.2e-7).
+__device__ __forceinline__ float2 pt_rcp2_fma(float2 d) {
+    float2 r = make_float2(__int_as_float(0x7EF311C7 - __float_as_int(d.x)), __int_as_float(0x7EF311C7 - __float_as_int(d.y)));
+    const float2 nd = make_float2(-d.x, -d.y), one = zg_splat2(1.f);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) r = zg_fma2(r, zg_fma2(nd, r, one), r);
+    return r;
+}
+// SiLU of a channel pair.  ZG_SCAN_RCP_FMA: the reciprocal of the sigmoid on the FMA pipe instead of MUFU.RCP -- the scan kernels
+// are bound by the MUFU pipe (20 per (b, e, l), one of them this reciprocal) and have issue slots to spare.  The exponent is
+// clamped so that 1 + 2^t stays finite (z < -87: silu(z) ~ -1e-36 instead of -0).
+#ifndef ZG_SCAN_RCP_FMA
+#define ZG_SCAN_RCP_FMA 0
+#endif
 __device__ __forceinline__ float2 pt_silu2(float2 z) {
-    const float2 t = zg_mul2(z, zg_splat2(-ZG_LOG2E));
+    float2 t = zg_mul2(z, zg_splat2(-ZG_LOG2E));
+#if ZG_SCAN_RCP_FMA
+    t.x = fminf(t.x, 126.f);
+    t.y = fminf(t.y, 126.f);
+    const float2 d = zg_add2(make_float2(zg_ex2(t.x), zg_ex2(t.y)), zg_splat2(1.f));
+    return zg_mul2(z, pt_rcp2_fma(d));
+#else
     const float2 d = zg_add2(make_float2(zg_ex2(t.x), zg_ex2(t.y)), zg_splat2(1.f));
     return zg_mul2(z, make_float2(zg_rcp(d.x), zg_rcp(d.y)));
+#endif
 }
 
 __device__ __forceinline__ void pt_ldmatrix_x4(uint32_t &r0, uint32_t &r1, uint32_t &r2, uint32_t &r3, uint32_t saddr) {
