@@ -33,4 +33,11 @@ except Exception as ex:
     print("bench parse failed", ex)
 P
 done
-echo done
+echo done1
+# ---- the build of record (default library): smoke, the full default bench line, launch list
+unset ZIGMA_B200_LIB
+echo "== smoke"; timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
+echo "== bench (default flags)"; timeout 1200 python bench.py > gpurun_out/r02b_bench_n1.json 2> gpurun_out/r02b_bench_n1.err; echo "bench rc=$?"; tail -c 1500 gpurun_out/r02b_bench_n1.json; tail -3 gpurun_out/r02b_bench_n1.err
+echo "== launch list (ncu, eager launches)"
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/r02b_launches.csv python bench.py --steps 2 --warmup 3 --no-graph --no-cpu-baseline --no-ref-cuda --no-train --no-configs > gpurun_out/launchlist_bench.log 2>&1; echo "ncu list rc=$?"
+echo done2

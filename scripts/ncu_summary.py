@@ -9,7 +9,10 @@ KEYS = ["Kernel Name", "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__
         "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active", "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active",
         "sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
         "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
-        "smsp__cycles_active.avg", "lts__t_sector_hit_rate.pct"]
+        "smsp__cycles_active.avg", "smsp__cycles_active.max", "smsp__inst_executed.avg", "smsp__inst_executed.max", "lts__t_sector_hit_rate.pct",
+        "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
+        "l1tex__data_pipe_lsu_wavefronts_mem_shared_op_ld.sum", "l1tex__data_pipe_lsu_wavefronts_mem_shared_op_st.sum",
+        "smsp__sass_l1tex_data_pipe_lsu_wavefronts_mem_shared_op_ldgsts.sum", "sm__inst_executed_pipe_xu.max.pct_of_peak_sustained_active"]
 rep = sys.argv[1]
 out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(out.splitlines()))
@@ -20,6 +23,6 @@ for r in rows[2:]:
         if k in h:
             i = h.index(k)
             print(f"{k:75s} {r[i]:>22s} {units[i]}")
-    stalls = sorted(((float(r[i].replace(',', '') or 0), k) for i, k in enumerate(h) if "warp_issue_stalled" in k and k.endswith("_per_warp_active.pct")), reverse=True)
-    for v, k in stalls[:6]:
-        print(f"  stall {k.replace('smsp__warp_issue_stalled_', '').replace('_per_warp_active.pct', ''):40s} {v:8.2f} %")
+    stalls = sorted(((float(r[i].replace(',', '') or 0), k) for i, k in enumerate(h) if k.startswith("smsp__average_warps_issue_stalled_") and k.endswith("_per_issue_active.ratio")), reverse=True)
+    for v, k in stalls[:7]:
+        print(f"  stalled warps per issue: {k.replace('smsp__average_warps_issue_stalled_', '').replace('_per_issue_active.ratio', ''):28s} {v:8.2f}")
