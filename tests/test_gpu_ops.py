@@ -180,7 +180,7 @@ def test_selective_scan_hot_path_four_threads_per_channel_variant():
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-1000:]
 
 
-@pytest.mark.parametrize("mode", ["1", "2", "3", "4", "5"])
+@pytest.mark.parametrize("mode", ["1", "2", "3", "4", "5", "5:4:2", "5:4:6", "5:8:0"])
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
 def test_selective_scan_warp_private_pipeline_bit_identical(mode, dtype, monkeypatch):
     """ZG_SCAN_WP=1 / 2 (scan_fwd_wp.cuh: every warp runs its own staging ring, no block barrier; cp.async or TMA staging of
@@ -190,6 +190,10 @@ def test_selective_scan_warp_private_pipeline_bit_identical(mode, dtype, monkeyp
     (The CTA-wide kernel itself is checked against the C oracle by the tests above and below.)"""
     from zigma_b200.selective_scan_interface import _scan_fwd
     N = 16
+    if ":" in mode:     # mixed CTAs with another split than the default 8 wide + 2 narrow warps (scan_auto_choice picks these too)
+        mode, nd, ns = mode.split(":")
+        monkeypatch.setenv("ZG_SCAN_WPH_ND", nd)
+        monkeypatch.setenv("ZG_SCAN_WPH_NS", ns)
 
     def both(fn):
         monkeypatch.setenv("ZG_SCAN_WP", "0")
