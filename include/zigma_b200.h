@@ -57,6 +57,10 @@ const char *zg_last_error(void);
 uint64_t zg_launch_count(void);
 /* name of the kernel the most recent zg_selective_scan_fwd call launched ("" before the first call): bench / profile labels */
 const char *zg_last_scan_kernel(void);
+/* The shape rule behind that choice (host arithmetic only, no GPU needed): which hot-path forward kernel runs a call of
+ * units16 = batch * dim / 16 sixteen-channel units on a device with `sms` SMs -- 0 the CTA-wide kernel, 3 the 32-channel-per-warp
+ * pipeline, 5 CTAs of *nd wide + *ns narrow warps.  All kernels produce identical bits. */
+int zg_scan_kernel_choice(int64_t units16, int32_t sms, int32_t training_forward, int32_t *nd, int32_t *ns);
 
 /* ---------------------------------------------------------------------------------------------
  * Selective scan (S6).  Logical shapes: u, delta, z, out (batch, dim, seqlen); any of the two

@@ -81,3 +81,26 @@ def test_ops_fail_loudly_without_cuda():
     from zigma_b200.block_ops import block_tail_fn
     with pytest.raises(RuntimeError):
         block_tail_fn(torch.randn(1, 4, 8), None, None, torch.zeros(1, 8), torch.zeros(1, 8), torch.ones(8), None, None, 1e-5)
+
+
+def test_scan_kernel_choice_shape_rule():
+    """zg_scan_kernel_choice (the pure part of scan_auto_choice, scan_fwd.cuh): which hot-path forward-scan kernel a call gets on a
+    148-SM B200.  The BASELINE workloads per GPU: config 2 -> CTAs of 8 wide + 2 narrow warps (9 units on every sub-partition),
+    FacesHQ-1024 and both video layer shapes -> 32-channel warps, small batches and the training forward -> the CTA-wide kernel."""
+    from zigma_b200 import _lib
+    ch = _lib.scan_kernel_choice
+    assert ch(64, 1280) == (5, 8, 2)                       # zigzag8_b1 / sweep2_b1, bs 64
+    assert ch(32, 1536) == (3, 0, 0)                       # faceshq1024, bs 32
+    assert ch(16 * 16, 1536) == (3, 0, 0)                  # ucf101_sst spatial layers: 256 sequences
+    assert ch(16 * 256, 1536) == (3, 0, 0)                 # ucf101_sst temporal layers: 4096 sequences
+    assert ch(16, 1280) == (0, 0, 0) and ch(2, 128) == (0, 0, 0)
+    assert ch(64, 1280, training_forward=True) == (0, 0, 0)
+    mode, nd, ns = ch(32, 1280)
+    assert (mode, nd, ns) == (5, 4, 2)
+    for bs in range(1, 200):                               # whatever is picked is launchable: <= 10 warps, even narrow count, wide in fours
+        mode, nd, ns = ch(bs, 1280)
+        assert mode in (0, 3, 5)
+        if mode == 5:
+            assert nd in (4, 8) and ns % 2 == 0 and 0 <= ns and nd + ns <= 10
+            units_per_sm = -(-bs * 80 // 148)
+            assert 2 * (2 * nd + ns) >= units_per_sm       # two CTAs per SM hold the SM's share: one wave

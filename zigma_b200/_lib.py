@@ -91,7 +91,7 @@ class AdamWParams(C.Structure):
                                       "ema_decay", "grad_scale")])
 
 
-EXPORTS = ["zg_abi_version", "zg_last_error", "zg_launch_count", "zg_last_scan_kernel", "zg_selective_scan_fwd", "zg_selective_scan_bwd",
+EXPORTS = ["zg_abi_version", "zg_last_error", "zg_launch_count", "zg_last_scan_kernel", "zg_scan_kernel_choice", "zg_selective_scan_fwd", "zg_selective_scan_bwd",
            "zg_causal_conv1d_fwd", "zg_causal_conv1d_bwd", "zg_add_norm_fwd", "zg_add_norm_bwd",
            "zg_block_tail_fwd", "zg_block_tail_bwd", "zg_gemm_bf16_tn", "zg_adamw_ema_step"]
 
@@ -111,7 +111,9 @@ def lib():
         l.zg_launch_count.restype = C.c_uint64
         l.zg_last_scan_kernel.restype = C.c_char_p
         l.zg_last_scan_kernel.argtypes = []
-        for name in EXPORTS[4:]:
+        l.zg_scan_kernel_choice.restype = C.c_int
+        l.zg_scan_kernel_choice.argtypes = [C.c_int64, C.c_int32, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
+        for name in EXPORTS[5:]:
             getattr(l, name).restype = C.c_int
             getattr(l, name).argtypes = [C.c_void_p, C.c_void_p]
         _lib = l
@@ -120,6 +122,13 @@ def lib():
 
 def launch_count():
     return int(lib().zg_launch_count())
+
+
+def scan_kernel_choice(batch, dim, sms=148, training_forward=False):
+    """(mode, wide warps, narrow warps) the shape rule picks for a hot-path forward-scan call (zg_scan_kernel_choice; host arithmetic)."""
+    nd, ns = C.c_int32(0), C.c_int32(0)
+    mode = lib().zg_scan_kernel_choice(int(batch) * (int(dim) // 16), int(sms), int(bool(training_forward)), C.byref(nd), C.byref(ns))
+    return int(mode), int(nd.value), int(ns.value)
 
 
 def last_scan_kernel():

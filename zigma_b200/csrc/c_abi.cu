@@ -33,6 +33,12 @@ int zg_abi_version(void) { return 3; }   // 3: fused dt_proj prologue fields in 
 const char *zg_last_error(void) { return g_err; }
 uint64_t zg_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 const char *zg_last_scan_kernel(void) { return g_scan_kernel.load(std::memory_order_relaxed); }
+int zg_scan_kernel_choice(int64_t units16, int32_t sms, int32_t training_forward, int32_t *nd, int32_t *ns) {
+    const zg::ScanChoice c = zg::scan_choice_for(units16, sms, training_forward != 0);
+    if (nd) *nd = c.nd;
+    if (ns) *ns = c.ns;
+    return c.mode;
+}
 
 int zg_selective_scan_fwd(const zg_scan_params *pp, void *stream) {
     ZG_REQUIRE(pp != nullptr, "selective_scan_fwd: null params");

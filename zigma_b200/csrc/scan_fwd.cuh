@@ -461,6 +461,25 @@ template <typename T, int NS, bool SEQ> int launch_scan_fwd_npoly(const zg_scan_
     return launch_scan_fwd<T, NS, SEQ, false, 0>(p, stream);
 }
 
+// Pure part of scan_auto_choice (scan_fwd_tma.cuh; exported as zg_scan_kernel_choice so that the rule is testable without a GPU):
+// U 16-channel units, S SMs, ckpt = the training forward.  mode 0: CTA-wide kernel, 3: 32-channel warps, 5: mixed CTAs of nd wide +
+// ns narrow warps.
+struct ScanChoice { int mode, nd, ns; };
+inline ScanChoice scan_choice_for(long long U, long long S, bool ckpt) {
+    if (ckpt || S <= 0) return {0, 0, 0};
+    if (U < 16 * S) return {0, 0, 0};      // under four units per sub-partition nothing saturates the pipe: the narrow warps' shorter steps win (batch 16: 0.211 vs 0.229 ms)
+    if (U > 36 * S) return {3, 0, 0};
+    const long long base = ((U + 3) / 4 + S - 1) / S;
+    const long long wide = 2 * ((((U + 1) / 2 + S - 1) / S + 3) / 4);
+    if (wide <= base) return {3, 0, 0};
+    const long long per_cta = (((U + S - 1) / S + 1) / 2 + 1) & ~1LL;      // units per CTA, two CTAs per SM, even
+    for (int nd = 8; nd >= 4; nd -= 4) {                                   // wide warps in multiples of 4 (one per sub-partition), at most 10 warps
+        const long long ns = per_cta - 2 * nd;
+        if (ns >= 0 && (ns & 1) == 0 && nd + ns <= 10 && per_cta / 2 <= base) return {5, nd, (int)ns};
+    }
+    return {0, 0, 0};
+}
+
 template <typename T> int try_launch_scan_fwd_tpc2(const zg_scan_params &p, cudaStream_t stream);   // scan_fwd_tpc2.cuh
 template <typename T> int try_launch_scan_fwd_tma(const zg_scan_params &p, cudaStream_t stream);    // scan_fwd_tma.cuh
 

@@ -676,26 +676,12 @@ template <typename T> inline int wp_dispatch(const zg_scan_params &p, cudaStream
 // 32-channel warps when they quantise no worse than the CTA-wide kernel (FacesHQ-1024 layer shape: 6 = 6, measured - 7 %), else
 // mixed CTAs when those do (config 2: U = 5120 -> 18 units per CTA = 8 + 2 warps, 9 = 9, measured - 8 %), else the CTA-wide kernel
 // (batch 16: 3 against 4).  The training forward (checkpoints) keeps the CTA-wide kernel.
-struct ScanChoice { int mode, nd, ns; };
 inline ScanChoice scan_auto_choice(const zg_scan_params &p) {
-    if (p.ckpt) return {0, 0, 0};
     static int sms_dev[64] = {};
     int dev = 0;
     cudaGetDevice(&dev);
     if (!sms_dev[dev & 63]) cudaDeviceGetAttribute(&sms_dev[dev & 63], cudaDevAttrMultiProcessorCount, dev);
-    const long long S = sms_dev[dev & 63] > 0 ? sms_dev[dev & 63] : 148;
-    const long long U = (long long)(p.dim / 16) * p.batch;
-    if (U < 16 * S) return {0, 0, 0};      // under four units per sub-partition nothing saturates the pipe: the narrow warps' shorter steps win (batch 16: 0.211 vs 0.229 ms)
-    if (U > 36 * S) return {3, 0, 0};
-    const long long base = ((U + 3) / 4 + S - 1) / S;
-    const long long wide = 2 * ((((U + 1) / 2 + S - 1) / S + 3) / 4);
-    if (wide <= base) return {3, 0, 0};
-    const long long per_cta = (((U + S - 1) / S + 1) / 2 + 1) & ~1LL;      // units per CTA, two CTAs per SM, even
-    for (int nd = 8; nd >= 4; nd -= 4) {                                   // wide warps in multiples of 4 (one per sub-partition), at most 10 warps
-        const long long ns = per_cta - 2 * nd;
-        if (ns >= 0 && (ns & 1) == 0 && nd + ns <= 10 && per_cta / 2 <= base) return {5, nd, (int)ns};
-    }
-    return {0, 0, 0};
+    return scan_choice_for((long long)(p.dim / 16) * p.batch, sms_dev[dev & 63] > 0 ? sms_dev[dev & 63] : 148, p.ckpt != nullptr);
 }
 
 // host-side eligibility test + launch; returns -1 when the call does not fit the specialisation (never for a fused request:
