@@ -4,9 +4,9 @@ LDGSTS = cp.async, HMMA = mma.sync, MUFU, FFMA2 ...) and the instruction total.
     python scripts/sass_opcodes.py > profiles/r02_sass_opcodes.txt"""
 import collections, os, re, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-OBJS = ["gemm_tcgen05.o", "scan_fwd_bf16.o", "conv1d.o", "norm.o"]
+OBJS = ["gemm_tcgen05.o", "scan_fwd_bf16.o", "scan_fwd_wp_bf16.o", "scan_fwd_wp2_bf16.o", "scan_fwd_wph_bf16.o", "conv1d.o", "norm.o"]
 WANT = ["UTCHMMA", "UTMALDG", "UTMASTG", "LDTM", "UTCBAR", "UBLKCP", "SYNCS", "LDGSTS", "ARRIVES", "HMMA", "LDSM", "MUFU", "FFMA2", "FMUL2", "FADD2", "BAR"]
-KEEP = re.compile(r"gemm_bf16_tn_kernel|scan_fwd_tma_kernel|scan_fwd_tpc2_kernel|conv_fwd_tok4_kernel|block_tail_kernel")
+KEEP = re.compile(r"gemm_bf16_tn_kernel|scan_fwd_tma_kernel|scan_fwd_tpc2_kernel|scan_fwd_wp_kernel|scan_fwd_wp2_kernel|scan_fwd_wph_kernel|conv_fwd_tok4_kernel|block_tail_kernel|block_tail_row4_kernel")
 for o in OBJS:
     path = os.path.join(ROOT, "build", "obj", o)
     txt = subprocess.run(["cuobjdump", "-sass", path], capture_output=True, text=True).stdout
