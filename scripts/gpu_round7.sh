@@ -14,6 +14,11 @@ echo "== timings"
   for cfg in "16 1024 1280" "32 1024 1280" "32 4096 1536" "256 256 1536" "4096 16 1536"; do set -- $cfg
     BS=$1 SEQ=$2 EDIM=$3 ZG_SCAN_WP=0 sw; BS=$1 SEQ=$2 EDIM=$3 sw; BS=$1 SEQ=$2 EDIM=$3 ZIGMA_B200_LIB=$EXP sw
   done ) | tee gpurun_out/scan_auto_sweep.log
+echo "== conv row-prefetch experiment (libzigma_expconvpf*.so)"
+( timeout 120 python scripts/conv_sweep.py 2>&1 | tail -1
+  for v in convpf6 convpf5 convpf4r; do echo -n "$v: "; ZIGMA_B200_LIB=$PWD/zigma_b200/lib/libzigma_exp$v.so timeout 120 python scripts/conv_sweep.py 2>&1 | tail -1; done
+  timeout 120 python scripts/conv_sweep.py 2>&1 | tail -1 ) | tee gpurun_out/conv_prefetch_sweep.log
+for v in convpf6 convpf5; do ZIGMA_B200_LIB=$PWD/zigma_b200/lib/libzigma_exp$v.so timeout 600 python -m pytest tests/test_gpu_ops.py -m gpu -q -x -k "conv" -p no:cacheprovider > gpurun_out/pytest_$v.log 2>&1; echo "pytest conv ($v) rc=$?"; tail -2 gpurun_out/pytest_$v.log; done
 echo "== ncu full (default library, kernel chosen per call)"
 FUSED=0 timeout 300 ncu --set full --clock-control none --import-source on -k regex:scan_fwd_ -s 3 -c 1 -f -o gpurun_out/r02f_scan_auto python scripts/scan_sweep.py > gpurun_out/ncu_auto.log 2>&1; echo "ncu rc=$?"
 echo "== pytest -m gpu (all), default library"

@@ -128,6 +128,9 @@ __global__ void __launch_bounds__(128, 5) conv_fwd_dimc_kernel(const zg_conv_par
 // the generic kernel's 28 (ncu round 1: the generic kernel was instruction-issue bound at 52 % issue
 // utilisation, 130 us for 335 MB).
 template <typename T>
+#ifndef ZG_CONV_PREFETCH
+#define ZG_CONV_PREFETCH 0  // 1: software-pipelined row fetches (timing experiment, scripts/build_exp.sh)
+#endif
 #ifndef ZG_CONV_MINB
 #define ZG_CONV_MINB 8      // (64 registers, 8 CTAs per SM: 74.0 us vs 75.4 at 6; fetching 4 rows per batch instead of 8: 83-88 us)
 #endif
@@ -184,15 +187,11 @@ __global__ void __launch_bounds__(128, ZG_CONV_MINB) conv_fwd_tok4_kernel(const 
 #define ZG_CONV_RB4 CONV_RB
 #endif
     constexpr int RB4 = ZG_CONV_RB4;       // rows fetched per batch of independent loads in this kernel
-#pragma unroll 1
-    for (int lb = 0; lb < CONV_LCH; lb += RB4) {
+    auto compute_batch = [&](int lb, const uint2 (&raw)[RB4]) {
         if (seg > 0 && lb > 0 && ((l0 + lb) % seg) == 0) {      // a new segment starts with this batch of rows: zero history
 #pragma unroll
             for (int h = 0; h < 2; ++h) x1[h] = x2[h] = x3[h] = make_float2(0.f, 0.f);
         }
-        uint2 raw[RB4];
-#pragma unroll
-        for (int j = 0; j < RB4; ++j) raw[j] = *row_ptr(l0 + lb + j);
 #pragma unroll
         for (int j = 0; j < RB4; ++j) {
             zg_f2 x0[2];
@@ -218,7 +217,34 @@ __global__ void __launch_bounds__(128, ZG_CONV_MINB) conv_fwd_tok4_kernel(const 
             }
             *reinterpret_cast<uint2 *>(out + (lb + j) * osl) = o;
         }
+    };
+#if ZG_CONV_PREFETCH
+    // software-pipelined: the rows of batch k + 1 are in flight while batch k is computed (ncu of the plain loop: long_scoreboard
+    // 5.4 warps per issue -- every warp waits for its own batch before it computes anything)
+    static_assert((CONV_LCH / RB4) % 2 == 0, "an even number of batches");
+    uint2 ra[RB4], rb[RB4];
+#pragma unroll
+    for (int j = 0; j < RB4; ++j) ra[j] = *row_ptr(l0 + j);
+#pragma unroll 1
+    for (int lb = 0; lb < CONV_LCH; lb += 2 * RB4) {
+#pragma unroll
+        for (int j = 0; j < RB4; ++j) rb[j] = *row_ptr(l0 + lb + RB4 + j);
+        compute_batch(lb, ra);
+        if (lb + 2 * RB4 < CONV_LCH) {
+#pragma unroll
+            for (int j = 0; j < RB4; ++j) ra[j] = *row_ptr(l0 + lb + 2 * RB4 + j);
+        }
+        compute_batch(lb + RB4, rb);
     }
+#else
+#pragma unroll 1
+    for (int lb = 0; lb < CONV_LCH; lb += RB4) {
+        uint2 raw[RB4];
+#pragma unroll
+        for (int j = 0; j < RB4; ++j) raw[j] = *row_ptr(l0 + lb + j);
+        compute_batch(lb, raw);
+    }
+#endif
 }
 
 // forward, seq-contiguous
