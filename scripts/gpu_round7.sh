@@ -9,6 +9,8 @@ echo "== timings"
   ZG_SCAN_WP=0 sw
   ZG_SCAN_WP=0 ZIGMA_B200_LIB=$EXP sw
   ZG_SCAN_WP=3 ZIGMA_B200_LIB=$EXP sw
+  for k in 1 2 4 8 16; do ZG_SCAN_WP_SYNC=$k sw; done          # staggered fairness barrier every k stages (mixed CTAs)
+  ZG_SCAN_WP=1 ZG_SCAN_WP_WARPS=18 ZG_SCAN_WP_SYNC=4 sw
   sw
   ZIGMA_B200_LIB=$EXP sw
   for cfg in "16 1024 1280" "32 1024 1280" "32 4096 1536" "256 256 1536" "4096 16 1536"; do set -- $cfg

@@ -202,7 +202,7 @@ template <typename T> __device__ __forceinline__ void pt_mma_k8(float &d0, float
 // exp2(delta' A) of step t + 1 -- which depend on nothing but (delta', A) -- are issued BEFORE the FMA part of step t.
 template <int NP, int TPC, int PITCH = PT_F32ROW>
 __device__ __forceinline__ void pt_main_stage(const unsigned char *__restrict__ ddu_c, const float *__restrict__ bcf_p, unsigned char *__restrict__ ypart, int ypitch,
-                                              zg_f2 (&h2)[8 / TPC], const zg_f2 (&Al2p)[8 / TPC], bool store = true) {
+                                              zg_f2 (&h2)[8 / TPC], const zg_f2 (&Al2p)[8 / TPC], bool store = true, int sync_step = -1, int bar_threads = 0) {
     constexpr int NPAIR = 8 / TPC, NQ = 4 / TPC;           // state pairs per thread; float4 loads of B (and of C) per step
     auto decay = [&](float dlx, zg_f2 (&a)[NPAIR]) {
         const zg_f2 dl = zg_splat2(dlx);
@@ -243,6 +243,8 @@ __device__ __forceinline__ void pt_main_stage(const unsigned char *__restrict__ 
             y2 = zg_fma2(Cp[q], h2[q], y2);
         }
         *reinterpret_cast<float *>(ypart + t * ypitch) = y2.x + y2.y;
+        // staggered fairness barrier of the warp-private kernels (scan_fwd_wp.cuh): warp w of a CTA arrives after step w % 8
+        if (t == sync_step) asm volatile("bar.sync 1, %0;" ::"r"(bar_threads) : "memory");
         if (t + 1 < PT_TL) {
 #pragma unroll
             for (int q = 0; q < NPAIR; ++q) a_cur[q] = a_nxt[q];

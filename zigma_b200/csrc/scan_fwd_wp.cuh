@@ -46,10 +46,12 @@ struct WpLayout {                     // per warp
 
 // The work of one warp: 16 channels [e0, e0 + 16) of group g of batch row b, all seqlen steps.  `smem`: the warp's WpLayout bytes.
 // sync_every = K > 0: the cta_warps warps of the CTA that have work meet at a named barrier every K stages.  They exchange nothing --
-// the barrier is a fairness throttle (see wp_pick_shape; measured: it only costs).
+// the barrier is a fairness throttle (see wp_pick_shape).  The warp arrives after step `sync_step` of the stage's recurrence loop: the
+// callers hand out different steps (warp index % 8), so that the barrier equalises the warps' progress WITHOUT aligning their phases
+// (a barrier at the stage boundary puts every warp into the MUFU-heavy recurrence at the same time: measured, every setting lost).
 template <typename T, bool CKPT, bool PLAIN, bool TMA, int NPOLY>
 __device__ __forceinline__ void wp_body(const zg_scan_params &p, const PtMaps &maps, unsigned char *smem, const int lane, const int b, const int g, const int e0,
-                                        const int sync_every, const int cta_warps) {
+                                        const int sync_every, const int cta_warps, const int sync_step = 0) {
     static_assert(sizeof(T) == 2, "16-bit I/O only");
     using LY = WpLayout;
     constexpr int NSTAGE = LY::NSTAGE, TL = PT_TL, TILE = LY::TILE, NPAIR = 4;
@@ -197,8 +199,10 @@ __device__ __forceinline__ void wp_body(const zg_scan_params &p, const PtMaps &m
     int slot = 0, nslot = 1;
     uint32_t npar = 0;                                             // phase parity of the next stage's slot
     for (int s = 0; s < nstages; ++s) {
-        if (NPOLY > 0 && use_poly) pt_main_stage<NPOLY, 2, LY::DDU_ROW>(ddu_c, bcf_p, ypart, LY::DDU_ROW, h2, Al2p);
-        else pt_main_stage<0, 2, LY::DDU_ROW>(ddu_c, bcf_p, ypart, LY::DDU_ROW, h2, Al2p);
+        int sstep = -1;                                 // every warp of the CTA runs the same number of stages
+        if (sync_every > 0 && --sync_left == 0) { sync_left = sync_every; sstep = sync_step; }
+        if (NPOLY > 0 && use_poly) pt_main_stage<NPOLY, 2, LY::DDU_ROW>(ddu_c, bcf_p, ypart, LY::DDU_ROW, h2, Al2p, true, sstep, cta_warps * 32);
+        else pt_main_stage<0, 2, LY::DDU_ROW>(ddu_c, bcf_p, ypart, LY::DDU_ROW, h2, Al2p, true, sstep, cta_warps * 32);
         if constexpr (CKPT) {       // recompute seeds of the backward: state after every 8 steps, (batch, n_ckpt, dim, dstate)
             float4 *dst = reinterpret_cast<float4 *>(p.ckpt + (((int64_t)b * (L >> 3) + s) * E + e) * 16 + 8 * part);
             dst[0] = make_float4(h2[0].x, h2[0].y, h2[1].x, h2[1].y);
@@ -221,10 +225,6 @@ __device__ __forceinline__ void wp_body(const zg_scan_params &p, const PtMaps &m
         issue_stage(slot);
         slot = nslot;
         if (++nslot == NSTAGE) { nslot = 0; npar ^= 1; }
-        if (sync_every > 0 && --sync_left == 0) {       // every warp of the CTA runs the same number of stages
-            sync_left = sync_every;
-            asm volatile("bar.sync 1, %0;" ::"r"(cta_warps * 32) : "memory");
-        }
     }
     if (p.last_state) {
         float4 *dst = reinterpret_cast<float4 *>(p.last_state + ((int64_t)b * E + e) * 16 + 8 * part);
@@ -247,7 +247,7 @@ __global__ void __launch_bounds__(32 * WP_MAX_WARPS, 2) scan_fwd_wp_kernel(const
     // warps of this CTA that have work (the last CTA may be short): the participants of the fairness barrier
     const int cta_warps = min((int)(blockDim.x >> 5), units * p.batch - (int)blockIdx.x * (int)(blockDim.x >> 5));
     const int unit = wu % units;
-    wp_body<T, CKPT, PLAIN, TMA, NPOLY>(p, maps, smem_all + warp * WpLayout::WARP_BYTES, lane, wu / units, unit / units_per_group, unit * WP_CH, sync_every, cta_warps);
+    wp_body<T, CKPT, PLAIN, TMA, NPOLY>(p, maps, smem_all + warp * WpLayout::WARP_BYTES, lane, wu / units, unit / units_per_group, unit * WP_CH, sync_every, cta_warps, warp & 7);
 }
 
 // CTA shape.  The warps exchange nothing, so the CTA size is free; what it decides is how the SM's warp schedulers treat the

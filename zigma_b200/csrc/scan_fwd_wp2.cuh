@@ -41,7 +41,7 @@ struct Wp2Layout {                    // per warp
 // Software-pipelined like pt_main_stage: the 16 decay factors of step t + 1 are issued before the FMAs of step t.
 template <int PITCH>
 __device__ __forceinline__ void wp2_main_stage(const unsigned char *__restrict__ ddu_j, const float *__restrict__ bq, unsigned char *__restrict__ ypart,
-                                               zg_f2 (&h)[2][4], const zg_f2 (&Al)[2][4]) {
+                                               zg_f2 (&h)[2][4], const zg_f2 (&Al)[2][4], int sync_step = -1, int bar_threads = 0) {
     auto decay = [&](float dlx, const zg_f2 (&al)[4], zg_f2 (&a)[4]) {
         const zg_f2 dl = zg_splat2(dlx);
 #pragma unroll
@@ -78,6 +78,7 @@ __device__ __forceinline__ void wp2_main_stage(const unsigned char *__restrict__
         }
         // (both lanes of the channel pair have read the 16 bytes -- one converged LDS -- before either overwrites its half)
         *reinterpret_cast<float2 *>(ypart + t * PITCH) = make_float2(y0.x + y0.y, y1.x + y1.y);
+        if (t == sync_step) asm volatile("bar.sync 1, %0;" ::"r"(bar_threads) : "memory");      // staggered fairness barrier, see wp_body
         if (t + 1 < PT_TL) {
 #pragma unroll
             for (int q = 0; q < 4; ++q) { a0[q] = n0[q]; a1[q] = n1[q]; }
@@ -87,7 +88,8 @@ __device__ __forceinline__ void wp2_main_stage(const unsigned char *__restrict__
 
 // The work of one warp: 32 channels [e0, e0 + 32) of group g of batch row b, all seqlen steps.  `smem`: the warp's Wp2Layout bytes.
 template <typename T, bool CKPT, bool PLAIN, bool TMA>
-__device__ __forceinline__ void wp2_body(const zg_scan_params &p, const PtMaps &maps, unsigned char *smem, const int lane, const int b, const int g, const int e0) {
+__device__ __forceinline__ void wp2_body(const zg_scan_params &p, const PtMaps &maps, unsigned char *smem, const int lane, const int b, const int g, const int e0,
+                                         const int sync_every = 0, const int cta_warps = 0, const int sync_step = 0) {
     static_assert(sizeof(T) == 2, "16-bit I/O only");
     using LY = Wp2Layout;
     constexpr int NSTAGE = LY::NSTAGE, TL = PT_TL, TILE = LY::TILE, NITEM = 4;
@@ -101,6 +103,7 @@ __device__ __forceinline__ void wp2_body(const zg_scan_params &p, const PtMaps &
     const bool has_z = PLAIN ? true : (p.z != nullptr);
     const bool softplus = PLAIN ? true : ((p.flags & ZG_SCAN_DELTA_SOFTPLUS) != 0);
     const int nstages = L / TL;
+    int sync_left = sync_every;
 
     // ---- per-thread constants -----------------------------------------------------------------------------------
     zg_f2 Al2p[2][4], h2[2][4];
@@ -236,7 +239,9 @@ __device__ __forceinline__ void wp2_body(const zg_scan_params &p, const PtMaps &
     int slot = 0, nslot = 1;
     uint32_t npar = 0;                                             // phase parity of the next stage's slot
     for (int s = 0; s < nstages; ++s) {
-        wp2_main_stage<LY::DDU_ROW>(ddu_j, bq, ypart, h2, Al2p);
+        int sstep = -1;
+        if (sync_every > 0 && --sync_left == 0) { sync_left = sync_every; sstep = sync_step; }
+        wp2_main_stage<LY::DDU_ROW>(ddu_j, bq, ypart, h2, Al2p, sstep, cta_warps * 32);
         if constexpr (CKPT) {       // recompute seeds of the backward: state after every 8 steps, (batch, n_ckpt, dim, dstate)
 #pragma unroll
             for (int c = 0; c < 2; ++c) {
