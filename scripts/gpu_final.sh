@@ -10,5 +10,7 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --c
 echo "== ncu full (scan, config 2 layer shape)"
 FUSED=0 timeout 300 ncu --set full --clock-control none --import-source on -k regex:scan_fwd_ -s 3 -c 1 -f -o gpurun_out/r02g_scan_final python scripts/scan_sweep.py > gpurun_out/ncu_final.log 2>&1; echo "ncu rc=$?"
 FUSED=0 timeout 100 python scripts/scan_sweep.py | tail -1
+echo "== staggered fairness barrier every k stages (mixed CTAs)"
+( for k in 1 2 4 8 16; do ZG_SCAN_WP_SYNC=$k FUSED=0 timeout 100 python scripts/scan_sweep.py | tail -1; done; ZG_SCAN_WP=3 ZG_SCAN_WP_SYNC=4 BS=32 SEQ=4096 EDIM=1536 FUSED=0 timeout 100 python scripts/scan_sweep.py | tail -1; BS=32 SEQ=4096 EDIM=1536 FUSED=0 timeout 100 python scripts/scan_sweep.py | tail -1 ) | tee gpurun_out/scan_sync_sweep.log
 timeout 100 python scripts/conv_sweep.py | tail -1
 echo done

@@ -157,7 +157,6 @@ __device__ __forceinline__ void wp2_body(const zg_scan_params &p, const PtMaps &
         u_step = (uint32_t)p.u_sl * (2u * TL);
         d_step = (uint32_t)p.delta_sl * (2u * TL);
     }
-    const uint64_t bc_policy = zg_l2_policy_evict_last();            // the B|C rows are re-read by every warp of the batch row: keep them in L2
     int s_issue = 0;                                               // stages are issued in order
     auto issue_stage = [&](int slot) {                             // all lanes
         if (s_issue >= nstages) return;
@@ -181,7 +180,7 @@ __device__ __forceinline__ void wp2_body(const zg_scan_params &p, const PtMaps &
             const int ln = l0 + TL + zr;
             zrow_next = (ln < L) ? (zmap ? zmap[ln] : ln) : 0;
         }
-        zg_cp_async16_hint(raw + 3 * TILE + lane * 16, bc_src, bc_policy);
+        zg_cp_async16(raw + 3 * TILE + lane * 16, bc_src);
         bc_src += bc_step;
         pt_cp_async_arrive(bar);
         ++s_issue;

@@ -104,17 +104,6 @@ __device__ __forceinline__ void zg_cp_async16(void *smem_dst, const void *gmem_s
     const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem_src) : "memory");
 }
-// the same with an L2 eviction-priority hint (createpolicy): rows that many warps re-read (the B|C rows of the scan) stay in L2
-// while the streamed tensors pass through
-__device__ __forceinline__ uint64_t zg_l2_policy_evict_last() {
-    uint64_t pol;
-    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
-    return pol;
-}
-__device__ __forceinline__ void zg_cp_async16_hint(void *smem_dst, const void *gmem_src, uint64_t policy) {
-    const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(s), "l"(gmem_src), "l"(policy) : "memory");
-}
 __device__ __forceinline__ void zg_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void zg_cp_async_wait() {
     asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
