@@ -232,6 +232,13 @@ typedef struct {
 
 int zg_block_tail_fwd(const zg_block_tail_params *p, void *stream);
 
+/* The FIRST tail of a forward with the positional embedding folded in: `mix` is ONE (seqlen, dim) table shared by every
+ * batch element, gate / rowmap / residual are NULL:
+ *     hidden = round_to_dtype(x + mix[l, :])        -- the reference's `x = x + self.pos_embed` (model_zigma.py:941)
+ * then r = hidden, normed, modded as above.  Saves the elementwise pass over (batch, seqlen, dim) that the add costs as a
+ * kernel of its own.  dim <= 2048. */
+int zg_block_tail_fwd_pe(const zg_block_tail_params *p, void *stream);
+
 /* Backward of the block tail (training).  With the forward's
  *     hidden = x + gate * mix[rowmap];  r = residual + hidden;  normed = r * rstd * norm_w;  modded = normed * (1 + scale) + shift
  * and incoming gradients d_residual_out (fp32), d_normed, d_modded (dtype; any of them may be NULL = zero):

@@ -82,6 +82,24 @@ def test_zigma_forward_bf16():
     check_close(out, g32["out"], "ZigMa.forward tiny bf16 vs reference fp32", rtol=5e-2, atol=5e-2, scale_atol=False, max_strict_viol=1.0)
 
 
+def test_engine_pos_embed_folded_into_first_tail_bit_identical(monkeypatch):
+    """The engine adds pos_embed inside its first fused tail (zg_block_tail_fwd_pe); ZIGMA_FOLD_PE=0 runs the eager add of
+    ZigMa.embed (model_zigma.py:941) instead.  Same rounding point -> the two evaluations agree bit for bit; the folded one
+    launches one zigma_b200 kernel of the same count (the add was a torch kernel) and stays on the reference's bf16 output."""
+    from zigma_b200 import ZigMa
+    g, cfg, shapes = model_case("tiny_zigzag8_bf16")
+    assert cfg.get("use_pe", 0) in (1, 2)
+    x, tt, y = model_io(cfg, g["out"].shape[0])
+    outs = []
+    for fold in ("1", "0"):
+        monkeypatch.setenv("ZIGMA_FOLD_PE", fold)
+        m, _ = _build(cfg, shapes, torch.bfloat16)
+        with torch.no_grad():
+            outs.append(m(x.to(DEV).bfloat16(), tt.to(DEV).bfloat16()))
+    assert torch.equal(outs[0], outs[1])
+    check_close(outs[0], g["out"], "ZigMa.forward tiny bf16, pos_embed folded", rtol=5e-2, atol=5e-2, scale_atol=False, max_strict_viol=1.0)
+
+
 def test_zigma_forward_sweep2_bf16_fused_flip_add():
     """scan_type v2 in bf16: the engine folds `y_fwd + y_bwd.flip(1)` into the second scan kernel (OUT_REVERSE | OUT_ACCUMULATE)
     when the layer fits the hot-path kernel (D = 128 here: dt_rank 8, 16-byte aligned B / C columns); result vs the fp32 oracle

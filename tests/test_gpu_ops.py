@@ -567,6 +567,27 @@ def test_add_norm_backward_vs_autograd_oracle():
             check_close(b.grad, br.grad, "norm bwd dbias", atol=1e-4)
 
 
+def test_block_tail_pos_embed_fold_matches_separate_add():
+    """zg_block_tail_fwd_pe (first tail, positional embedding as a broadcast mix table, no gate) is bit-identical to the eager
+    `tokens + pos_embed` (model_zigma.py:941) followed by the plain first tail, and agrees with the oracle's add + RMSNorm."""
+    from zigma_b200.engine import block_tail
+    for dtype, D in ((torch.bfloat16, 640), (torch.float16, 768), (torch.float32, 64), (torch.bfloat16, 1536)):
+        torch.manual_seed(11)
+        Bt, L = 3, 48
+        tok, pe = torch.randn(Bt, L, D).to(dtype), (0.5 * torch.randn(1, L, D)).to(dtype)
+        mods = (0.3 * torch.randn(Bt, 3 * D)).to(dtype)
+        nw = (1 + 0.1 * torch.randn(D)).to(dtype)
+        md, nwd = mods.to(DEV), nw.to(DEV)
+        r0, n0, m0 = block_tail((tok.to(DEV) + pe.to(DEV)).contiguous(), None, None, md[:, :D], md[:, D:2 * D], nwd, None, None, 1e-5)
+        r1, n1, m1 = block_tail(tok.to(DEV), pe.to(DEV).reshape(L, D), None, md[:, :D], md[:, D:2 * D], nwd, None, None, 1e-5, mix_bcast=True)
+        assert torch.equal(r0, r1) and torch.equal(n0, n1) and torch.equal(m0, m1), f"{dtype} D={D}"
+        normed_ref, res_ref = zo.add_norm(tok + pe, nw, None, None, True, True, 1e-5, True)
+        check_close(r1, res_ref, f"block_tail_pe residual {dtype}")
+        check_close(n1, normed_ref, f"block_tail_pe normed {dtype}", **(dict(rtol=1e-3) if dtype == torch.float32 else dict(rtol=8e-3, max_strict_viol=1.0)))
+    with pytest.raises(RuntimeError):      # the table takes no gate
+        block_tail(tok.to(DEV), pe.to(DEV).reshape(L, D), md[:, :D], md[:, :D], md[:, :D], nwd, None, None, 1e-5, mix_bcast=True)
+
+
 def test_block_tail_matches_unfused_chain():
     """zg_block_tail_fwd == x + gate*mix[perm_rev] -> add+RMSNorm -> modulate done with separate
     torch ops on the CPU in the same dtype (the reference's unfused Block.forward chain)."""

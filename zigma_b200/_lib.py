@@ -93,7 +93,7 @@ class AdamWParams(C.Structure):
 
 EXPORTS = ["zg_abi_version", "zg_last_error", "zg_launch_count", "zg_last_scan_kernel", "zg_scan_kernel_choice", "zg_selective_scan_fwd", "zg_selective_scan_bwd",
            "zg_causal_conv1d_fwd", "zg_causal_conv1d_bwd", "zg_add_norm_fwd", "zg_add_norm_bwd",
-           "zg_block_tail_fwd", "zg_block_tail_bwd", "zg_gemm_bf16_tn", "zg_adamw_ema_step"]
+           "zg_block_tail_fwd", "zg_block_tail_fwd_pe", "zg_block_tail_bwd", "zg_gemm_bf16_tn", "zg_adamw_ema_step"]
 
 _lib = None
 

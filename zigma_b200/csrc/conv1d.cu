@@ -131,6 +131,9 @@ template <typename T>
 #ifndef ZG_CONV_PREFETCH
 #define ZG_CONV_PREFETCH 0  // 1: software-pipelined row fetches (timing experiment, scripts/build_exp.sh)
 #endif
+#ifndef ZG_CONV_RCP_FMA
+#define ZG_CONV_RCP_FMA 0
+#endif
 #ifndef ZG_CONV_MINB
 #define ZG_CONV_MINB 8      // (64 registers, 8 CTAs per SM: 74.0 us vs 75.4 at 6; fetching 4 rows per batch instead of 8: 83-88 us)
 #endif
@@ -203,7 +206,20 @@ __global__ void __launch_bounds__(128, ZG_CONV_MINB) conv_fwd_tok4_kernel(const 
                 acc = zg_fma2(w[2][h], x2[h], acc);
                 acc = zg_fma2(w[1][h], x1[h], acc);
                 acc = zg_fma2(w[0][h], x0[h], acc);
+#if ZG_CONV_RCP_FMA
+                if (p.silu) {      // timing experiment (scripts/build_exp.sh): the sigmoid's reciprocal on the FMA pipe (integer seed + 3 Newton steps), 1 MUFU per value
+                    float2 t = zg_mul2(acc, zg_splat2(-ZG_LOG2E));
+                    t.x = fminf(t.x, 126.f); t.y = fminf(t.y, 126.f);
+                    const float2 d = zg_add2(make_float2(zg_ex2(t.x), zg_ex2(t.y)), zg_splat2(1.f));
+                    float2 r = make_float2(__int_as_float(0x7EF311C7 - __float_as_int(d.x)), __int_as_float(0x7EF311C7 - __float_as_int(d.y)));
+                    const float2 nd = make_float2(-d.x, -d.y), one = zg_splat2(1.f);
+#pragma unroll
+                    for (int it = 0; it < 3; ++it) r = zg_fma2(r, zg_fma2(nd, r, one), r);
+                    acc = zg_mul2(acc, r);
+                }
+#else
                 if (p.silu) { acc.x = zg_silu(acc.x); acc.y = zg_silu(acc.y); }
+#endif
                 x3[h] = x2[h]; x2[h] = x1[h]; x1[h] = x0[h];
                 unsigned packed;
                 if (std::is_same<T, __nv_bfloat16>::value) {

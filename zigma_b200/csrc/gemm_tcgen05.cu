@@ -175,6 +175,22 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&v)[32])
         : "r"(taddr));
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+// the same load without the wait: the caller issues several and waits once (tmem_ld_wait) before it touches the registers
+__device__ __forceinline__ void tmem_ld_32x32_nowait(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+          "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+          "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+          "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+#ifndef ZG_GEMM_EPI_LD2
+#define ZG_GEMM_EPI_LD2 0      // 1: both 32-column halves of a 64-column epilogue chunk are loaded from TMEM before ONE wait (timing experiment)
+#endif
 
 struct GemmArgs {
     __nv_bfloat16 *C;
@@ -367,10 +383,20 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                         else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");     // one chunk per tile: same buffer every time
                     }
                     __syncwarp();
+#if ZG_GEMM_EPI_LD2
+                    uint32_t vv[2][32];
+                    tmem_ld_32x32_nowait(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + c0), vv[0]);
+                    tmem_ld_32x32_nowait(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + c0 + 32), vv[1]);
+                    tmem_ld_wait();
+#endif
 #pragma unroll
                     for (int hh = 0; hh < 2; ++hh) {
+#if ZG_GEMM_EPI_LD2
+                        uint32_t (&v)[32] = vv[hh];
+#else
                         uint32_t v[32];
                         tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + c0 + hh * 32), v);
+#endif
                         const int col0 = n_blk * BN + c0 + hh * 32;
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {

@@ -285,6 +285,10 @@ template <typename T> __device__ __forceinline__ Raw4<T> ldraw(const T *p, int64
     r.v = *reinterpret_cast<const decltype(r.v) *>(p + i);
     return r;
 }
+template <typename T> __device__ __forceinline__ Raw4<T> raw_ones();       // four 1.0 in the storage format
+template <> __device__ __forceinline__ Raw4<float> raw_ones<float>() { Raw4<float> r; r.v = make_float4(1.f, 1.f, 1.f, 1.f); return r; }
+template <> __device__ __forceinline__ Raw4<__nv_bfloat16> raw_ones<__nv_bfloat16>() { Raw4<__nv_bfloat16> r; r.v = make_uint2(0x3f803f80u, 0x3f803f80u); return r; }
+template <> __device__ __forceinline__ Raw4<__half> raw_ones<__half>() { Raw4<__half> r; r.v = make_uint2(0x3c003c00u, 0x3c003c00u); return r; }
 template <typename T> __device__ __forceinline__ void cvt4(const Raw4<T> &r, float (&o)[4]);
 template <> __device__ __forceinline__ void cvt4<float>(const Raw4<float> &r, float (&o)[4]) {
     o[0] = r.v.x; o[1] = r.v.y; o[2] = r.v.z; o[3] = r.v.w;
@@ -427,7 +431,10 @@ __global__ void __launch_bounds__(128, (MAXQ <= 6) ? 6 : 1) block_tail_kernel(co
 // shared-memory reduction per statistic.  Same arithmetic and rounding points.  Measured at config 2 (672 MB per call):
 // 149.7 us (one warp per row) -> 136.5 us (this kernel, 40 registers, 12 CTAs / SM) -> 121.1 us = 5.54 TB/s = 0.84 of the measured
 // HBM peak with the scale / shift rows prefetched too (ZG_TAIL_PREFETCH_MOD); 32 registers / 16 CTAs without that prefetch: 122.0 us.
-template <typename T, int MAXQ>
+// PE (zg_block_tail_fwd_pe, the first tail of a forward): mix is the (seqlen, dim) positional-embedding table shared by every
+// batch element and there is no gate: hidden = round(tokens + pos_embed), the reference's `x = x + self.pos_embed`
+// (model_zigma.py:941), without an elementwise pass of its own.  A separate instantiation: the per-layer instance is unchanged.
+template <typename T, int MAXQ, bool PE>
 __global__ void __launch_bounds__(128, ZG_TAIL_MINB) block_tail_row4_kernel(const zg_block_tail_params p) {
     __shared__ float red[3][4];
     const int64_t row = blockIdx.x;
@@ -437,10 +444,10 @@ __global__ void __launch_bounds__(128, ZG_TAIL_MINB) block_tail_row4_kernel(cons
     const T *x = reinterpret_cast<const T *>(p.x) + row * D;
     const T *mix = nullptr;
     if (p.mix) {
-        const int64_t src = (int64_t)b * p.seqlen + (p.rowmap ? p.rowmap[l] : l);
+        const int64_t src = (PE ? 0 : (int64_t)b * p.seqlen) + (p.rowmap ? p.rowmap[l] : l);
         mix = reinterpret_cast<const T *>(p.mix) + src * D;
     }
-    const T *gate = p.gate ? reinterpret_cast<const T *>(p.gate) + (int64_t)b * p.mod_rs : nullptr;
+    const T *gate = (!PE && p.gate) ? reinterpret_cast<const T *>(p.gate) + (int64_t)b * p.mod_rs : nullptr;
     const T *shift = p.shift ? reinterpret_cast<const T *>(p.shift) + (int64_t)b * p.mod_rs : nullptr;
     const T *scale = p.scale ? reinterpret_cast<const T *>(p.scale) + (int64_t)b * p.mod_rs : nullptr;
     const T *nw = reinterpret_cast<const T *>(p.norm_w);
@@ -466,7 +473,7 @@ __global__ void __launch_bounds__(128, ZG_TAIL_MINB) block_tail_row4_kernel(cons
         const int q = tid + 128 * k;
         if (q < nq) {
             rx[k] = ldraw<T>(x, 4 * q);
-            if (mix) { rm[k] = ldraw<T>(mix, 4 * q); rg[k] = ldraw<T>(gate, 4 * q); }
+            if (mix) { rm[k] = ldraw<T>(mix, 4 * q); rg[k] = PE ? raw_ones<T>() : ldraw<T>(gate, 4 * q); }     // PE: gate = 1, round(1 * m) = m
             if (res) rr[k] = *reinterpret_cast<const float4 *>(res + 4 * q);
             rw[k] = ldraw<T>(nw, 4 * q);
 #if ZG_TAIL_PREFETCH_MOD
@@ -558,19 +565,22 @@ __global__ void __launch_bounds__(128, ZG_TAIL_MINB) block_tail_row4_kernel(cons
     }
 }
 
-template <typename T> static int block_tail_t(const zg_block_tail_params &p, cudaStream_t s) {
+template <typename T> static int block_tail_t(const zg_block_tail_params &p, cudaStream_t s, bool pe = false) {
     const int64_t nrows = (int64_t)p.batch * p.seqlen;
     static int row4 = -1;       // ZG_TAIL_ROW4=0: the round-1 kernel (one warp per row)
     if (row4 < 0) { const char *e = getenv("ZG_TAIL_ROW4"); row4 = e ? atoi(e) : 1; }
-    if (row4 && nrows <= 0x7fffffffLL && p.dim <= 2048) {
+    if ((row4 || pe) && nrows <= 0x7fffffffLL && p.dim <= 2048) {
         const unsigned g4 = (unsigned)nrows;
-        if (p.dim <= 512) block_tail_row4_kernel<T, 1><<<g4, 128, 0, s>>>(p);
-        else if (p.dim <= 1024) block_tail_row4_kernel<T, 2><<<g4, 128, 0, s>>>(p);
-        else if (p.dim <= 1536) block_tail_row4_kernel<T, 3><<<g4, 128, 0, s>>>(p);
-        else block_tail_row4_kernel<T, 4><<<g4, 128, 0, s>>>(p);
+#define ZG_TAIL4(Q) do { if (pe) block_tail_row4_kernel<T, Q, true><<<g4, 128, 0, s>>>(p); else block_tail_row4_kernel<T, Q, false><<<g4, 128, 0, s>>>(p); } while (0)
+        if (p.dim <= 512) ZG_TAIL4(1);
+        else if (p.dim <= 1024) ZG_TAIL4(2);
+        else if (p.dim <= 1536) ZG_TAIL4(3);
+        else ZG_TAIL4(4);
+#undef ZG_TAIL4
         zg_count_launch();
         return zg_check_launch("block_tail_fwd");
     }
+    if (pe) return zg_set_error("block_tail_fwd_pe: dim <= 2048 and fewer than 2^31 rows only, got dim %d", p.dim);
     const unsigned grid = (unsigned)((nrows * 32 + 127) / 128);
     // MAXQ = ceil(D / 128) exactly for the model widths of the reference zoo (368, 640, 768, 1024, 1536): the raw
     // operand vectors of a row live in registers, so an over-sized MAXQ costs occupancy (ncu round 1: 92 registers at
@@ -833,11 +843,12 @@ extern "C" int zg_add_norm_bwd(const zg_norm_bwd_params *pp, void *stream) {
     return zg_set_error("add_norm_bwd: bad dtype %d", p.dtype);
 }
 
-extern "C" int zg_block_tail_fwd(const zg_block_tail_params *pp, void *stream) {
+static int block_tail_fwd_entry(const zg_block_tail_params *pp, void *stream, bool pe) {
     ZG_REQUIRE(pp != nullptr, "block_tail_fwd: null params");
     const zg_block_tail_params &p = *pp;
     ZG_REQUIRE(p.x && p.norm_w && p.normed, "block_tail_fwd: null tensor pointer");
-    ZG_REQUIRE(!p.mix || p.gate, "block_tail_fwd: mix needs gate");
+    if (pe) ZG_REQUIRE(p.mix && !p.gate && !p.rowmap && !p.residual, "block_tail_fwd_pe: takes the (seqlen, dim) table as mix and no gate / rowmap / residual");
+    else ZG_REQUIRE(!p.mix || p.gate, "block_tail_fwd: mix needs gate");
     ZG_REQUIRE(!p.modded || (p.shift && p.scale), "block_tail_fwd: modded needs shift and scale");
     ZG_REQUIRE(p.dim > 0 && p.dim % 4 == 0 && p.dim <= 4 * 32 * zg::NORM_MAXQ, "block_tail_fwd: dim must be a multiple of 4 and <= %d, got %d",
                4 * 32 * zg::NORM_MAXQ, p.dim);
@@ -848,12 +859,15 @@ extern "C" int zg_block_tail_fwd(const zg_block_tail_params *pp, void *stream) {
     if (nrows == 0) return 0;
     cudaStream_t s = (cudaStream_t)stream;
     switch (p.dtype) {
-        case ZG_F32: return zg::block_tail_t<float>(p, s);
-        case ZG_F16: return zg::block_tail_t<__half>(p, s);
-        case ZG_BF16: return zg::block_tail_t<__nv_bfloat16>(p, s);
+        case ZG_F32: return zg::block_tail_t<float>(p, s, pe);
+        case ZG_F16: return zg::block_tail_t<__half>(p, s, pe);
+        case ZG_BF16: return zg::block_tail_t<__nv_bfloat16>(p, s, pe);
     }
     return zg_set_error("block_tail_fwd: bad dtype %d", p.dtype);
 }
+
+extern "C" int zg_block_tail_fwd(const zg_block_tail_params *pp, void *stream) { return block_tail_fwd_entry(pp, stream, false); }
+extern "C" int zg_block_tail_fwd_pe(const zg_block_tail_params *pp, void *stream) { return block_tail_fwd_entry(pp, stream, true); }
 
 extern "C" int zg_block_tail_bwd(const zg_block_tail_bwd_params *pp, void *stream) {
     ZG_REQUIRE(pp != nullptr, "block_tail_bwd: null params");

@@ -54,9 +54,11 @@ def scan_hot_path_ok(dtype, E, L, N, R):
             and (R + 2 * N) % 8 == 0 and os.environ.get("ZG_SCAN_TMA", "1") != "0")
 
 
-def block_tail(x, mix, gate, shift, scale, norm_w, residual, rowmap, eps, final=False, mod_div=1, want_modded=True, want_rstd=False):
+def block_tail(x, mix, gate, shift, scale, norm_w, residual, rowmap, eps, final=False, mod_div=1, want_modded=True, want_rstd=False,
+               mix_bcast=False):
     """zg_block_tail_fwd wrapper.  x: (Bt, L, D) contiguous; gate/shift/scale: (Bt // mod_div, D)
-    views with a common row stride.  Returns residual_out (fp32), normed, modded."""
+    views with a common row stride.  Returns residual_out (fp32), normed, modded.
+    mix_bcast: ``mix`` is one (L, D) table added to every batch element (gate None = 1): the positional embedding."""
     _lib.require_cuda(x, mix, gate, shift, scale, norm_w, residual, rowmap)
     Bt, L, D = x.shape
     if mod_div != 1:
@@ -103,7 +105,9 @@ def block_tail(x, mix, gate, shift, scale, norm_w, residual, rowmap, eps, final=
     p.dtype, p.final_layer, p.eps = _lib.dt(x), int(final), float(eps)
     rstd = torch.empty((Bt * L,), dtype=torch.float32, device=x.device) if want_rstd else None
     p.rstd = _lib.ptr(rstd)
-    _lib.call("zg_block_tail_fwd", p)
+    if mix_bcast and (mix is None or mix.numel() != L * D or gate is not None or rowmap is not None or residual is not None):
+        raise RuntimeError("block_tail: mix_bcast takes a (seqlen, dim) mix table and no gate / rowmap / residual")
+    _lib.call("zg_block_tail_fwd_pe" if mix_bcast else "zg_block_tail_fwd", p)
     if want_rstd:
         return res_out, normed, modded, rstd
     return res_out, normed, modded
@@ -307,15 +311,25 @@ class ZigMaEngine:
     # ---- whole forward -----------------------------------------------------------------------------
     def _forward_impl(self, x, t, y):
         m = self.m
-        hs, c, text = m.embed(x, t, y, tokens=self._patch_embed(x))
+        tokens = self._patch_embed(x)
+        # `tokens + pos_embed` (model_zigma.py:941) inside the first tail (mix = the (L, D) table, no gate) instead of an
+        # elementwise pass of its own: same rounding (one add in the token dtype).  Not with a temporal embedding on top.
+        pe = None
+        if (tokens is not None and m.use_pe in (1, 2) and not (m.video_frames > 0 and m.tpe) and m.pos_embed.dtype == tokens.dtype
+                and tokens.shape[-1] <= 2048 and os.environ.get("ZIGMA_FOLD_PE", "1") != "0"):
+            pe = m.pos_embed.detach().reshape(-1, m.pos_embed.shape[-1]).contiguous()
+        hs, c, text = m.embed(x, t, y, tokens=tokens, add_pos=pe is None)
         hs = hs.contiguous()
         B, L, D = hs.shape
+        if pe is not None and pe.shape[0] != L:
+            raise RuntimeError(f"pos_embed has {pe.shape[0]} rows, the model {L} tokens")
         depth = len(self.layers)
         nmod = 6 if m.has_text else 3          # (+ shift, scale, gate of the text cross-attention branch)
         mods = _linear(F.silu(c), self.ada_w, self.ada_b).view(B, depth, nmod, D)  # shift, scale, gate per block (one GEMM for all)
         eps = m.blocks[0].norm.eps
         lay0 = self.layers[0]
-        residual, normed, modded = block_tail(hs, None, None, mods[:, 0, 0], mods[:, 0, 1], lay0["norm_w"], None, None, eps)
+        residual, normed, modded = block_tail(hs, pe, None, mods[:, 0, 0], mods[:, 0, 1], lay0["norm_w"], None, None, eps,
+                                              mix_bcast=pe is not None)
         for i, lay in enumerate(self.layers):
             mix, rowmap, fold = self._mixer(modded, lay)
             last = i == depth - 1

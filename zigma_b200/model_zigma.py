@@ -372,7 +372,7 @@ class ZigMa(nn.Module):
                 .reshape(x.shape[0], video_frames, c, h * p, w * p))
 
     # ---- forward ----------------------------------------------------------------------------------
-    def embed(self, hidden_states, t, y=None, tokens=None):
+    def embed(self, hidden_states, t, y=None, tokens=None, add_pos=True):
         """Everything before the blocks (model_zigma.py:923-947): tokens (B, L, D) and conditioning c.  ``tokens``: the
         patch-embedding result when the caller computed it itself (the sampling engine runs that GEMM on its tcgen05 kernel)."""
         hidden_states = self.x_embedder(hidden_states) if tokens is None else tokens
@@ -385,7 +385,7 @@ class ZigMa(nn.Module):
             c = t + self.y_embedder(y, self.training)
         else:
             c = t
-        if self.use_pe in (1, 2):
+        if self.use_pe in (1, 2) and add_pos:      # (add_pos False: the sampling engine adds the table inside its first fused tail)
             hidden_states = hidden_states + self.pos_embed
         if self.video_frames > 0 and self.tpe:
             T = self.video_frames
