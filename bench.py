@@ -329,6 +329,81 @@ def scan_roofline(name, bs, dev, step_ms=None, depth=None):
     return roof
 
 
+def other_kernel_rooflines(name, bs, dev):
+    """The other kernels of a layer of the workload, each timed alone (20 launches, CUDA events, working sets > L2) against the roofline
+    that bounds it: conv and block tail -> HBM (algorithmic bytes), the four projections -> tensor pipe (in / out) or HBM (x_proj reads,
+    dt_proj writes one (tokens, d_inner) tensor; their flops are negligible).  GEMMs also carry the library's (cuBLAS) time as the bar."""
+    import torch
+    import torch.nn.functional as F
+    from zigma_b200 import zigzag_path, reverse_permut_np
+    from zigma_b200.causal_conv1d_interface import _conv_fwd
+    from zigma_b200.engine import block_tail
+    from zigma_b200.gemm import linear_bf16
+    wl = WORKLOADS[name]
+    D = wl["cfg"]["embed_dim"]
+    E, N, R = 2 * D, 16, (D + 15) // 16
+    kind, nseq, L = wl["scan_shapes"][0]
+    Bt = bs * nseq
+    M = Bt * L
+    dtype = torch.bfloat16
+    hbm, _ = measured_peaks()
+    pk = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
+    tf_peak = float(pk.get("bf16_tflops", 1666.9))          # burst figure: each kernel is timed alone
+
+    def timeit(fn, n=20):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(n):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / n
+
+    out = []
+    side = int(round(L ** 0.5))
+    perm = torch.from_numpy(zigzag_path(side)[1]).to(dev).to(torch.int32) if (kind != "sweep" and side * side == L) else None
+    rev = torch.from_numpy(reverse_permut_np(zigzag_path(side)[1])).to(dev).to(torch.int32) if perm is not None else None
+    # conv: reads the x half of xz through the zigzag table, writes xc
+    xz = torch.randn(Bt, L, 2 * E, device=dev).to(dtype)
+    cw, cb = torch.randn(E, 4, device=dev).to(dtype), torch.randn(E, device=dev).to(dtype)
+    xc = torch.empty(Bt, L, E, device=dev, dtype=dtype).transpose(1, 2)
+    ms = timeit(lambda: _conv_fwd(xz[:, :, :E].transpose(1, 2), cw, cb, True, x_rowmap=perm, out=xc))
+    by = 2 * 2 * M * E
+    out.append({"kernel": "zg::conv_fwd_tok4_kernel<bf16> (causal conv1d + SiLU, rows gathered through the zigzag table)", "bound": "hbm", "ms_per_launch": ms,
+                "algorithmic_bytes": by, "achieved": by / ms / 1e6, "peak": hbm, "unit": "GB/s", "frac": by / ms / 1e6 / hbm})
+    del xz, xc
+    # block tail: x, mix (bf16) + residual (fp32) in; residual (fp32), normed, modded (bf16) out
+    x, mix = torch.randn(Bt, L, D, device=dev).to(dtype), torch.randn(Bt, L, D, device=dev).to(dtype)
+    mods, res, nw = torch.randn(Bt, 3 * D, device=dev).to(dtype), torch.randn(Bt, L, D, device=dev), torch.ones(D, device=dev, dtype=dtype)
+    ms = timeit(lambda: block_tail(x, mix, mods[:, :D], mods[:, D:2 * D], mods[:, 2 * D:], nw, res, rev, 1e-5))
+    by = M * D * (2 + 2 + 4 + 4 + 2 + 2)
+    out.append({"kernel": "zg::block_tail_row4_kernel<bf16> (gated residual + add + RMSNorm + modulate, un-permuting)", "bound": "hbm", "ms_per_launch": ms,
+                "algorithmic_bytes": by, "achieved": by / ms / 1e6, "peak": hbm, "unit": "GB/s", "frac": by / ms / 1e6 / hbm})
+    del x, mix, res
+    # the four projections of a layer
+    for pname, Nn, Kk, bound in (("in_proj", 2 * E, D, "tensor"), ("out_proj", D, E, "tensor"), ("x_proj", R + 2 * N, E, "hbm"), ("dt_proj", E, R, "hbm")):
+        Kp = (Kk + 7) // 8 * 8
+        a = torch.randn(M, Kp, device=dev).to(dtype)[:, :Kk]
+        w = (torch.randn(Nn, Kp, device=dev) / Kk ** 0.5).to(dtype)[:, :Kk]
+        c = torch.empty(M, Nn, device=dev, dtype=dtype)
+        ms = timeit(lambda: linear_bf16(a, w, out=c))
+        ms_lib = timeit(lambda: F.linear(a, w))
+        ent = {"kernel": f"zg::gemm_bf16_tn_kernel {pname} ({M} x {Nn} x {Kk})", "bound": bound, "ms_per_launch": ms, "library_ms_per_launch": ms_lib}
+        if bound == "tensor":
+            fl = 2.0 * M * Nn * Kk
+            ent.update({"algorithmic_flops": fl, "achieved": fl / ms / 1e9, "peak": tf_peak, "unit": "TFLOP/s", "frac": fl / ms / 1e9 / tf_peak})
+        else:
+            by = 2 * (M * Kk + Nn * Kk + M * Nn)
+            ent.update({"algorithmic_bytes": by, "achieved": by / ms / 1e6, "peak": hbm, "unit": "GB/s", "frac": by / ms / 1e6 / hbm})
+        out.append(ent)
+        del a, w, c
+    torch.cuda.empty_cache()
+    return out
+
+
 def run_workload(name, bs, K, W, dev, world, rank, use_graph=True, with_e2e=True):
     """Builds the model of workload `name`, times K Euler steps (one CUDA graph for the whole K-step loop), the end-to-end
     leg with host buffers, and returns the measurements.  Every rank calls this; collectives only when world > 1."""
@@ -469,6 +544,11 @@ def main():
 
     main_res = run_workload(name, bs, K, W, dev, world, rank, use_graph=not args.no_graph)
     roof = scan_roofline(name, bs, dev, main_res["ms_per_step"], wl["cfg"]["depth"]) if rank == 0 else None
+    if rank == 0 and name == DEFAULT and not args.no_configs:
+        try:        # the rest of a layer, each kernel against its own roofline (side information next to `roofline`)
+            roof["other_kernels"] = other_kernel_rooflines(name, bs, dev)
+        except Exception as ex:
+            roof["other_kernels"] = {"error": repr(ex)[:300]}
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -25,4 +25,7 @@ x = torch.randn(bs, L, D, device=dev).bfloat16(); mix = torch.randn(bs, L, D, de
 mods = torch.randn(bs, 3 * D, device=dev).bfloat16(); res = torch.randn(bs, L, D, device=dev); nw = torch.ones(D, device=dev).bfloat16()
 rev = torch.from_numpy(reverse_permut_np(zigzag_path(32)[1])).to(dev).to(torch.int32)
 t2 = timeit(lambda: block_tail(x, mix, mods[:, :D], mods[:, D:2*D], mods[:, 2*D:], nw, res, rev, 1e-5))
-print(f"ZG_CONV_VEC={os.environ.get('ZG_CONV_VEC','default(4)')}: conv {t*1e3:.1f} us ({2*2*bs*L*E/t/1e6:.0f} GB/s of 335 MB)   block_tail {t2*1e3:.1f} us ({bs*L*D*(2+2+4+4+2+2)/t2/1e6:.0f} GB/s of 671 MB)")
+if os.environ.get("CONV_SWEEP_JSON"):      # machine-readable line for scripts
+    import json
+    print(json.dumps({"conv_us": t * 1e3, "tail_us": t2 * 1e3, "smem": os.environ.get("ZG_CONV_SMEM", ""), "lch": os.environ.get("ZG_CONV_SMEM_LCH", "")}))
+print(f"ZG_CONV_SMEM={os.environ.get('ZG_CONV_SMEM','default')} LCH={os.environ.get('ZG_CONV_SMEM_LCH','default(32)')} ZG_CONV_VEC={os.environ.get('ZG_CONV_VEC','default(4)')}: conv {t*1e3:.1f} us ({2*2*bs*L*E/t/1e6:.0f} GB/s of 335 MB)   block_tail {t2*1e3:.1f} us ({bs*L*D*(2+2+4+4+2+2)/t2/1e6:.0f} GB/s of 671 MB)")

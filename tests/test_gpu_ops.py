@@ -567,6 +567,36 @@ def test_add_norm_backward_vs_autograd_oracle():
             check_close(b.grad, br.grad, "norm bwd dbias", atol=1e-4)
 
 
+@pytest.mark.parametrize("lch", ["16", "32", "64"])
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+def test_causal_conv1d_smem_staged_kernel_bit_identical(lch, dtype, monkeypatch):
+    """ZG_CONV_SMEM=1 (conv_fwd_tok8s_kernel: 8 channels per lane, rows staged through a per-lane cp.async ring) against the default
+    token-major kernel (conv_fwd_tok4_kernel, itself checked against the oracle above): same taps in the same order -> same bits.
+    Plain rows, rows gathered through a table, and independent segments (the temporal video layers)."""
+    from zigma_b200.causal_conv1d_interface import _conv_fwd
+    torch.manual_seed(5)
+    for Bt, L, E, seg in ((3, 128, 256, 0), (2, 192, 768, 0), (2, 256, 512, 16), (1, 64, 1280, 0)):
+        xz = torch.randn(Bt, L, 2 * E, device=DEV).to(dtype)
+        w, b = torch.randn(E, 4, device=DEV).to(dtype), torch.randn(E, device=DEV).to(dtype)
+        perm = torch.from_numpy(np.random.RandomState(7).permutation(L)).to(DEV).to(torch.int32)
+        for rowmap in (None, perm):
+            outs = []
+            for flag in ("0", "1"):
+                monkeypatch.setenv("ZG_CONV_SMEM", flag)
+                monkeypatch.setenv("ZG_CONV_SMEM_LCH", lch)
+                outs.append(_conv_fwd(xz[:, :, :E].transpose(1, 2), w, b, True, x_rowmap=rowmap, seg_len=seg).clone())
+            torch.cuda.synchronize()
+            assert torch.equal(outs[0], outs[1]), f"{dtype} lch {lch} {(Bt, L, E, seg)} rowmap {rowmap is not None}: max|diff| {(outs[0].float() - outs[1].float()).abs().max().item():.3e}"
+    # and against the oracle directly (fp32 math on the rounded inputs)
+    monkeypatch.setenv("ZG_CONV_SMEM", "1")
+    x = torch.randn(2, 512, 128, device=DEV).to(dtype)       # (B, E, L) logical, token-major memory
+    xt = x.transpose(1, 2).contiguous().transpose(1, 2)
+    w, b = torch.randn(512, 4, device=DEV).to(dtype), torch.randn(512, device=DEV).to(dtype)
+    got = _conv_fwd(xt, w, b, True)
+    ref = zo.causal_conv1d(x.float().cpu(), w.float().cpu(), b.float().cpu(), "silu")
+    check_close(got, ref, f"conv smem-staged kernel vs oracle {dtype}", rtol=8e-3, max_strict_viol=1.0)
+
+
 def test_block_tail_pos_embed_fold_matches_separate_add():
     """zg_block_tail_fwd_pe (first tail, positional embedding as a broadcast mix table, no gate) is bit-identical to the eager
     `tokens + pos_embed` (model_zigma.py:941) followed by the plain first tail, and agrees with the oracle's add + RMSNorm."""

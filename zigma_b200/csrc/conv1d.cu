@@ -131,6 +131,9 @@ template <typename T>
 #ifndef ZG_CONV_PREFETCH
 #define ZG_CONV_PREFETCH 0  // 1: software-pipelined row fetches (timing experiment, scripts/build_exp.sh)
 #endif
+#ifndef ZG_CONV_SMEM_DEFAULT
+#define ZG_CONV_SMEM_DEFAULT 0      // the cp.async-staged forward kernel is opt-in until measured faster
+#endif
 #ifndef ZG_CONV_RCP_FMA
 #define ZG_CONV_RCP_FMA 0
 #endif
@@ -261,6 +264,114 @@ __global__ void __launch_bounds__(128, ZG_CONV_MINB) conv_fwd_tok4_kernel(const 
         compute_batch(lb, raw);
     }
 #endif
+}
+
+// forward, token-major, rows staged through shared memory by cp.async (opt-in: ZG_CONV_SMEM=1).
+// Why: ncu of conv_fwd_tok4_kernel shows a latency-bound kernel (long_scoreboard 5.4 warps per issue at 0.69 of the HBM roofline): a
+// thread has its 8 rows x 8 bytes in flight only while it is NOT computing, and registers for a second batch cost more occupancy than
+// the prefetch hides (ZG_CONV_PREFETCH, rejected).  Here a lane owns 8 adjacent channels (16 bytes per row) and keeps TWO batches of 8
+// rows in flight in a per-lane shared-memory ring (3 batches x 8 rows x 16 B) while it computes the third: 128 KB in flight per SM with
+// 16 resident warps, no registers spent on data in flight.  Every lane reads back exactly the 16 bytes it copied itself, so its own
+// cp.async.wait_group is the only synchronisation (no barrier, no __syncwarp).  Same arithmetic and rounding as conv_fwd_tok4_kernel
+// (packed FFMA2 taps in the same order, the same SiLU): bit-identical results.
+constexpr int CS_ROWS = 8, CS_STAGES = 3, CS_WARPS = 4, CS_CH = 256;          // rows per batch, ring depth, warps per CTA, channels per warp
+constexpr int CS_WARP_BYTES = CS_STAGES * CS_ROWS * CS_CH * 2;                // 12 KB
+template <typename T, int LCH>
+__global__ void __launch_bounds__(32 * CS_WARPS, 4) conv_fwd_tok8s_kernel(const zg_conv_params p) {
+    static_assert(sizeof(T) == 2, "16-bit I/O");
+    static_assert(LCH % CS_ROWS == 0 && LCH / CS_ROWS >= 2, "whole batches");
+    extern __shared__ __align__(16) unsigned char conv_smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int E = p.dim, L = p.seqlen, W = p.width;
+    const int nv = E / CS_CH, nchunk = L / LCH;
+    const int64_t wid = (int64_t)blockIdx.x * CS_WARPS + warp;
+    if (wid >= (int64_t)p.batch * nchunk * nv) return;          // (no block-wide barrier anywhere below)
+    const int v = (int)(wid % nv);
+    const int ch = (int)((wid / nv) % nchunk);
+    const int b = (int)(wid / ((int64_t)nv * nchunk));
+    const int e0 = v * CS_CH + lane * 8;
+    const int l0 = ch * LCH;
+    const T *x = reinterpret_cast<const T *>(p.x) + (int64_t)b * p.x_sb + e0;
+    T *out = reinterpret_cast<T *>(p.out) + (int64_t)b * p.out_sb + e0 + (int64_t)l0 * p.out_sl;
+    const int xsl = (int)p.x_sl, osl = (int)p.out_sl;
+    unsigned char *ring = conv_smem + warp * CS_WARP_BYTES + lane * 16;      // this lane's 16 bytes of row r of batch slot s: + (s * CS_ROWS + r) * 512
+
+    zg_f2 w[4][4], bias[4];
+#pragma unroll
+    for (int h = 0; h < 4; ++h) {
+        bias[h].x = p.bias ? load_w_dt(p.bias, e0 + 2 * h, p.wdtype) : 0.f;
+        bias[h].y = p.bias ? load_w_dt(p.bias, e0 + 2 * h + 1, p.wdtype) : 0.f;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {   // w[k] multiplies x[l - k]  (weight index W-1-k)
+            w[k][h].x = (k < W) ? load_w_dt(p.weight, (int64_t)(e0 + 2 * h) * W + (W - 1 - k), p.wdtype) : 0.f;
+            w[k][h].y = (k < W) ? load_w_dt(p.weight, (int64_t)(e0 + 2 * h + 1) * W + (W - 1 - k), p.wdtype) : 0.f;
+        }
+    }
+    auto row_ptr = [&](int l) -> const unsigned char * {
+        const int row = p.x_rowmap ? p.x_rowmap[l] : l;
+        return reinterpret_cast<const unsigned char *>(x + row * xsl);
+    };
+    auto unpack = [](uint4 r, zg_f2 (&d)[4]) {
+        const unsigned rr[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+            if (std::is_same<T, __nv_bfloat16>::value) d[h] = make_float2(__uint_as_float(rr[h] << 16), __uint_as_float(rr[h] & 0xffff0000u));
+            else d[h] = __half22float2(*reinterpret_cast<const __half2 *>(&rr[h]));
+        }
+    };
+    constexpr int NB = LCH / CS_ROWS;
+    auto issue = [&](int k) {           // the 8 rows of batch k -> ring slot k % CS_STAGES, one commit group
+        unsigned char *dst = ring + (k % CS_STAGES) * (CS_ROWS * CS_CH * 2);
+#pragma unroll
+        for (int j = 0; j < CS_ROWS; ++j) zg_cp_async16(dst + j * (CS_CH * 2), row_ptr(l0 + k * CS_ROWS + j));
+        zg_cp_async_commit();
+    };
+    issue(0);
+    issue(1);
+    zg_f2 x1[4], x2[4], x3[4];
+    const int seg = p.seg_len;      // 0, or a multiple of CS_ROWS: independent segments (no taps across a segment start)
+    {
+        const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+        const int hist = seg > 0 ? (l0 % seg) : l0;      // positions of this segment before l0
+        unpack(hist >= 1 ? *reinterpret_cast<const uint4 *>(row_ptr(l0 - 1)) : zero, x1);
+        unpack(hist >= 2 ? *reinterpret_cast<const uint4 *>(row_ptr(l0 - 2)) : zero, x2);
+        unpack(hist >= 3 ? *reinterpret_cast<const uint4 *>(row_ptr(l0 - 3)) : zero, x3);
+    }
+#pragma unroll 1
+    for (int k = 0; k < NB; ++k) {
+        if (k + 2 < NB) issue(k + 2);           // slot (k - 1) % 3: its rows were consumed (and stored) in the previous iteration
+        else zg_cp_async_commit();              // empty group: the wait below always leaves exactly two groups pending
+        zg_cp_async_wait<2>();                  // this lane's copies of batch k have landed
+        const int lb = k * CS_ROWS;
+        if (seg > 0 && lb > 0 && ((l0 + lb) % seg) == 0) {      // a new segment starts with this batch of rows: zero history
+#pragma unroll
+            for (int h = 0; h < 4; ++h) x1[h] = x2[h] = x3[h] = make_float2(0.f, 0.f);
+        }
+        const unsigned char *src = ring + (k % CS_STAGES) * (CS_ROWS * CS_CH * 2);
+#pragma unroll
+        for (int j = 0; j < CS_ROWS; ++j) {
+            zg_f2 x0[4];
+            unpack(*reinterpret_cast<const uint4 *>(src + j * (CS_CH * 2)), x0);
+            unsigned o[4];
+#pragma unroll
+            for (int h = 0; h < 4; ++h) {
+                zg_f2 acc = zg_fma2(w[3][h], x3[h], bias[h]);
+                acc = zg_fma2(w[2][h], x2[h], acc);
+                acc = zg_fma2(w[1][h], x1[h], acc);
+                acc = zg_fma2(w[0][h], x0[h], acc);
+                if (p.silu) { acc.x = zg_silu(acc.x); acc.y = zg_silu(acc.y); }
+                x3[h] = x2[h]; x2[h] = x1[h]; x1[h] = x0[h];
+                if (std::is_same<T, __nv_bfloat16>::value) {
+                    __nv_bfloat162 t = __floats2bfloat162_rn(acc.x, acc.y);
+                    o[h] = *reinterpret_cast<unsigned *>(&t);
+                } else {
+                    __half2 t = __floats2half2_rn(acc.x, acc.y);
+                    o[h] = *reinterpret_cast<unsigned *>(&t);
+                }
+            }
+            *reinterpret_cast<uint4 *>(out + (lb + j) * osl) = make_uint4(o[0], o[1], o[2], o[3]);
+        }
+    }
 }
 
 // forward, seq-contiguous
@@ -759,6 +870,21 @@ template <typename T> static int conv_fwd_t(const zg_conv_params &p, bool seq, c
             const bool fast = (dv_env == 0 || p.seg_len > 0) && (p.seg_len % CONV_RB == 0) && (p.seg_len == 0 || p.seqlen % p.seg_len == 0) && (p.dim % 4 == 0) && (align_bits % 8 == 0) && (p.x_sb % 4 == 0) && (p.x_sl % 4 == 0) &&
                               (p.out_sb % 4 == 0) && (p.out_sl % 4 == 0) && (p.seqlen % CONV_LCH == 0) &&
                               ((int64_t)p.seqlen * p.x_sl < 0x7fffffffLL) && ((int64_t)p.seqlen * p.out_sl < 0x7fffffffLL);
+            // ZG_CONV_SMEM=1: the cp.async-staged kernel (8 channels per lane) where the shape allows; ZG_CONV_SMEM_LCH = 16 | 32 | 64 tokens
+            // per warp (read per call, like ZG_SCAN_WP, so that a test can compare both kernels in one process)
+            const char *smem_e = getenv("ZG_CONV_SMEM"), *smem_l = getenv("ZG_CONV_SMEM_LCH");
+            const int smem_env = smem_e ? atoi(smem_e) : ZG_CONV_SMEM_DEFAULT, smem_lch = smem_l ? atoi(smem_l) : 32;
+            if (fast && smem_env == 1 && (smem_lch == 16 || smem_lch == 32 || smem_lch == 64) && (p.dim % CS_CH == 0) && (align_bits % 16 == 0) && (p.x_sb % 8 == 0) &&
+                (p.x_sl % 8 == 0) && (p.out_sb % 8 == 0) && (p.out_sl % 8 == 0) && (p.seqlen % smem_lch == 0)) {
+                const int64_t nwarp = (int64_t)p.batch * (p.seqlen / smem_lch) * (p.dim / CS_CH);
+                const unsigned grid = (unsigned)((nwarp + CS_WARPS - 1) / CS_WARPS);
+                constexpr int SMEM = CS_WARPS * CS_WARP_BYTES;      // 48 KB: the default dynamic limit, no attribute needed
+                if (smem_lch == 16) conv_fwd_tok8s_kernel<T, 16><<<grid, 32 * CS_WARPS, SMEM, s>>>(p);
+                else if (smem_lch == 32) conv_fwd_tok8s_kernel<T, 32><<<grid, 32 * CS_WARPS, SMEM, s>>>(p);
+                else conv_fwd_tok8s_kernel<T, 64><<<grid, 32 * CS_WARPS, SMEM, s>>>(p);
+                zg_count_launch();
+                return zg_check_launch("causal_conv1d_fwd(smem)");
+            }
             if (fast) {
                 const int64_t n = (int64_t)p.batch * (p.seqlen / CONV_LCH) * (p.dim / 4);
                 conv_fwd_tok4_kernel<T><<<(unsigned)((n + 127) / 128), 128, 0, s>>>(p);
