@@ -544,16 +544,16 @@ def main():
 
     main_res = run_workload(name, bs, K, W, dev, world, rank, use_graph=not args.no_graph)
     roof = scan_roofline(name, bs, dev, main_res["ms_per_step"], wl["cfg"]["depth"]) if rank == 0 else None
-    if rank == 0 and name == DEFAULT and not args.no_configs:
-        try:        # the rest of a layer, each kernel against its own roofline (side information next to `roofline`)
-            roof["other_kernels"] = other_kernel_rooflines(name, bs, dev)
-        except Exception as ex:
-            roof["other_kernels"] = {"error": repr(ex)[:300]}
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     if rank != 0:
         return
+    if name == DEFAULT and not args.no_configs:
+        try:        # the rest of a layer, each kernel against its own roofline (side information next to `roofline`; rank 0 alone, after the job)
+            roof["other_kernels"] = other_kernel_rooflines(name, bs, dev)
+        except Exception as ex:
+            roof["other_kernels"] = {"error": repr(ex)[:300]}
 
     ms, per_eval = main_res["ms"], main_res["per_eval"]
     line = {
