@@ -59,6 +59,31 @@ def test_reference_constructor_init_properties():
     assert m.pos_embed.abs().sum() > 0 and not m.pos_embed.requires_grad
 
 
+def test_embed_without_pos_embed_is_the_hand_off_of_the_folded_first_tail():
+    """ZigMa.embed(add_pos=False) returns the tokens BEFORE `x = x + self.pos_embed` (model_zigma.py:941): the sampling engine adds the
+    table inside its first fused tail (zg_block_tail_fwd_pe).  Everything else -- conditioning, the temporal embedding of video
+    models -- is unchanged, and the default still includes the table."""
+    from zigma_b200 import ZigMa
+    torch.manual_seed(0)
+    for cfg in (dict(in_channels=4, embed_dim=32, depth=2, img_dim=8, scan_type="zigzagN8", use_pe=2),
+                dict(in_channels=4, embed_dim=32, depth=3, img_dim=8, patch_size=2, scan_type="zzvideo_sst", use_pe=2, video_frames=4, num_classes=5)):
+        m = ZigMa(device="cpu", **cfg).eval()
+        with torch.no_grad():
+            m.pos_embed.normal_(0, 0.5)
+        video = cfg.get("video_frames", 0) > 0
+        x = torch.randn(2, 4, 4, 8, 8) if video else torch.randn(2, 4, 8, 8)
+        t = torch.tensor([0.1, 0.7])
+        y = torch.tensor([1, 3]) if cfg.get("num_classes", -1) > 0 else None
+        with torch.no_grad():
+            full, c1, _ = m.embed(x, t, y)
+            bare, c2, _ = m.embed(x, t, y, add_pos=False)
+        assert torch.equal(c1, c2)
+        assert m.pos_embed.shape[1] == full.shape[1]            # one row per token: the (seqlen, dim) table of the fold
+        if not (video and m.tpe):
+            assert torch.allclose(bare + m.pos_embed, full, atol=1e-6)
+        assert not torch.allclose(bare, full)
+
+
 def test_sampler_euler_matches_oracle_and_reference_grid():
     from zigma_b200 import create_transport, Sampler
     tr = create_transport("Linear", "velocity", None, None, None)
