@@ -84,6 +84,32 @@ def test_embed_without_pos_embed_is_the_hand_off_of_the_folded_first_tail():
         assert not torch.allclose(bare, full)
 
 
+def test_temporal_composite_row_tables_are_the_reference_rearrange_plus_permutation():
+    """engine._temporal_tables: the copy-free temporal layer addresses the (b, t k) token-major rows through ONE int32 table per
+    direction.  In: position k T + t of the (b k) t working order reads model row perm[t] K + k -- the reference's
+    `rearrange(x, "b (t k) d -> (b k) t d")` followed by the gather along t (mamba_simple.py:416-425); out: model row t K + k
+    takes working row k T + perm_rev[t] (:436-442).  Pure index arithmetic, checked against the rearranged tensors."""
+    import types
+    from zigma_b200.engine import ZigMaEngine
+    T, K, D = 8, 6, 3
+    rng = np.random.RandomState(1)
+    perm = torch.from_numpy(rng.permutation(T))
+    rev = torch.empty_like(perm)
+    rev[perm] = torch.arange(T)
+    lay = {"perm64": perm, "perm_rev64": rev}
+    stub = types.SimpleNamespace(_rev_cache={})
+    tb = ZigMaEngine._temporal_tables(stub, lay, T, K, "cpu")
+    assert tb["in"].dtype == torch.int32 and tb["out"].dtype == torch.int32 and tb["in"].numel() == T * K
+    x = torch.randn(T * K, D)                                        # rows in (t, k) order
+    work = x.view(T, K, D).permute(1, 0, 2)[:, perm].reshape(T * K, D)   # (k, t) order, every sequence permuted along t
+    assert torch.equal(x[tb["in"].long()], work)
+    y = torch.randn(K * T, D)                                        # a layer output in the working order
+    back = y.view(K, T, D)[:, rev].permute(1, 0, 2).reshape(T * K, D)
+    assert torch.equal(y[tb["out"].long()], back)
+    assert torch.equal(x[tb["in"].long()][tb["out"].long()], x)      # the two tables are inverse of each other
+    assert ZigMaEngine._temporal_tables(stub, lay, T, K, "cpu") is tb  # cached per (layer, T, K)
+
+
 def test_sampler_euler_matches_oracle_and_reference_grid():
     from zigma_b200 import create_transport, Sampler
     tr = create_transport("Linear", "velocity", None, None, None)
